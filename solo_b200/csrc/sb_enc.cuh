@@ -1,0 +1,235 @@
+// solo_b200 -- one SOLO packet (40 ms, 16 kHz) through the encoder: QMF split, two SILK frames with the
+// MD noise-shaping quantiser, two high-band frames, payload assembly [MD1 | MD2 | HB].
+// Reference: /root/reference/JC1_SDK_SRC_ARM/src/libBWE/AGR_BWE_encode_frame_FIX.c:8-174, AGR_BWE_qmf.c:38-80,
+// AGR_BWE_find_HB_LPC_FIX.c:4-49, AGR_BWE_quant_highband.c:23-147, AGR_BWE_SDK_API.c:11-152,
+// libSATECodec/SKP_Silk_enc_API.c:127-273, SKP_Silk_encode_frame_FIX.c:34-327, SKP_Silk_control_codec_FIX.c:232-389.
+#pragma once
+#include "sb_enc_entropy.cuh"
+#include "sb_enc_front.cuh"
+#include "sb_enc_pred.cuh"
+#include "sb_enc_shape.cuh"
+#include "sb_nsq.cuh"
+
+namespace sb {
+
+// ---- Init: AGR_Sate_Encoder_Init + SKP_Silk_init_encoder_FIX + first SKP_Silk_control_encoder_FIX --------------
+// Returns 0, or -1 for a configuration the reference rejects / this build does not cover.
+SB_FN int enc_state_init(EncState* st, i32 targetRate_bps, i32 dtx_enable, i32 useMDIndex) {
+    memset(st, 0, sizeof(EncState));
+    if (targetRate_bps <= 0) targetRate_bps = 15600;
+    i32 silk_rate = targetRate_bps - 1600;  // bwe_framesize 20 ms (AGR_BWE_SDK_API.c:118)
+    silk_rate = limit(silk_rate, 5000, 100000);
+    st->targetRate_bps = silk_rate;
+    st->useDTX = dtx_enable ? 1 : 0;
+    st->useMDIndex = useMDIndex;
+    st->variable_HP_smth1_Q15 = 200844;
+    st->variable_HP_smth2_Q15 = 200844;
+    st->first_frame_after_reset = 1;
+    vad_init(&st->vad);
+    for (int i = 0; i < 3; i++) st->nsq[i].prev_inv_gain_Q16 = 65536;
+    // setup_fs (control_codec_FIX.c:232-317): only the centre NSQ gets lagPrev = 100 (App. A Q5)
+    st->prevLag = 100;
+    st->prev_sigtype = 1;
+    st->pf_lagPrev = 100;
+    st->LastGainIndex = 1;
+    st->nsq[0].lagPrev = 100;
+    // setup_rate (control_codec_FIX.c:319-389)
+    const i32* rt = SB_T(target_rate_table_nb);
+    const i32* snr = SB_T(snr_table_q1);
+    i32 md_rate = silk_rate / 2;
+    for (int k = 1; k < 8; k++) {
+        if (md_rate < rt[k]) {
+            i32 frac_Q6 = shl(md_rate - rt[k - 1], 6) / (rt[k] - rt[k - 1]);
+            st->SNRPerMD_dB_Q7 = shl(snr[k - 1], 6) + mulw(frac_Q6, snr[k] - snr[k - 1]);
+            break;
+        }
+    }
+    for (int k = 1; k < 8; k++) {
+        if (silk_rate <= rt[k]) {
+            i32 frac_Q6 = shl(silk_rate - rt[k - 1], 6) / (rt[k] - rt[k - 1]);
+            st->SNR_dB_Q7 = shl(snr[k - 1], 6) + mulw(frac_Q6, snr[k] - snr[k - 1]);
+            break;
+        }
+    }
+    st->hb_first = 1;
+    return 0;
+}
+
+// ---- AGR_Sate_qmf_decomp (AGR_BWE_qmf.c:38-80), N = 640, M = 64, fixed point ------------------------------------
+SB_FN void qmf_decomp(const i16* xx, i16* y1, i16* y2, i16* mem) {
+    enum { N = PACKET, M = 64 };
+    i16 x[N + M - 1];
+    const i16* aa = SB_T(qmf_fix);
+    for (int i = 0; i < M - 1; i++) x[i] = mem[M - i - 2];
+    for (int i = 0; i < N; i++) x[i + M - 1] = (i16)(xx[i] >> 1);
+    for (int i = 0; i < M - 1; i++) mem[i] = (i16)(xx[N - i - 1] >> 1);
+    const i16* x2 = x + M - 1;
+    for (int i = 0, k = 0; i < N; i += 2, k++) {
+        i32 y1k = 0, y2k = 0;
+        for (int j = 0; j < M / 2; j += 2) {
+            i32 a0 = aa[M - j - 1], a1 = aa[M - j - 2];
+            i32 s0 = (i16)(x[i + j] + x2[i - j]), d0 = (i16)(x[i + j] - x2[i - j]);
+            i32 s1 = (i16)(x[i + j + 1] + x2[i - j - 1]), d1 = (i16)(x[i + j + 1] - x2[i - j - 1]);
+            y1k = addw(y1k, a0 * s0);
+            y2k = subw(y2k, a0 * d0);
+            y1k = addw(y1k, a1 * s1);
+            y2k = addw(y2k, a1 * d1);
+        }
+        i32 v1 = addw(y1k, 16384) >> 15, v2 = addw(y2k, 16384) >> 15;
+        y1[k] = (i16)(v1 > 32767 ? 32767 : (v1 < -32767 ? -32767 : v1));
+        y2[k] = (i16)(v2 > 32767 ? 32767 : (v2 < -32767 ? -32767 : v2));
+    }
+}
+
+// ---- AGR_Sate_lsp_quant_highband (AGR_BWE_quant_highband.c:23-104) ----------------------------------------------
+SB_FN i32 hb_lsp_quant(i32* lsp) {
+    i32 weight[HB_ORDER];
+    nlsf_vq_weights_laroia(weight, lsp, HB_ORDER);
+    const i16* cb1 = SB_T(hb_lsp_cb1_fix);
+    const i16* cb2 = SB_T(hb_lsp_cb2_fix);
+    i32 min_dist = SB_I32_MAX; int idx1 = 0;
+    for (int i = 0; i < 256; i++) {
+        i32 dist = 0;
+        for (int j = 0; j < HB_ORDER; j++) { i32 t = lsp[j] - cb1[i * HB_ORDER + j]; dist = smlabb(dist, t, t); }
+        if (dist < min_dist) { min_dist = dist; idx1 = i; }
+    }
+    for (int i = 0; i < HB_ORDER; i++) lsp[i] -= cb1[idx1 * HB_ORDER + i];
+    i32 best = SB_I32_MAX; int idx2 = 0;
+    for (int i = 0; i < 16; i++) {
+        i32 dist = 0;
+        for (int j = 0; j < HB_ORDER; j++) { i32 t = subw(lsp[j], cb2[i * HB_ORDER + j]); dist = smlawb(dist, smulbb(t, t), weight[j]); }
+        if (dist < best) { best = dist; idx2 = i; }
+    }
+    for (int i = 0; i < HB_ORDER; i++) lsp[i] = (i32)cb1[idx1 * HB_ORDER + i] + (i32)cb2[idx2 * HB_ORDER + i];
+    return shl(idx2, 8) + idx1;
+}
+
+// ---- AGR_Bwe_encode_frame_FIX (AGR_BWE_encode_frame_FIX.c:8-82): one 20 ms high-band frame -> 4 bytes ----------
+SB_FN void hb_encode_frame(EncState* st, const i16* high, const i32* residue, u8* out4) {
+    const int LPCF = 80;
+    for (int i = 0; i < HB_FRAME; i++) st->x_hb_buf[HB_FRAME + 40 + i] = high[i];
+    // AGR_Sate_find_HB_LPC_FIX: 4 blocks of (80 + 8) samples, hop 80, starting 8 samples before the frame
+    i16 LPC_in_pre[4 * (LPCF + HB_ORDER)];
+    {
+        const i16* xp = st->x_hb_buf + HB_FRAME - HB_ORDER;
+        i16* d = LPC_in_pre;
+        for (int k = 0; k < 4; k++) {
+            for (int i = 0; i < LPCF + HB_ORDER; i++) d[i] = xp[i];
+            d += LPCF + HB_ORDER;
+            xp += LPCF;
+        }
+    }
+    i32 NLSF_Q15[HB_ORDER], interp, prev_dummy[HB_ORDER];
+    for (int i = 0; i < HB_ORDER; i++) prev_dummy[i] = 0;
+    find_lpc(NLSF_Q15, &interp, prev_dummy, 0, HB_ORDER, LPC_in_pre, LPCF + HB_ORDER);
+    i32 lsp_idx = hb_lsp_quant(NLSF_Q15);
+    i16 coef[HB_ORDER], exc[SUBFR];
+    nlsf2a_stable(coef, NLSF_Q15, HB_ORDER);
+    i32 gain_idx[4];
+    const i16* p_hb = st->x_hb_buf + HB_FRAME;
+    for (int sub = 0; sub < 4; sub++) {
+        lpc_analysis_filter_zero_state(p_hb, coef, exc, SUBFR, HB_ORDER);
+        i32 nrg0 = 0, nrg1 = 0;
+        for (int i = 0; i < SUBFR; i++) {
+            nrg0 = addw(nrg0, (i32)exc[i] * (i32)exc[i]);
+            i32 tmp = residue[sub * SUBFR + i] >> 10;
+            nrg1 = smlabb(nrg1, tmp, tmp);
+        }
+        nrg0 = sqrt_approx(nrg0);
+        nrg1 = sqrt_approx(nrg1);
+        i16 gain = (i16)(shl(nrg0 + 1, 4) / (nrg1 + 1));
+        i32 md = SB_I32_MAX; int gi = 0;
+        for (int i = 0; i < 32; i++) {
+            i16 t = (i16)(gain - SB_T(hb_gain_cb_fix)[i]);
+            i32 dist = smulbb(t, t);
+            if (dist < md) { md = dist; gi = i; }
+        }
+        gain_idx[sub] = gi;
+        p_hb += SUBFR;
+    }
+    // 12 + 4*5 bits, MSB first (AGR_BWE_bits.c:77-117)
+    u32 w = ((u32)lsp_idx & 0xFFF) << 20 | ((u32)gain_idx[0] << 15) | ((u32)gain_idx[1] << 10) | ((u32)gain_idx[2] << 5) | (u32)gain_idx[3];
+    out4[0] = (u8)(w >> 24); out4[1] = (u8)(w >> 16); out4[2] = (u8)(w >> 8); out4[3] = (u8)w;
+    for (int i = 0; i < HB_FRAME + 40; i++) st->x_hb_buf[i] = st->x_hb_buf[HB_FRAME + i];
+    st->hb_first = 0;
+}
+
+// ---- SKP_Silk_encode_frame_FIX (encode_frame_FIX.c:34-327), one 20 ms frame of the low band ------------------------
+struct EncFrameWork {
+    EncCtrl c;
+    NsqWork nsq;
+    i16 xfw[FRAME];
+    i16 pIn_HP[FRAME];
+    i16 res_pitch[2 * FRAME + LA_PITCH];
+    i8 q_md[2][FRAME];
+};
+
+SB_FN void encode_frame(EncState* st, EncFrameWork* W, const i16* pIn, int frame_in_packet, RangeEnc* rc, i32* r_out) {
+    EncCtrl* c = &W->c;
+    c->Seed = st->frameCounter++ & 3;
+    i16* x_frame = st->x_buf + FRAME;
+    vad_get_sa_q8(&st->vad, &st->speech_activity_Q8, c->input_quality_bands_Q15, &c->input_tilt_Q15, pIn);
+    hp_variable_cutoff(st, c, W->pIn_HP, pIn);
+    for (int i = 0; i < FRAME; i++) x_frame[LA_SHAPE + i] = W->pIn_HP[i];  // LP_variable_cutoff is a copy (transition_frame_no == 0)
+    find_pitch_lags(st, c, W->res_pitch, x_frame);
+    noise_shape_analysis(st, c, W->res_pitch + FRAME, x_frame);
+    prefilter(st, c, W->xfw, x_frame);
+    find_pred_coefs(st, c, W->res_pitch, frame_in_packet);
+    process_gains(st, c, frame_in_packet);
+    nsq_del_dec(st, c, &W->nsq, W->xfw, (i8*)0, W->q_md[0], W->q_md[1], r_out);
+    if (st->speech_activity_Q8 < SB_FIXC(0.1f, 8)) {
+        st->vadFlag = 0;
+        st->noSpeechCounter++;
+        if (st->noSpeechCounter > 5) st->inDTX = 1;
+        if (st->noSpeechCounter > 20 + 5) { st->noSpeechCounter = 5; st->inDTX = 0; }
+    } else {
+        st->noSpeechCounter = 0; st->inDTX = 0; st->vadFlag = 1;
+    }
+    for (int k = 0; k < 2; k++) encode_parameters(&rc[k], st, c, k, frame_in_packet, st->vadFlag, W->q_md[k]);
+    for (int i = 0; i < FRAME + LA_SHAPE; i++) st->x_buf[i] = st->x_buf[FRAME + i];
+    st->prev_sigtype = c->sigtype;
+    st->prevLag = c->pitchL[NB_SUBFR - 1];
+    st->first_frame_after_reset = 0;
+    // frame terminator: MORE_FRAMES (1) after the first frame, LAST_FRAME (0) after the second
+    for (int k = 0; k < 2; k++) rc_encode(&rc[k], frame_in_packet == 0 ? 1 : 0, SB_T(frame_term_cdf));
+}
+
+// ---- AGR_Sate_Encoder_Encode: returns the byte count; nBytesOut[0] = total, nBytesOut[1] = len(MD2) + 8 -------------
+struct EncPacketWork {
+    EncFrameWork f;
+    i16 low[PACKET / 2], high[PACKET / 2];
+    i32 res_Q10[PACKET / 2];
+    u8 rcbuf[2][MAX_PAYLOAD];
+};
+
+SB_FN i32 enc_packet(EncState* st, EncPacketWork* W, const i16* pcm, u8* out, i32 out_cap, i16* nBytesOut) {
+    qmf_decomp(pcm, W->low, W->high, st->qmf_mem);
+    RangeEnc rc[2];
+    rc_enc_init(&rc[0], W->rcbuf[0], MAX_PAYLOAD);
+    rc_enc_init(&rc[1], W->rcbuf[1], MAX_PAYLOAD);
+    for (int f = 0; f < 2; f++) encode_frame(st, &W->f, W->low + f * FRAME, f, rc, W->res_Q10 + f * FRAME);
+    int nb[2];
+    rc_get_length(&rc[0], &nb[0]);
+    rc_get_length(&rc[1], &nb[1]);
+    int silk_ok = (nb[0] + nb[1] <= MAX_PAYLOAD) && !rc[0].error && !rc[1].error;
+    if (silk_ok) { rc_enc_wrap_up(&rc[0]); rc_enc_wrap_up(&rc[1]); }
+    else { nb[0] = nb[1] = 0; }
+    if (st->useDTX && st->inDTX) { nb[0] = nb[1] = 0; }
+    u8 hb[8];
+    for (int f = 0; f < 2; f++) hb_encode_frame(st, W->high + f * HB_FRAME, W->res_Q10 + f * HB_FRAME, hb + 4 * f);
+    int lb = nb[0] + nb[1];
+    int total = lb + 8;
+    int n = imin(out_cap, total);
+    for (int i = 0; i < n; i++) {
+        u8 v;
+        if (i < nb[0]) v = W->rcbuf[0][i];
+        else if (i < lb) v = W->rcbuf[1][i - nb[0]];
+        else v = hb[i - lb];
+        out[i] = v;
+    }
+    if (lb) { nBytesOut[0] = (i16)total; nBytesOut[1] = (i16)(nb[1] + 8); }
+    else { nBytesOut[0] = 0; nBytesOut[1] = 0; }
+    return n;
+}
+
+}  // namespace sb
