@@ -1,0 +1,66 @@
+/*
+ * solo_b200 -- batched extension of the SOLO SDK ABI (plain C, no CUDA or torch types in the signatures).
+ *
+ * One batch object owns N independent codec streams whose state stays resident in GPU memory between
+ * calls; one call advances every stream by one 40 ms packet.  Semantics per stream are exactly those of
+ * AGR_Sate_Encoder_Encode / AGR_Sate_Decoder_Decode (AGR_JC1_SDK_API.h; reference
+ * /root/reference/JC1_SDK_SRC_ARM/src/libBWE/AGR_BWE_SDK_API.c:129-152, JC1_SDK_SRC_FLP/.../AGR_BWE_SDK_API.c:249-279).
+ *
+ * Two flavours of every call:
+ *   *_host    : buffers are host memory (pinned or pageable); host<->device copies happen inside the call
+ *   *_device  : buffers are device pointers; the call only enqueues kernels on `cuda_stream`
+ *               (a cudaStream_t passed as void*; NULL = legacy default stream) and does not synchronise.
+ *
+ * Layouts (row = stream):  pcm  int16 [N][640]        bits uint8 [N][cap]
+ *                          nbytes int16 [N][2]        ({total, len(MD2)+8} as the single-stream API)
+ *                          lostflag int32 [N]         (1 lost, 2 MD1 only, 3 MD2+HB only, 4 both)
+ * For decode, row i of `bits` holds the payload exactly as the caller would hand it to
+ * AGR_Sate_Decoder_Decode (already trimmed for lostflag 2 / 3) and nbytes[i] the matching {n0, n1};
+ * nbytes is NOT modified (the single-stream call rewrites its nBytes[]).
+ * ret[i] receives the per-stream return code of the reference call (0 ok, negative SILK error codes).
+ *
+ * All functions return 0 on success, a negative value on error (-1 bad argument, -2 CUDA failure;
+ * solo_b200_last_error() gives a text).  A missing GPU is an error: there is no CPU fallback.
+ */
+#ifndef SOLO_B200_H
+#define SOLO_B200_H
+
+#include <stdint.h>
+#include "AGR_JC1_SDK_API.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct solo_b200_enc_batch solo_b200_enc_batch;
+typedef struct solo_b200_dec_batch solo_b200_dec_batch;
+
+/* device = CUDA device ordinal; ctrl is applied to every stream (same checks as AGR_Sate_Encoder_Init). */
+solo_b200_enc_batch *solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_enc *ctrl, int device);
+int solo_b200_enc_batch_encode_host(solo_b200_enc_batch *b, const int16_t *pcm, uint8_t *bits, int cap, int16_t *nbytes);
+int solo_b200_enc_batch_encode_device(solo_b200_enc_batch *b, const int16_t *d_pcm, uint8_t *d_bits, int cap,
+                                      int16_t *d_nbytes, void *cuda_stream);
+void solo_b200_enc_batch_destroy(solo_b200_enc_batch *b);
+
+solo_b200_dec_batch *solo_b200_dec_batch_create(int n_streams, const USER_Ctrl_dec *ctrl, int device);
+int solo_b200_dec_batch_decode_host(solo_b200_dec_batch *b, int16_t *pcm, const uint8_t *bits, int cap,
+                                    const int16_t *nbytes, const int32_t *lostflag, int32_t *ret);
+int solo_b200_dec_batch_decode_device(solo_b200_dec_batch *b, int16_t *d_pcm, const uint8_t *d_bits, int cap,
+                                      const int16_t *d_nbytes, const int32_t *d_lostflag, int32_t *d_ret, void *cuda_stream);
+void solo_b200_dec_batch_destroy(solo_b200_dec_batch *b);
+
+/* Bytes of device state held per stream (encoder / decoder). */
+int solo_b200_enc_state_bytes(void);
+int solo_b200_dec_state_bytes(void);
+/* Number of kernels this library has launched in this process (for benchmark bookkeeping). */
+long long solo_b200_kernel_launches(void);
+/* Average duration in ms of the encode / decode kernel over the launches since the last reset, measured with
+   CUDA events recorded on the launching stream (only while profiling is enabled). */
+void solo_b200_profile_enable(int on);
+int solo_b200_profile_read(double *enc_ms_total, long long *enc_launches, double *dec_ms_total, long long *dec_launches);
+const char *solo_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,391 @@
+// solo_b200 -- sm_100a kernels and the C ABI of libsolo_b200.so.
+//
+// Mapping (round 1): one codec stream per thread, 32 independent streams per warp.  Every heavy loop of
+// the codec (the 160-sample x 12-recurrence MD noise-shaping quantiser, the warped autocorrelations, the
+// codebook searches) has data-independent trip counts, so the 32 streams of a warp run them in lock-step
+// with full lane utilisation and no shuffles; per-thread scratch (`EncPacketWork`, ~35 KB) lives in local
+// memory, which the hardware interleaves per lane so that the warp's accesses to the same scratch element
+// coalesce.  Persistent per-stream state lives in a device arena (array of EncState / DecState) that never
+// leaves the GPU between packets.  See DESIGN.md for the measured consequences and the plan for the
+// warp-cooperative NSQ.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+
+#include "../../include/solo_b200.h"
+#include "sb_dec.cuh"
+#include "sb_enc.cuh"
+
+using namespace sb;
+
+// ---------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------
+#define SB_TPB 64
+
+__global__ void __launch_bounds__(SB_TPB) sb_enc_init_kernel(EncState* states, int n, int rate, int dtx, int mdi) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) enc_state_init(&states[s], rate, dtx, mdi);
+}
+
+__global__ void __launch_bounds__(SB_TPB) sb_encode_kernel(EncState* states, const i16* __restrict__ pcm, u8* __restrict__ bits, int cap,
+                                                           i16* __restrict__ nbytes, int n) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    EncPacketWork W;
+    i16 x[PACKET];
+    // 128-bit loads of this stream's 1280-byte PCM row
+    const int4* src = reinterpret_cast<const int4*>(pcm + (size_t)s * PACKET);
+    int4* dst = reinterpret_cast<int4*>(x);
+#pragma unroll 4
+    for (int i = 0; i < PACKET * 2 / 16; i++) dst[i] = src[i];
+    i16 nb[2];
+    enc_packet(&states[s], &W, x, bits + (size_t)s * cap, cap, nb);
+    nbytes[2 * s] = nb[0];
+    nbytes[2 * s + 1] = nb[1];
+}
+
+__global__ void __launch_bounds__(SB_TPB) sb_dec_init_kernel(DecState* states, int n, int mdi) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) dec_state_init(&states[s], mdi);
+}
+
+__global__ void __launch_bounds__(SB_TPB) sb_decode_kernel(DecState* states, i16* __restrict__ pcm, const u8* __restrict__ bits, int cap,
+                                                           const i16* __restrict__ nbytes, const i32* __restrict__ lostflag,
+                                                           i32* __restrict__ ret, int n) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    DecPacketWork W;
+    i16 nb[2] = {nbytes[2 * s], nbytes[2 * s + 1]};
+    i16 out[PACKET];
+    i32 r = dec_packet(&states[s], &W, out, bits + (size_t)s * cap, cap, nb, lostflag[s]);
+    int4* dst = reinterpret_cast<int4*>(pcm + (size_t)s * PACKET);
+    const int4* src = reinterpret_cast<const int4*>(out);
+#pragma unroll 4
+    for (int i = 0; i < PACKET * 2 / 16; i++) dst[i] = src[i];
+    if (ret) ret[s] = r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[256] = "";
+static std::mutex g_mu;
+static long long g_launches = 0;
+static int g_profile = 0;
+struct EvPair { cudaEvent_t a, b; int kind; };
+static std::vector<EvPair> g_events;
+
+static int fail(const char* what, cudaError_t e) {
+    snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+    return -2;
+}
+#define CK(call)                                  \
+    do {                                          \
+        cudaError_t e_ = (call);                  \
+        if (e_ != cudaSuccess) return fail(#call, e_); \
+    } while (0)
+
+static void prof_begin(cudaStream_t st, int kind, EvPair* p) {
+    p->kind = -1;
+    if (!g_profile) return;
+    if (cudaEventCreate(&p->a) != cudaSuccess || cudaEventCreate(&p->b) != cudaSuccess) return;
+    p->kind = kind;
+    cudaEventRecord(p->a, st);
+}
+static void prof_end(cudaStream_t st, EvPair* p) {
+    if (p->kind < 0) return;
+    cudaEventRecord(p->b, st);
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_events.push_back(*p);
+}
+static void count_launch() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_launches++;
+}
+
+struct solo_b200_enc_batch {
+    int n, device;
+    EncState* d_states;
+    // staging for the *_host entry points
+    i16* d_pcm; u8* d_bits; i16* d_nbytes; int bits_cap;
+    cudaStream_t stream;
+};
+struct solo_b200_dec_batch {
+    int n, device;
+    DecState* d_states;
+    i16* d_pcm; u8* d_bits; i16* d_nbytes; i32* d_flags; i32* d_ret; int bits_cap;
+    cudaStream_t stream;
+};
+
+static int check_enc_ctrl(const USER_Ctrl_enc* c) {
+    if (!c) return -1;
+    if (c->samplerate != 16000 || c->framesize_ms != 40) return -1;
+    if (c->joint_enable) return -1;  // joint modes: "Unsupport" / 40 ms HB frame (AGR_BWE_SDK_API.c:56-81), out of scope
+    return 0;
+}
+static int check_dec_ctrl(const USER_Ctrl_dec* c) {
+    if (!c) return -1;
+    if (c->samplerate != 16000 || c->framesize_ms != 40) return -1;
+    if (c->joint_enable) return -1;
+    return 0;
+}
+
+static int require_gpu(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        snprintf(g_err, sizeof g_err, "no CUDA device available (%s): libsolo_b200 has no CPU fallback",
+                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return -2;
+    }
+    if (device < 0 || device >= count) { snprintf(g_err, sizeof g_err, "bad device ordinal %d", device); return -1; }
+    CK(cudaSetDevice(device));
+    return 0;
+}
+
+extern "C" {
+
+const char* solo_b200_last_error(void) { return g_err; }
+long long solo_b200_kernel_launches(void) { std::lock_guard<std::mutex> lk(g_mu); return g_launches; }
+int solo_b200_enc_state_bytes(void) { return (int)sizeof(EncState); }
+int solo_b200_dec_state_bytes(void) { return (int)sizeof(DecState); }
+void solo_b200_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_profile = on;
+    for (auto& p : g_events) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    g_events.clear();
+}
+int solo_b200_profile_read(double* enc_ms, long long* enc_n, double* dec_ms, long long* dec_n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    double t[2] = {0, 0}; long long c[2] = {0, 0};
+    for (auto& p : g_events) {
+        if (cudaEventSynchronize(p.b) != cudaSuccess) continue;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { t[p.kind] += ms; c[p.kind]++; }
+        cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+    }
+    g_events.clear();
+    if (enc_ms) *enc_ms = t[0];
+    if (enc_n) *enc_n = c[0];
+    if (dec_ms) *dec_ms = t[1];
+    if (dec_n) *dec_n = c[1];
+    return 0;
+}
+
+// ---- encoder batch --------------------------------------------------------------------------------
+solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_enc* ctrl, int device) {
+    if (n_streams <= 0 || check_enc_ctrl(ctrl)) { snprintf(g_err, sizeof g_err, "bad encoder configuration"); return nullptr; }
+    if (require_gpu(device)) return nullptr;
+    solo_b200_enc_batch* b = new solo_b200_enc_batch();
+    memset(b, 0, sizeof *b);
+    b->n = n_streams; b->device = device;
+    if (cudaMalloc(&b->d_states, sizeof(EncState) * (size_t)n_streams) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fail("enc_batch_create", cudaGetLastError());
+        delete b; return nullptr;
+    }
+    int rate = ctrl->targetRate_bps <= 0 ? 15600 : ctrl->targetRate_bps;
+    sb_enc_init_kernel<<<(n_streams + SB_TPB - 1) / SB_TPB, SB_TPB, 0, b->stream>>>(b->d_states, n_streams, rate, ctrl->dtx_enable, ctrl->useMDIndex);
+    count_launch();
+    cudaError_t e = cudaStreamSynchronize(b->stream);
+    if (e != cudaSuccess) { fail("enc init kernel", e); cudaFree(b->d_states); delete b; return nullptr; }
+    return b;
+}
+
+int solo_b200_enc_batch_encode_device(solo_b200_enc_batch* b, const int16_t* d_pcm, uint8_t* d_bits, int cap, int16_t* d_nbytes, void* cuda_stream) {
+    if (!b || !d_pcm || !d_bits || !d_nbytes || cap < 16) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    EvPair ev; prof_begin(st, 0, &ev);
+    sb_encode_kernel<<<(b->n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states, d_pcm, d_bits, cap, d_nbytes, b->n);
+    prof_end(st, &ev);
+    count_launch();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int enc_staging(solo_b200_enc_batch* b, int cap) {
+    if (!b->d_pcm) CK(cudaMalloc(&b->d_pcm, sizeof(i16) * PACKET * (size_t)b->n));
+    if (!b->d_nbytes) CK(cudaMalloc(&b->d_nbytes, sizeof(i16) * 2 * (size_t)b->n));
+    if (!b->d_bits || b->bits_cap < cap) {
+        if (b->d_bits) cudaFree(b->d_bits);
+        b->d_bits = nullptr;
+        CK(cudaMalloc(&b->d_bits, (size_t)cap * b->n));
+        b->bits_cap = cap;
+    }
+    return 0;
+}
+
+int solo_b200_enc_batch_encode_host(solo_b200_enc_batch* b, const int16_t* pcm, uint8_t* bits, int cap, int16_t* nbytes) {
+    if (!b || !pcm || !bits || !nbytes || cap < 16) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
+    CK(cudaSetDevice(b->device));
+    int r = enc_staging(b, cap);
+    if (r) return r;
+    CK(cudaMemcpyAsync(b->d_pcm, pcm, sizeof(i16) * PACKET * (size_t)b->n, cudaMemcpyHostToDevice, b->stream));
+    r = solo_b200_enc_batch_encode_device(b, b->d_pcm, b->d_bits, cap, b->d_nbytes, b->stream);
+    if (r) return r;
+    CK(cudaMemcpyAsync(bits, b->d_bits, (size_t)cap * b->n, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(nbytes, b->d_nbytes, sizeof(i16) * 2 * (size_t)b->n, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+void solo_b200_enc_batch_destroy(solo_b200_enc_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    cudaFree(b->d_states); cudaFree(b->d_pcm); cudaFree(b->d_bits); cudaFree(b->d_nbytes);
+    cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+// ---- decoder batch --------------------------------------------------------------------------------
+solo_b200_dec_batch* solo_b200_dec_batch_create(int n_streams, const USER_Ctrl_dec* ctrl, int device) {
+    if (n_streams <= 0 || check_dec_ctrl(ctrl)) { snprintf(g_err, sizeof g_err, "bad decoder configuration"); return nullptr; }
+    if (require_gpu(device)) return nullptr;
+    solo_b200_dec_batch* b = new solo_b200_dec_batch();
+    memset(b, 0, sizeof *b);
+    b->n = n_streams; b->device = device;
+    if (cudaMalloc(&b->d_states, sizeof(DecState) * (size_t)n_streams) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fail("dec_batch_create", cudaGetLastError());
+        delete b; return nullptr;
+    }
+    sb_dec_init_kernel<<<(n_streams + SB_TPB - 1) / SB_TPB, SB_TPB, 0, b->stream>>>(b->d_states, n_streams, ctrl->useMDIndex);
+    count_launch();
+    cudaError_t e = cudaStreamSynchronize(b->stream);
+    if (e != cudaSuccess) { fail("dec init kernel", e); cudaFree(b->d_states); delete b; return nullptr; }
+    return b;
+}
+
+int solo_b200_dec_batch_decode_device(solo_b200_dec_batch* b, int16_t* d_pcm, const uint8_t* d_bits, int cap, const int16_t* d_nbytes,
+                                      const int32_t* d_lostflag, int32_t* d_ret, void* cuda_stream) {
+    if (!b || !d_pcm || !d_bits || !d_nbytes || !d_lostflag || cap < 16) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    EvPair ev; prof_begin(st, 1, &ev);
+    sb_decode_kernel<<<(b->n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states, d_pcm, d_bits, cap, d_nbytes, d_lostflag, d_ret, b->n);
+    prof_end(st, &ev);
+    count_launch();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int dec_staging(solo_b200_dec_batch* b, int cap) {
+    if (!b->d_pcm) CK(cudaMalloc(&b->d_pcm, sizeof(i16) * PACKET * (size_t)b->n));
+    if (!b->d_nbytes) CK(cudaMalloc(&b->d_nbytes, sizeof(i16) * 2 * (size_t)b->n));
+    if (!b->d_flags) CK(cudaMalloc(&b->d_flags, sizeof(i32) * (size_t)b->n));
+    if (!b->d_ret) CK(cudaMalloc(&b->d_ret, sizeof(i32) * (size_t)b->n));
+    if (!b->d_bits || b->bits_cap < cap) {
+        if (b->d_bits) cudaFree(b->d_bits);
+        b->d_bits = nullptr;
+        CK(cudaMalloc(&b->d_bits, (size_t)cap * b->n));
+        b->bits_cap = cap;
+    }
+    return 0;
+}
+
+int solo_b200_dec_batch_decode_host(solo_b200_dec_batch* b, int16_t* pcm, const uint8_t* bits, int cap, const int16_t* nbytes,
+                                    const int32_t* lostflag, int32_t* ret) {
+    if (!b || !pcm || !bits || !nbytes || !lostflag || cap < 16) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
+    CK(cudaSetDevice(b->device));
+    int r = dec_staging(b, cap);
+    if (r) return r;
+    CK(cudaMemcpyAsync(b->d_bits, bits, (size_t)cap * b->n, cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemcpyAsync(b->d_nbytes, nbytes, sizeof(i16) * 2 * (size_t)b->n, cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemcpyAsync(b->d_flags, lostflag, sizeof(i32) * (size_t)b->n, cudaMemcpyHostToDevice, b->stream));
+    r = solo_b200_dec_batch_decode_device(b, b->d_pcm, b->d_bits, cap, b->d_nbytes, b->d_flags, b->d_ret, b->stream);
+    if (r) return r;
+    CK(cudaMemcpyAsync(pcm, b->d_pcm, sizeof(i16) * PACKET * (size_t)b->n, cudaMemcpyDeviceToHost, b->stream));
+    if (ret) CK(cudaMemcpyAsync(ret, b->d_ret, sizeof(i32) * (size_t)b->n, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+void solo_b200_dec_batch_destroy(solo_b200_dec_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    cudaFree(b->d_states); cudaFree(b->d_pcm); cudaFree(b->d_bits); cudaFree(b->d_nbytes); cudaFree(b->d_flags); cudaFree(b->d_ret);
+    cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+// ---- single-stream drop-in entry points (AGR_JC1_SDK_API.h) -------------------------------------------------------
+// A handle is a batch of one stream.  Same names / return conventions as AGR_BWE_SDK_API.c:11-296.
+void* AGR_Sate_Encoder_Init(USER_Ctrl_enc* enc_Ctrl) {
+    if (!enc_Ctrl) return nullptr;
+    if (enc_Ctrl->targetRate_bps <= 0) enc_Ctrl->targetRate_bps = 15600;  // written back (AGR_BWE_SDK_API.c:34-36)
+    if (enc_Ctrl->joint_enable && (enc_Ctrl->joint_mode < 0 || enc_Ctrl->joint_mode > 3)) {
+        printf("Error in setting joint mode! It must be 0, 1, 2, 3\n");
+        return nullptr;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    solo_b200_enc_batch* b = solo_b200_enc_batch_create(1, enc_Ctrl, dev);
+    if (!b) fprintf(stderr, "solo_b200: AGR_Sate_Encoder_Init failed: %s\n", g_err);
+    return b;
+}
+SKP_int32 AGR_Sate_Encoder_Encode(void* SATEEnc_State, const SKP_int16* AGR_Sate_PCM, SKP_uint8* AGR_Sate_Bit, SKP_int32 AGR_Sate_Buf_Size,
+                                  SKP_int16* nBytesOut) {
+    if (!SATEEnc_State) return -1;
+    solo_b200_enc_batch* b = (solo_b200_enc_batch*)SATEEnc_State;
+    uint8_t tmp[MAX_PAYLOAD + 8];
+    int16_t nb[2] = {0, 0};
+    int r = solo_b200_enc_batch_encode_host(b, AGR_Sate_PCM, tmp, MAX_PAYLOAD + 8, nb);
+    if (r) { fprintf(stderr, "solo_b200: encode failed: %s\n", g_err); return -1; }
+    // DTX packets return the 8 high-band bytes with nBytesOut[0] == 0 (App. A Q16)
+    int total = nb[0] ? nb[0] : 8;
+    int n = total < AGR_Sate_Buf_Size ? total : AGR_Sate_Buf_Size;
+    if (n < 0) n = 0;
+    memcpy(AGR_Sate_Bit, tmp, n);
+    nBytesOut[0] = nb[0];
+    nBytesOut[1] = nb[1];
+    return n;
+}
+int AGR_Sate_Encoder_Uninit(void* SATEEnc_State) {
+    if (!SATEEnc_State) return -1;
+    solo_b200_enc_batch_destroy((solo_b200_enc_batch*)SATEEnc_State);
+    return 0;
+}
+
+void* AGR_Sate_Decoder_Init(USER_Ctrl_dec* dec_Ctrl) {
+    if (!dec_Ctrl) return nullptr;
+    if (dec_Ctrl->joint_enable && (dec_Ctrl->joint_mode < 0 || dec_Ctrl->joint_mode > 3)) {
+        fprintf(stderr, "Error in setting joint mode! It must be 0, 1, 2, 3\n");
+        return nullptr;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    solo_b200_dec_batch* b = solo_b200_dec_batch_create(1, dec_Ctrl, dev);
+    if (!b) fprintf(stderr, "solo_b200: AGR_Sate_Decoder_Init failed: %s\n", g_err);
+    return b;
+}
+SKP_int32 AGR_Sate_Decoder_Decode(void* SATEDec_State, SKP_int16* AGR_Sate_PCM, SKP_int16* nSamplesOut, const SKP_uint8* AGR_Sate_Bit,
+                                  SKP_int16 nBytes[], SKP_int32 lostflag) {
+    if (!SATEDec_State) return -1;
+    if (nBytes[0] <= 0) return -1;
+    solo_b200_dec_batch* b = (solo_b200_dec_batch*)SATEDec_State;
+    uint8_t tmp[MAX_PAYLOAD + 8];
+    memset(tmp, 0, sizeof tmp);
+    int n0 = nBytes[0] > MAX_PAYLOAD + 8 ? MAX_PAYLOAD + 8 : nBytes[0];
+    memcpy(tmp, AGR_Sate_Bit, n0);
+    int16_t nb[2] = {nBytes[0], nBytes[1]};
+    int32_t flag = lostflag, ret = 0;
+    int r = solo_b200_dec_batch_decode_host(b, AGR_Sate_PCM, tmp, MAX_PAYLOAD + 8, nb, &flag, &ret);
+    if (r) { fprintf(stderr, "solo_b200: decode failed: %s\n", g_err); return -1; }
+    // the reference rewrites the caller's nBytes[] while splitting the payload (AGR_BWE_decode_frame_FLP.c:171-190)
+    dec_split_lengths(nb, lostflag);
+    nBytes[0] = nb[0];
+    nBytes[1] = nb[1];
+    *nSamplesOut = PACKET;
+    return ret;
+}
+SKP_int32 AGR_Sate_Decoder_Uninit(void* SATEDec_State) {
+    if (!SATEDec_State) return -1;
+    solo_b200_dec_batch_destroy((solo_b200_dec_batch*)SATEDec_State);
+    return 0;
+}
+
+}  // extern "C"

@@ -2,6 +2,7 @@
 // TEST INFRASTRUCTURE ONLY: lets the CPU-only container check the kernel logic bit-for-bit against the
 // compiled reference (oracle/_ref).  Never linked into libsolo_b200.so.
 #include "../../solo_b200/csrc/sb_enc.cuh"
+#include "../../solo_b200/csrc/sb_dec.cuh"
 #include <stdlib.h>
 
 extern "C" {
@@ -20,4 +21,19 @@ int hs_enc_state_size() { return (int)sizeof(sb::EncState); }
 int hs_enc_work_size() { return (int)sizeof(sb::EncPacketWork); }
 void* hs_enc_state(void* p) { return &((HsEnc*)p)->st; }
 void* hs_enc_ctrl(void* p) { return &((HsEnc*)p)->w.f.c; }
+
+struct HsDec { sb::DecState st; sb::DecPacketWork w; };
+void* hs_dec_create(int mdi) {
+    HsDec* h = (HsDec*)calloc(1, sizeof(HsDec));
+    sb::dec_state_init(&h->st, mdi);
+    return h;
+}
+// same calling convention as AGR_Sate_Decoder_Decode (payload pre-trimmed by the caller); nb is not modified
+int hs_dec_decode(void* p, short* pcm, const unsigned char* bits, int cap, const short* nb, int lostflag) {
+    HsDec* h = (HsDec*)p;
+    return sb::dec_packet(&h->st, &h->w, pcm, bits, cap, nb, lostflag);
+}
+void hs_dec_destroy(void* p) { free(p); }
+int hs_dec_state_size() { return (int)sizeof(sb::DecState); }
+int hs_dec_work_size() { return (int)sizeof(sb::DecPacketWork); }
 }
