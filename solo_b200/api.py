@@ -1,0 +1,231 @@
+"""ctypes binding of libsolo_b200.so.
+
+Mirrors the reference interface for the hot path:
+  * ``SoloEncoder`` / ``SoloDecoder``  -- the six ``AGR_Sate_*`` entry points (one stream per handle), same argument
+    meaning and return conventions as /root/reference/JC1_SDK_SRC_ARM/interface/AGR_JC1_SDK_API.h:33-64;
+  * ``EncoderBatch`` / ``DecoderBatch`` -- the batched extension (``include/solo_b200.h``), N streams per call.
+Buffers are numpy arrays (host entry points) or raw device pointers (ints) for the ``*_device`` entry points.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsolo_b200.so")
+PACKET = 640
+
+
+class SoloError(RuntimeError):
+    pass
+
+
+class EncCtrl(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("mode", "targetRate_bps", "samplerate", "dtx_enable", "framesize_ms",
+                                         "joint_enable", "joint_mode", "useMDIndex")]
+
+
+class DecCtrl(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("packetLoss_perc", "samplerate", "framesize_ms", "joint_enable",
+                                         "joint_mode", "useMDIndex")]
+
+
+_lib = None
+
+
+def lib():
+    """Load libsolo_b200.so (fails loudly when it has not been built: there is no CPU implementation)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SoloError("%s missing: run `python -m solo_b200.build` (needs nvcc); no CPU fallback exists" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, i32p = C.c_void_p, C.c_void_p
+        L.solo_b200_last_error.restype = C.c_char_p
+        L.solo_b200_kernel_launches.restype = C.c_longlong
+        L.solo_b200_enc_batch_create.restype = vp
+        L.solo_b200_enc_batch_create.argtypes = [C.c_int, C.POINTER(EncCtrl), C.c_int]
+        L.solo_b200_enc_batch_encode_host.argtypes = [vp, vp, vp, C.c_int, vp]
+        L.solo_b200_enc_batch_encode_device.argtypes = [vp, vp, vp, C.c_int, vp, vp]
+        L.solo_b200_enc_batch_destroy.argtypes = [vp]
+        L.solo_b200_dec_batch_create.restype = vp
+        L.solo_b200_dec_batch_create.argtypes = [C.c_int, C.POINTER(DecCtrl), C.c_int]
+        L.solo_b200_dec_batch_decode_host.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
+        L.solo_b200_dec_batch_decode_device.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp]
+        L.solo_b200_dec_batch_destroy.argtypes = [vp]
+        L.solo_b200_profile_enable.argtypes = [C.c_int]
+        L.solo_b200_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+        L.AGR_Sate_Encoder_Init.restype = vp
+        L.AGR_Sate_Encoder_Init.argtypes = [C.POINTER(EncCtrl)]
+        L.AGR_Sate_Encoder_Encode.restype = C.c_int32
+        L.AGR_Sate_Encoder_Encode.argtypes = [vp, vp, vp, C.c_int32, vp]
+        L.AGR_Sate_Encoder_Uninit.argtypes = [vp]
+        L.AGR_Sate_Decoder_Init.restype = vp
+        L.AGR_Sate_Decoder_Init.argtypes = [C.POINTER(DecCtrl)]
+        L.AGR_Sate_Decoder_Decode.restype = C.c_int32
+        L.AGR_Sate_Decoder_Decode.argtypes = [vp, vp, vp, vp, vp, C.c_int32]
+        L.AGR_Sate_Decoder_Uninit.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def _err():
+    return lib().solo_b200_last_error().decode("utf-8", "replace")
+
+
+def kernel_launches():
+    return int(lib().solo_b200_kernel_launches())
+
+
+def state_bytes():
+    return int(lib().solo_b200_enc_state_bytes()), int(lib().solo_b200_dec_state_bytes())
+
+
+def profile_enable(on=True):
+    lib().solo_b200_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    a, b, c, d = C.c_double(), C.c_longlong(), C.c_double(), C.c_longlong()
+    lib().solo_b200_profile_read(C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+    return {"enc_ms": a.value, "enc_launches": b.value, "dec_ms": c.value, "dec_launches": d.value}
+
+
+class SoloEncoder:
+    """One stream through AGR_Sate_Encoder_Init / Encode / Uninit."""
+
+    def __init__(self, rate=13600, dtx=0, use_md_index=0, samplerate=16000, framesize_ms=40, joint_enable=0, joint_mode=0):
+        self.ctrl = EncCtrl(2, rate, samplerate, dtx, framesize_ms, joint_enable, joint_mode, use_md_index)
+        self.h = lib().AGR_Sate_Encoder_Init(C.byref(self.ctrl))
+        if not self.h:
+            raise SoloError("AGR_Sate_Encoder_Init returned NULL: " + _err())
+        self._bits = np.zeros(1024, np.uint8)
+        self._nb = np.zeros(6, np.int16)
+
+    def encode(self, pcm640, bufsize=1024):
+        pcm = np.ascontiguousarray(pcm640, dtype=np.int16)
+        assert pcm.size == PACKET
+        self._nb[:] = 0
+        n = lib().AGR_Sate_Encoder_Encode(self.h, pcm.ctypes.data, self._bits.ctypes.data, bufsize, self._nb.ctypes.data)
+        return bytes(self._bits[:max(n, 0)]), (int(self._nb[0]), int(self._nb[1])), n
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().AGR_Sate_Encoder_Uninit(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class SoloDecoder:
+    """One stream through AGR_Sate_Decoder_Init / Decode / Uninit (payload pre-trimmed by the caller)."""
+
+    def __init__(self, use_md_index=0, samplerate=16000, framesize_ms=40, joint_enable=0, joint_mode=0):
+        self.ctrl = DecCtrl(0, samplerate, framesize_ms, joint_enable, joint_mode, use_md_index)
+        self.h = lib().AGR_Sate_Decoder_Init(C.byref(self.ctrl))
+        if not self.h:
+            raise SoloError("AGR_Sate_Decoder_Init returned NULL: " + _err())
+        self._out = np.zeros(960, np.int16)
+        self._ns = C.c_int16(0)
+
+    def decode(self, payload, nbytes, lostflag):
+        buf = np.zeros(1040, np.uint8)
+        buf[:len(payload)] = np.frombuffer(bytes(payload), np.uint8)
+        nb = np.array([nbytes[0], nbytes[1], 0, 0, 0, 0], np.int16)
+        ret = lib().AGR_Sate_Decoder_Decode(self.h, self._out.ctypes.data, C.byref(self._ns), buf.ctypes.data, nb.ctypes.data, int(lostflag))
+        self.last_nbytes = (int(nb[0]), int(nb[1]))
+        self.last_nsamples = int(self._ns.value)
+        return self._out[:PACKET].copy(), ret
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().AGR_Sate_Decoder_Uninit(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class EncoderBatch:
+    """N encoder streams resident on one GPU; one call = one 40 ms packet for every stream."""
+
+    def __init__(self, n, rate=13600, dtx=0, use_md_index=0, device=0):
+        self.n = int(n)
+        self.ctrl = EncCtrl(2, rate, 16000, dtx, 40, 0, 0, use_md_index)
+        self.h = lib().solo_b200_enc_batch_create(self.n, C.byref(self.ctrl), device)
+        if not self.h:
+            raise SoloError("solo_b200_enc_batch_create failed: " + _err())
+
+    def encode(self, pcm, cap=256, bits=None, nbytes=None):
+        """pcm: int16 [N, 640] host array -> (bits uint8 [N, cap], nbytes int16 [N, 2])."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        assert pcm.shape == (self.n, PACKET)
+        if bits is None:
+            bits = np.empty((self.n, cap), np.uint8)
+        if nbytes is None:
+            nbytes = np.empty((self.n, 2), np.int16)
+        r = lib().solo_b200_enc_batch_encode_host(self.h, pcm.ctypes.data, bits.ctypes.data, cap, nbytes.ctypes.data)
+        if r:
+            raise SoloError("encode_host failed (%d): %s" % (r, _err()))
+        return bits, nbytes
+
+    def encode_ptr(self, pcm_ptr, bits_ptr, cap, nbytes_ptr):
+        """Host entry point on raw addresses (e.g. pinned torch tensors' data_ptr())."""
+        r = lib().solo_b200_enc_batch_encode_host(self.h, pcm_ptr, bits_ptr, cap, nbytes_ptr)
+        if r:
+            raise SoloError("encode_host failed (%d): %s" % (r, _err()))
+
+    def encode_device(self, d_pcm, d_bits, cap, d_nbytes, stream=0):
+        r = lib().solo_b200_enc_batch_encode_device(self.h, d_pcm, d_bits, cap, d_nbytes, stream)
+        if r:
+            raise SoloError("encode_device failed (%d): %s" % (r, _err()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().solo_b200_enc_batch_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class DecoderBatch:
+    """N decoder streams resident on one GPU."""
+
+    def __init__(self, n, use_md_index=0, device=0):
+        self.n = int(n)
+        self.ctrl = DecCtrl(0, 16000, 40, 0, 0, use_md_index)
+        self.h = lib().solo_b200_dec_batch_create(self.n, C.byref(self.ctrl), device)
+        if not self.h:
+            raise SoloError("solo_b200_dec_batch_create failed: " + _err())
+
+    def decode(self, bits, nbytes, lostflag, pcm=None, ret=None):
+        """bits uint8 [N, cap], nbytes int16 [N, 2], lostflag int32 [N] -> (pcm int16 [N, 640], ret int32 [N])."""
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        nbytes = np.ascontiguousarray(nbytes, dtype=np.int16)
+        lostflag = np.ascontiguousarray(lostflag, dtype=np.int32)
+        assert bits.shape[0] == self.n and nbytes.shape == (self.n, 2) and lostflag.shape == (self.n,)
+        if pcm is None:
+            pcm = np.zeros((self.n, PACKET), np.int16)
+        if ret is None:
+            ret = np.zeros(self.n, np.int32)
+        r = lib().solo_b200_dec_batch_decode_host(self.h, pcm.ctypes.data, bits.ctypes.data, bits.shape[1], nbytes.ctypes.data,
+                                                  lostflag.ctypes.data, ret.ctypes.data)
+        if r:
+            raise SoloError("decode_host failed (%d): %s" % (r, _err()))
+        return pcm, ret
+
+    def decode_ptr(self, pcm_ptr, bits_ptr, cap, nbytes_ptr, flags_ptr, ret_ptr):
+        r = lib().solo_b200_dec_batch_decode_host(self.h, pcm_ptr, bits_ptr, cap, nbytes_ptr, flags_ptr, ret_ptr)
+        if r:
+            raise SoloError("decode_host failed (%d): %s" % (r, _err()))
+
+    def decode_device(self, d_pcm, d_bits, cap, d_nbytes, d_flags, d_ret=0, stream=0):
+        r = lib().solo_b200_dec_batch_decode_device(self.h, d_pcm, d_bits, cap, d_nbytes, d_flags, d_ret, stream)
+        if r:
+            raise SoloError("decode_device failed (%d): %s" % (r, _err()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().solo_b200_dec_batch_destroy(self.h)
+            self.h = None
+
+    __del__ = close
