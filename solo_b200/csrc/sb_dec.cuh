@@ -460,7 +460,10 @@ SB_FN void plc_conceal(DecState* st, DecCtrl* c, i16* signal) {
 }
 
 // ---- SKP_Silk_PLC_glue_frames (PLC.c:333-387) --------------------------------------------------------------
-SB_FN void plc_glue_frames(DecState* st, i16* signal) {
+// `len_ref`: the frame length the reference divides the fade slope by.  It is 160 except for the very first decoded frame,
+// where SKP_Silk_decode_frame still holds the start-up length 480 (fs 24 kHz) it read before the range decoder switched
+// the core to 8 kHz (decode_frame.c:277 vs decoder_set_fs); the extra 320 samples it touches are scratch.
+SB_FN void plc_glue_frames(DecState* st, i16* signal, int len_ref) {
     if (st->lossCnt) {
         sum_sqr_shift(&st->plc_conc_energy, &st->plc_conc_energy_shift, signal, FRAME, 0);
         st->plc_last_frame_lost = 1;
@@ -476,7 +479,7 @@ SB_FN void plc_glue_frames(DecState* st, i16* signal) {
                 energy = energy >> imax(24 - LZ, 0);
                 i32 frac_Q24 = st->plc_conc_energy / imax(energy, 1);
                 i32 gain_Q12 = sqrt_approx(frac_Q24);
-                i32 slope_Q12 = ((1 << 12) - gain_Q12) / FRAME;
+                i32 slope_Q12 = ((1 << 12) - gain_Q12) / len_ref;
                 for (int i = 0; i < FRAME; i++) {
                     signal[i] = (i16)(mulw(gain_Q12, signal[i]) >> 12);
                     gain_Q12 += slope_Q12;
@@ -534,6 +537,7 @@ SB_FN i32 dec_silk_frame(DecState* st, DecCtrl* c, RangeDec* rc, i32 (*Pulses)[F
                          int action, i16* pOut) {
     i32 ret = 0;
     int used_bytes0 = 0;
+    const int len_ref = st->seen_good ? FRAME : 480;
     if (st->moreInternalDecoderFrames == 0) st->nFramesDecoded = 0;
     c->LTP_scale_Q14 = 0;
     for (int i = 0; i < FRAME; i++) pOut[i] = 0;
@@ -593,7 +597,7 @@ SB_FN i32 dec_silk_frame(DecState* st, DecCtrl* c, RangeDec* rc, i32 (*Pulses)[F
         st->lossCnt++;
     }
     for (int i = 0; i < FRAME; i++) st->outBuf[i] = pOut[i];
-    plc_glue_frames(st, pOut);
+    plc_glue_frames(st, pOut, len_ref);
     cng(st, c, pOut);
     st->lagPrev = c->pitchL[NB_SUBFR - 1];
     if (used_bytes0) {
