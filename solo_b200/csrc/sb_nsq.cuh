@@ -14,27 +14,33 @@
 
 namespace sb {
 
+// Delayed-decision history.  The reference gives every state private 32-deep rings and memcpy()s all of them when a
+// survivor replaces another state (SKP_Silk_copy_del_dec_state, ~1.5 KB x 3 quantisers per copy).  Here each ring
+// position holds one entry per *writing* state (slot) and every state carries a 64-bit path word: 2 bits per ring
+// position naming the slot that holds its value there.  All states write position `idx` in the same sample, so an entry
+// is never referenced after it has been overwritten; a state copy is a copy of the path word.
+struct NsqTab {
+    i32 RandState[DD_DELAY][N_DD];
+    i32 Xq_Q10[DD_DELAY][N_DD];
+    i32 Pred_Q16[DD_DELAY][N_DD];
+    i32 Shape_Q10[DD_DELAY][N_DD];
+    i32 exc_Q10[DD_DELAY][N_DD];
+    i8 Q_Q0[DD_DELAY][N_DD];
+};
 struct NsqDelDec {
-    i32 RandState[DD_DELAY];
-    i32 Q_Q0[DD_DELAY];
-    i32 Xq_Q10[DD_DELAY];
-    i32 Pred_Q16[DD_DELAY];
-    i32 Shape_Q10[DD_DELAY];
-    i32 exc_Q10[DD_DELAY];
+    u64 path;
     i32 sAR2_Q14[SHAPE_ORDER];
     i32 sLPC_Q14[SUBFR + DD_DELAY];
     i32 LF_AR_Q12, Seed, Seed2, SeedInit2, RD_Q10;
 };
+SB_HD int nsq_slot(const NsqDelDec* d, int idx) { return (int)((d->path >> (2 * idx)) & 3); }
 struct NsqSample {
     i32 Q_Q0, Q_Q10, RD_Q10, xq_Q14, LF_AR_Q12, sLTP_shp_Q10, LPC_exc_Q16, exc_Q10, Rd_ind_Q10;
 };
 
 // SKP_Silk_copy_del_dec_state (:1669-1692)
 SB_FN void nsq_copy_state(NsqDelDec* d, const NsqDelDec* s, int lpc_idx) {
-    for (int i = 0; i < DD_DELAY; i++) {
-        d->RandState[i] = s->RandState[i]; d->Q_Q0[i] = s->Q_Q0[i]; d->Xq_Q10[i] = s->Xq_Q10[i];
-        d->Pred_Q16[i] = s->Pred_Q16[i]; d->Shape_Q10[i] = s->Shape_Q10[i]; d->exc_Q10[i] = s->exc_Q10[i];
-    }
+    d->path = s->path;
     for (int i = 0; i < SHAPE_ORDER; i++) d->sAR2_Q14[i] = s->sAR2_Q14[i];
     for (int i = 0; i < DD_DELAY; i++) d->sLPC_Q14[lpc_idx + i] = s->sLPC_Q14[lpc_idx + i];
     d->LF_AR_Q12 = s->LF_AR_Q12; d->Seed = s->Seed; d->Seed2 = s->Seed2; d->SeedInit2 = s->SeedInit2; d->RD_Q10 = s->RD_Q10;
@@ -148,6 +154,7 @@ SB_HD void nsq_undo_pred(NsqSample* ss, i32 LTP_pred_Q14, i32 LPC_pred_Q10, i32 
 
 struct NsqWork {
     NsqDelDec dd[3][N_DD];
+    NsqTab tab[3];
     NsqSample ss[3][N_DD][2];
     i32 sLTP_Q16[3][2 * FRAME];
     i16 sLTP[3][2 * FRAME];
@@ -159,15 +166,17 @@ struct NsqWork {
 SB_FN void nsq_flush(NsqState* ns, NsqWork* W, int qz, int w, int smpl_buf_idx, int decisionDelay, int sig_off, int shp_idx,
                      int ltp_idx, i8* q, i32* r, int write_pred) {
     const NsqDelDec* psDD = &W->dd[qz][w];
+    const NsqTab* T = &W->tab[qz];
     int last = smpl_buf_idx + decisionDelay;
     for (int i = 0; i < decisionDelay; i++) {
         last = (last - 1) & DD_MASK;
+        const int sl = nsq_slot(psDD, last);
         int o = sig_off + i - decisionDelay;
-        if (q) q[o] = (i8)psDD->Q_Q0[last];
-        if (r) r[o] = psDD->exc_Q10[last];
-        ns->xq[FRAME + o] = (i16)sat16(rshift_round(smulww(psDD->Xq_Q10[last], W->Gain_Q16[last]), 10));
-        ns->sLTP_shp_Q10[shp_idx - decisionDelay + i] = psDD->Shape_Q10[last];
-        if (write_pred) W->sLTP_Q16[qz][ltp_idx - decisionDelay + i] = psDD->Pred_Q16[last];
+        if (q) q[o] = T->Q_Q0[last][sl];
+        if (r) r[o] = T->exc_Q10[last][sl];
+        ns->xq[FRAME + o] = (i16)sat16(rshift_round(smulww(T->Xq_Q10[last][sl], W->Gain_Q16[last]), 10));
+        ns->sLTP_shp_Q10[shp_idx - decisionDelay + i] = T->Shape_Q10[last][sl];
+        if (write_pred) W->sLTP_Q16[qz][ltp_idx - decisionDelay + i] = T->Pred_Q16[last][sl];
     }
 }
 
@@ -191,14 +200,16 @@ SB_FN void nsq_del_dec(EncState* st, EncCtrl* c, NsqWork* W, const i16* x, i8* q
         for (int k = 0; k < N_DD; k++) {
             NsqDelDec* d = &W->dd[qz][k];
             memset(d, 0, sizeof(NsqDelDec));
+            d->path = 0x5555555555555555ull * (u64)k;  // every ring position -> own slot
             d->Seed = (k + c->Seed) & 3;
             d->Seed2 = d->Seed;
             d->SeedInit2 = d->Seed;
             d->LF_AR_Q12 = NS[qz]->sLF_AR_shp_Q12;
-            d->Shape_Q10[0] = NS[qz]->sLTP_shp_Q10[FRAME - 1];
             for (int i = 0; i < DD_DELAY; i++) d->sLPC_Q14[i] = NS[qz]->sLPC_Q14[i];
             for (int i = 0; i < SHAPE_ORDER; i++) d->sAR2_Q14[i] = NS[qz]->sAR2_Q14[i];
         }
+        memset(&W->tab[qz], 0, sizeof(NsqTab));
+        for (int k = 0; k < N_DD; k++) W->tab[qz].Shape_Q10[0][k] = NS[qz]->sLTP_shp_Q10[FRAME - 1];
         for (int i = 0; i < 2 * FRAME; i++) { W->sLTP_Q16[qz][i] = 0; W->sLTP[qz][i] = 0; }
     }
     for (int i = 0; i < DD_DELAY; i++) W->Gain_Q16[i] = 0;
@@ -257,11 +268,12 @@ SB_FN void nsq_del_dec(EncState* st, EncCtrl* c, NsqWork* W, const i16* x, i8* q
                     d->LF_AR_Q12 = smulww(gain_adj_Q16, d->LF_AR_Q12);
                     for (int i = 0; i < DD_DELAY; i++) d->sLPC_Q14[i] = smulww(gain_adj_Q16, d->sLPC_Q14[i]);
                     for (int i = 0; i < SHAPE_ORDER; i++) d->sAR2_Q14[i] = smulww(gain_adj_Q16, d->sAR2_Q14[i]);
-                    for (int i = 0; i < DD_DELAY; i++) {
-                        d->Pred_Q16[i] = smulww(gain_adj_Q16, d->Pred_Q16[i]);
-                        d->Shape_Q10[i] = smulww(gain_adj_Q16, d->Shape_Q10[i]);
-                    }
                 }
+                for (int i = 0; i < DD_DELAY; i++)
+                    for (int s = 0; s < N_DD; s++) {
+                        W->tab[qz].Pred_Q16[i][s] = smulww(gain_adj_Q16, W->tab[qz].Pred_Q16[i][s]);
+                        W->tab[qz].Shape_Q10[i][s] = smulww(gain_adj_Q16, W->tab[qz].Shape_Q10[i][s]);
+                    }
             }
             ns->prev_inv_gain_Q16 = inv_gain_Q16;
         }
@@ -330,7 +342,7 @@ SB_FN void nsq_del_dec(EncState* st, EncCtrl* c, NsqWork* W, const i16* x, i8* q
                     n_AR = smlawb(n_AR, d->LF_AR_Q12, Tilt_Q14);
                     n_AR_Q10[qz] = n_AR;
                     // Agora_Silk_LFS (:129-141)
-                    i32 n_LF = shl(smulwb(d->Shape_Q10[smpl_buf_idx], LF_shp_Q14), 2);
+                    i32 n_LF = shl(smulwb(W->tab[qz].Shape_Q10[smpl_buf_idx][nsq_slot(d, smpl_buf_idx)], LF_shp_Q14), 2);
                     n_LF = smlawt(n_LF, d->LF_AR_Q12, LF_shp_Q14);
                     n_LF_Q10[qz] = n_LF;
                     // Agora_Silk_DoPred_And_Shap (:143-163)
@@ -372,12 +384,12 @@ SB_FN void nsq_del_dec(EncState* st, EncCtrl* c, NsqWork* W, const i16* x, i8* q
                     i32 j = addw(addw(W->ss[0][s][0].RD_Q10, smulww(W->ss[1][s][0].RD_Q10, JL)), smulww(W->ss[2][s][0].RD_Q10, JL));
                     if (j < RDmin) { RDmin = j; Winner_ind = s; }
                 }
-                i32 wr0 = W->dd[0][Winner_ind].RandState[last_smple_idx];
-                i32 wr1 = W->dd[1][Winner_ind].RandState[last_smple_idx];
-                i32 wr2 = W->dd[2][Winner_ind].RandState[last_smple_idx];
+                i32 wr[3];
+                for (int qz = 0; qz < 3; qz++) wr[qz] = W->tab[qz].RandState[last_smple_idx][nsq_slot(&W->dd[qz][Winner_ind], last_smple_idx)];
                 for (int s = 0; s < N_DD; s++) {
-                    if (W->dd[0][s].RandState[last_smple_idx] != wr0 || W->dd[1][s].RandState[last_smple_idx] != wr1 ||
-                        W->dd[2][s].RandState[last_smple_idx] != wr2) {
+                    int mism = 0;
+                    for (int qz = 0; qz < 3; qz++) mism |= (W->tab[qz].RandState[last_smple_idx][nsq_slot(&W->dd[qz][s], last_smple_idx)] != wr[qz]);
+                    if (mism) {
                         RandSyncCtl++;
                         W->ss[0][s][0].RD_Q10 = addw(W->ss[0][s][0].RD_Q10, SB_I32_MAX >> 4);
                         W->ss[0][s][1].RD_Q10 = addw(W->ss[0][s][1].RD_Q10, SB_I32_MAX >> 4);
@@ -410,12 +422,14 @@ SB_FN void nsq_del_dec(EncState* st, EncCtrl* c, NsqWork* W, const i16* x, i8* q
                 if (subfr > 0 || i >= decisionDelay) {
                     for (int qz = 0; qz < 3; qz++) {
                         const NsqDelDec* d = &W->dd[qz][Winner_ind];
+                        const NsqTab* T = &W->tab[qz];
+                        const int sl = nsq_slot(d, last_smple_idx);
                         const int o = sig_off + i - decisionDelay;
-                        if (Q[qz]) Q[qz][o] = (i8)d->Q_Q0[last_smple_idx];
-                        if (qz == 0) r[o] = d->exc_Q10[last_smple_idx];
-                        NS[qz]->xq[FRAME + o] = (i16)sat16(rshift_round(smulww(d->Xq_Q10[last_smple_idx], W->Gain_Q16[last_smple_idx]), 10));
-                        NS[qz]->sLTP_shp_Q10[shp_idx - decisionDelay] = d->Shape_Q10[last_smple_idx];
-                        W->sLTP_Q16[qz][ltp_idx - decisionDelay] = d->Pred_Q16[last_smple_idx];
+                        if (Q[qz]) Q[qz][o] = T->Q_Q0[last_smple_idx][sl];
+                        if (qz == 0) r[o] = T->exc_Q10[last_smple_idx][sl];
+                        NS[qz]->xq[FRAME + o] = (i16)sat16(rshift_round(smulww(T->Xq_Q10[last_smple_idx][sl], W->Gain_Q16[last_smple_idx]), 10));
+                        NS[qz]->sLTP_shp_Q10[shp_idx - decisionDelay] = T->Shape_Q10[last_smple_idx][sl];
+                        W->sLTP_Q16[qz][ltp_idx - decisionDelay] = T->Pred_Q16[last_smple_idx][sl];
                     }
                 }
                 shp_idx++;
@@ -428,14 +442,16 @@ SB_FN void nsq_del_dec(EncState* st, EncCtrl* c, NsqWork* W, const i16* x, i8* q
                     const NsqSample* p = &W->ss[qz][s][0];
                     d->LF_AR_Q12 = p->LF_AR_Q12;
                     d->sLPC_Q14[DD_DELAY + i] = p->xq_Q14;
-                    d->Xq_Q10[smpl_buf_idx] = p->xq_Q14 >> 4;
-                    d->Q_Q0[smpl_buf_idx] = p->Q_Q0;
-                    d->Pred_Q16[smpl_buf_idx] = p->LPC_exc_Q16;
-                    d->Shape_Q10[smpl_buf_idx] = p->sLTP_shp_Q10;
+                    NsqTab* T = &W->tab[qz];
+                    T->Xq_Q10[smpl_buf_idx][s] = p->xq_Q14 >> 4;
+                    T->Q_Q0[smpl_buf_idx][s] = (i8)p->Q_Q0;
+                    T->Pred_Q16[smpl_buf_idx][s] = p->LPC_exc_Q16;
+                    T->Shape_Q10[smpl_buf_idx][s] = p->sLTP_shp_Q10;
                     d->Seed = addw(d->Seed, p->Q_Q0);
-                    d->RandState[smpl_buf_idx] = d->Seed;
+                    T->RandState[smpl_buf_idx][s] = d->Seed;
                     d->RD_Q10 = p->RD_Q10;
-                    d->exc_Q10[smpl_buf_idx] = p->exc_Q10;
+                    T->exc_Q10[smpl_buf_idx][s] = p->exc_Q10;
+                    d->path = (d->path & ~((u64)3 << (2 * smpl_buf_idx))) | ((u64)s << (2 * smpl_buf_idx));
                 }
             }
             W->Gain_Q16[smpl_buf_idx] = Gain_Q16;
