@@ -54,10 +54,10 @@ int solo_b200_enc_state_bytes(void);
 int solo_b200_dec_state_bytes(void);
 /* Number of kernels this library has launched in this process (for benchmark bookkeeping). */
 long long solo_b200_kernel_launches(void);
-/* Average duration in ms of the encode / decode kernel over the launches since the last reset, measured with
-   CUDA events recorded on the launching stream (only while profiling is enabled). */
+/* Kernel timing with CUDA events recorded on the launching stream (only while enabled).  profile_read fills two arrays
+   of 4: total ms and launch count since the last read for {encoder analysis, encoder NSQ, encoder finish, decode}. */
 void solo_b200_profile_enable(int on);
-int solo_b200_profile_read(double *enc_ms_total, long long *enc_launches, double *dec_ms_total, long long *dec_launches);
+int solo_b200_profile_read(double ms_total[4], long long launches[4]);
 const char *solo_b200_last_error(void);
 
 #ifdef __cplusplus

@@ -54,7 +54,7 @@ def lib():
         L.solo_b200_dec_batch_decode_device.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp]
         L.solo_b200_dec_batch_destroy.argtypes = [vp]
         L.solo_b200_profile_enable.argtypes = [C.c_int]
-        L.solo_b200_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+        L.solo_b200_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
         L.AGR_Sate_Encoder_Init.restype = vp
         L.AGR_Sate_Encoder_Init.argtypes = [C.POINTER(EncCtrl)]
         L.AGR_Sate_Encoder_Encode.restype = C.c_int32
@@ -86,9 +86,12 @@ def profile_enable(on=True):
 
 
 def profile_read():
-    a, b, c, d = C.c_double(), C.c_longlong(), C.c_double(), C.c_longlong()
-    lib().solo_b200_profile_read(C.byref(a), C.byref(b), C.byref(c), C.byref(d))
-    return {"enc_ms": a.value, "enc_launches": b.value, "dec_ms": c.value, "dec_launches": d.value}
+    """{kernel: (total_ms, launches)} since the last read."""
+    t = (C.c_double * 4)()
+    n = (C.c_longlong * 4)()
+    lib().solo_b200_profile_read(t, n)
+    names = ("enc_analysis", "enc_nsq", "enc_finish", "decode")
+    return {k: (t[i], n[i]) for i, k in enumerate(names)}
 
 
 class SoloEncoder:

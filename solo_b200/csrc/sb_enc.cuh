@@ -104,8 +104,10 @@ SB_FN i32 hb_lsp_quant(i32* lsp) {
     return shl(idx2, 8) + idx1;
 }
 
-// ---- AGR_Bwe_encode_frame_FIX (AGR_BWE_encode_frame_FIX.c:8-82): one 20 ms high-band frame -> 4 bytes ----------
-SB_FN void hb_encode_frame(EncState* st, const i16* high, const i32* residue, u8* out4) {
+// ---- AGR_Bwe_encode_frame_FIX (AGR_BWE_encode_frame_FIX.c:8-82), split in two because the gain needs the low-band
+// excitation produced by the noise-shaping quantiser: (1) buffer update, LPC analysis, LSP VQ, per-sub-frame residual
+// energy of the high band; (2) gain = 16*sqrt(E_hb)/sqrt(E_lb_exc), 32-level VQ, bit packing (12 + 4*5 bits, MSB first).
+SB_FN void hb_analyse_frame(EncState* st, const i16* high, i32* lsp_idx_out, i32* nrg0_out) {
     const int LPCF = 80;
     for (int i = 0; i < HB_FRAME; i++) st->x_hb_buf[HB_FRAME + 40 + i] = high[i];
     // AGR_Sate_find_HB_LPC_FIX: 4 blocks of (80 + 8) samples, hop 80, starting 8 samples before the frame
@@ -122,22 +124,28 @@ SB_FN void hb_encode_frame(EncState* st, const i16* high, const i32* residue, u8
     i32 NLSF_Q15[HB_ORDER], interp, prev_dummy[HB_ORDER];
     for (int i = 0; i < HB_ORDER; i++) prev_dummy[i] = 0;
     find_lpc(NLSF_Q15, &interp, prev_dummy, 0, HB_ORDER, LPC_in_pre, LPCF + HB_ORDER);
-    i32 lsp_idx = hb_lsp_quant(NLSF_Q15);
+    *lsp_idx_out = hb_lsp_quant(NLSF_Q15);
     i16 coef[HB_ORDER], exc[SUBFR];
     nlsf2a_stable(coef, NLSF_Q15, HB_ORDER);
-    i32 gain_idx[4];
     const i16* p_hb = st->x_hb_buf + HB_FRAME;
     for (int sub = 0; sub < 4; sub++) {
         lpc_analysis_filter_zero_state(p_hb, coef, exc, SUBFR, HB_ORDER);
-        i32 nrg0 = 0, nrg1 = 0;
-        for (int i = 0; i < SUBFR; i++) {
-            nrg0 = addw(nrg0, (i32)exc[i] * (i32)exc[i]);
-            i32 tmp = residue[sub * SUBFR + i] >> 10;
-            nrg1 = smlabb(nrg1, tmp, tmp);
-        }
-        nrg0 = sqrt_approx(nrg0);
+        i32 nrg0 = 0;
+        for (int i = 0; i < SUBFR; i++) nrg0 = addw(nrg0, (i32)exc[i] * (i32)exc[i]);
+        nrg0_out[sub] = sqrt_approx(nrg0);
+        p_hb += SUBFR;
+    }
+    for (int i = 0; i < HB_FRAME + 40; i++) st->x_hb_buf[i] = st->x_hb_buf[HB_FRAME + i];
+    st->hb_first = 0;
+}
+// r16 = (int16)(low-band excitation Q10 >> 10), the only form in which AGR_BWE_encode_frame_FIX.c:56-58 uses it
+SB_FN void hb_pack_frame(i32 lsp_idx, const i32* nrg0, const i16* r16, u8* out4) {
+    i32 gain_idx[4];
+    for (int sub = 0; sub < 4; sub++) {
+        i32 nrg1 = 0;
+        for (int i = 0; i < SUBFR; i++) nrg1 = smlabb(nrg1, r16[sub * SUBFR + i], r16[sub * SUBFR + i]);
         nrg1 = sqrt_approx(nrg1);
-        i16 gain = (i16)(shl(nrg0 + 1, 4) / (nrg1 + 1));
+        i16 gain = (i16)(shl(nrg0[sub] + 1, 4) / (nrg1 + 1));
         i32 md = SB_I32_MAX; int gi = 0;
         for (int i = 0; i < 32; i++) {
             i16 t = (i16)(gain - SB_T(hb_gain_cb_fix)[i]);
@@ -145,27 +153,34 @@ SB_FN void hb_encode_frame(EncState* st, const i16* high, const i32* residue, u8
             if (dist < md) { md = dist; gi = i; }
         }
         gain_idx[sub] = gi;
-        p_hb += SUBFR;
     }
-    // 12 + 4*5 bits, MSB first (AGR_BWE_bits.c:77-117)
     u32 w = ((u32)lsp_idx & 0xFFF) << 20 | ((u32)gain_idx[0] << 15) | ((u32)gain_idx[1] << 10) | ((u32)gain_idx[2] << 5) | (u32)gain_idx[3];
     out4[0] = (u8)(w >> 24); out4[1] = (u8)(w >> 16); out4[2] = (u8)(w >> 8); out4[3] = (u8)w;
-    for (int i = 0; i < HB_FRAME + 40; i++) st->x_hb_buf[i] = st->x_hb_buf[HB_FRAME + i];
-    st->hb_first = 0;
 }
 
-// ---- SKP_Silk_encode_frame_FIX (encode_frame_FIX.c:34-327), one 20 ms frame of the low band ------------------------
-struct EncFrameWork {
-    EncCtrl c;
-    NsqWork nsq;
-    i16 xfw[FRAME];
-    i16 pIn_HP[FRAME];
-    i16 res_pitch[2 * FRAME + LA_PITCH];
-    i8 q_md[2][FRAME];
+// ---- per-packet hand-over between the three encoder stages (device: global scratch, one slot per stream) ----------
+//   stage A (analysis, one thread per stream)   : QMF split, VAD .. process_gains for both frames, high-band analysis
+//   stage B (MD noise-shaping quantiser)         : consumes c[f], xfw[f]; produces q_md[f], r16[f], c[f].Seed
+//   stage C (entropy coding + packing)           : range-codes both descriptions, high-band gains, payload assembly
+struct EncScratch {
+    EncCtrl c[2];
+    i16 xfw[2][FRAME];
+    i8 q_md[2][2][FRAME];  // [frame][description]
+    i16 r16[2][FRAME];
+    i32 vadFlag[2];
+    i32 hb_lsp_idx[2];
+    i32 hb_nrg0[2][4];
+    i32 dtx_drop;
 };
 
-SB_FN void encode_frame(EncState* st, EncFrameWork* W, const i16* pIn, int frame_in_packet, RangeEnc* rc, i32* r_out) {
-    EncCtrl* c = &W->c;
+struct EncAnalysisWork {
+    i16 low[PACKET / 2], high[PACKET / 2];
+    i16 pIn_HP[FRAME];
+    i16 res_pitch[2 * FRAME + LA_PITCH];
+};
+
+// SKP_Silk_encode_frame_FIX (encode_frame_FIX.c:34-131, 151-165, 199-208) up to the quantiser, for one frame
+SB_FN void encode_frame_analysis(EncState* st, EncAnalysisWork* W, EncCtrl* c, i16* xfw, i32* vadFlag_out, const i16* pIn, int frame_in_packet) {
     c->Seed = st->frameCounter++ & 3;
     i16* x_frame = st->x_buf + FRAME;
     vad_get_sa_q8(&st->vad, &st->speech_activity_Q8, c->input_quality_bands_Q15, &c->input_tilt_Q15, pIn);
@@ -173,10 +188,9 @@ SB_FN void encode_frame(EncState* st, EncFrameWork* W, const i16* pIn, int frame
     for (int i = 0; i < FRAME; i++) x_frame[LA_SHAPE + i] = W->pIn_HP[i];  // LP_variable_cutoff is a copy (transition_frame_no == 0)
     find_pitch_lags(st, c, W->res_pitch, x_frame);
     noise_shape_analysis(st, c, W->res_pitch + FRAME, x_frame);
-    prefilter(st, c, W->xfw, x_frame);
+    prefilter(st, c, xfw, x_frame);
     find_pred_coefs(st, c, W->res_pitch, frame_in_packet);
     process_gains(st, c, frame_in_packet);
-    nsq_del_dec(st, c, &W->nsq, W->xfw, (i8*)0, W->q_md[0], W->q_md[1], r_out);
     if (st->speech_activity_Q8 < SB_FIXC(0.1f, 8)) {
         st->vadFlag = 0;
         st->noSpeechCounter++;
@@ -185,51 +199,70 @@ SB_FN void encode_frame(EncState* st, EncFrameWork* W, const i16* pIn, int frame
     } else {
         st->noSpeechCounter = 0; st->inDTX = 0; st->vadFlag = 1;
     }
-    for (int k = 0; k < 2; k++) encode_parameters(&rc[k], st, c, k, frame_in_packet, st->vadFlag, W->q_md[k]);
+    *vadFlag_out = st->vadFlag;
     for (int i = 0; i < FRAME + LA_SHAPE; i++) st->x_buf[i] = st->x_buf[FRAME + i];
     st->prev_sigtype = c->sigtype;
     st->prevLag = c->pitchL[NB_SUBFR - 1];
     st->first_frame_after_reset = 0;
-    // frame terminator: MORE_FRAMES (1) after the first frame, LAST_FRAME (0) after the second
-    for (int k = 0; k < 2; k++) rc_encode(&rc[k], frame_in_packet == 0 ? 1 : 0, SB_T(frame_term_cdf));
 }
 
-// ---- AGR_Sate_Encoder_Encode: returns the byte count; nBytesOut[0] = total, nBytesOut[1] = len(MD2) + 8 -------------
-struct EncPacketWork {
-    EncFrameWork f;
-    i16 low[PACKET / 2], high[PACKET / 2];
-    i32 res_Q10[PACKET / 2];
-    u8 rcbuf[2][MAX_PAYLOAD];
-};
-
-SB_FN i32 enc_packet(EncState* st, EncPacketWork* W, const i16* pcm, u8* out, i32 out_cap, i16* nBytesOut) {
+// stage A
+SB_FN void enc_packet_analysis(EncState* st, EncAnalysisWork* W, const i16* pcm, EncScratch* scr) {
     qmf_decomp(pcm, W->low, W->high, st->qmf_mem);
-    RangeEnc rc[2];
-    rc_enc_init(&rc[0], W->rcbuf[0], MAX_PAYLOAD);
-    rc_enc_init(&rc[1], W->rcbuf[1], MAX_PAYLOAD);
-    for (int f = 0; f < 2; f++) encode_frame(st, &W->f, W->low + f * FRAME, f, rc, W->res_Q10 + f * FRAME);
+    for (int f = 0; f < 2; f++) encode_frame_analysis(st, W, &scr->c[f], scr->xfw[f], &scr->vadFlag[f], W->low + f * FRAME, f);
+    scr->dtx_drop = (st->useDTX && st->inDTX) ? 1 : 0;
+    for (int f = 0; f < 2; f++) hb_analyse_frame(st, W->high + f * HB_FRAME, &scr->hb_lsp_idx[f], scr->hb_nrg0[f]);
+}
+
+// stage C: AGR_Sate_Encoder_Encode tail -- returns the byte count; nBytesOut[0] = total, nBytesOut[1] = len(MD2) + 8
+SB_FN i32 enc_packet_finish(EncState* st, const EncScratch* scr, u8* rcbuf /* MAX_PAYLOAD scratch */, u8* out, i32 out_cap, i16* nBytesOut) {
     int nb[2];
-    rc_get_length(&rc[0], &nb[0]);
-    rc_get_length(&rc[1], &nb[1]);
-    int silk_ok = (nb[0] + nb[1] <= MAX_PAYLOAD) && !rc[0].error && !rc[1].error;
-    if (silk_ok) { rc_enc_wrap_up(&rc[0]); rc_enc_wrap_up(&rc[1]); }
-    else { nb[0] = nb[1] = 0; }
-    if (st->useDTX && st->inDTX) { nb[0] = nb[1] = 0; }
+    int ok = 1;
+    int written = 0;
+    for (int k = 0; k < 2; k++) {
+        RangeEnc rc;
+        rc_enc_init(&rc, rcbuf, MAX_PAYLOAD);
+        for (int f = 0; f < 2; f++) {
+            encode_parameters(&rc, st, &scr->c[f], k, f, scr->vadFlag[f], scr->q_md[f][k]);
+            // frame terminator: MORE_FRAMES (1) after the first frame, LAST_FRAME (0) after the second
+            rc_encode(&rc, f == 0 ? 1 : 0, SB_T(frame_term_cdf));
+        }
+        rc_get_length(&rc, &nb[k]);
+        if (rc.error) ok = 0;
+        if (k == 1 && nb[0] + nb[1] > MAX_PAYLOAD) ok = 0;  // pnBytesOut[0] >= nMDBytes (encode_frame_FIX.c:245)
+        if (ok) {
+            rc_enc_wrap_up(&rc);
+            for (int i = 0; i < nb[k]; i++) if (written + i < out_cap) out[written + i] = rcbuf[i];
+            written += nb[k];
+        }
+    }
+    if (!ok) { nb[0] = nb[1] = 0; }
+    if (scr->dtx_drop) { nb[0] = nb[1] = 0; }
     u8 hb[8];
-    for (int f = 0; f < 2; f++) hb_encode_frame(st, W->high + f * HB_FRAME, W->res_Q10 + f * HB_FRAME, hb + 4 * f);
+    for (int f = 0; f < 2; f++) hb_pack_frame(scr->hb_lsp_idx[f], scr->hb_nrg0[f], scr->r16[f], hb + 4 * f);
     int lb = nb[0] + nb[1];
     int total = lb + 8;
-    int n = imin(out_cap, total);
-    for (int i = 0; i < n; i++) {
-        u8 v;
-        if (i < nb[0]) v = W->rcbuf[0][i];
-        else if (i < lb) v = W->rcbuf[1][i - nb[0]];
-        else v = hb[i - lb];
-        out[i] = v;
-    }
+    for (int i = 0; i < 8; i++) if (lb + i < out_cap) out[lb + i] = hb[i];
     if (lb) { nBytesOut[0] = (i16)total; nBytesOut[1] = (i16)(nb[1] + 8); }
     else { nBytesOut[0] = 0; nBytesOut[1] = 0; }
-    return n;
+    return imin(out_cap, total);
+}
+
+// Whole packet on one thread (host model used by tests/hostsim; the device runs stage B as a warp-per-stream kernel).
+struct EncPacketWork {
+    EncAnalysisWork a;
+    EncScratch scr;
+    NsqWork nsq;
+    i32 r[FRAME];
+    u8 rcbuf[MAX_PAYLOAD];
+};
+SB_FN i32 enc_packet(EncState* st, EncPacketWork* W, const i16* pcm, u8* out, i32 out_cap, i16* nBytesOut) {
+    enc_packet_analysis(st, &W->a, pcm, &W->scr);
+    for (int f = 0; f < 2; f++) {
+        nsq_del_dec(st, &W->scr.c[f], &W->nsq, W->scr.xfw[f], (i8*)0, W->scr.q_md[f][0], W->scr.q_md[f][1], W->r);
+        for (int i = 0; i < FRAME; i++) W->scr.r16[f][i] = (i16)(W->r[i] >> 10);
+    }
+    return enc_packet_finish(st, &W->scr, W->rcbuf, out, out_cap, nBytesOut);
 }
 
 }  // namespace sb

@@ -17,6 +17,7 @@
 #include "../../include/solo_b200.h"
 #include "sb_dec.cuh"
 #include "sb_enc.cuh"
+#include "sb_nsq_warp.cuh"
 
 using namespace sb;
 
@@ -30,19 +31,41 @@ __global__ void __launch_bounds__(SB_TPB) sb_enc_init_kernel(EncState* states, i
     if (s < n) enc_state_init(&states[s], rate, dtx, mdi);
 }
 
-__global__ void __launch_bounds__(SB_TPB) sb_encode_kernel(EncState* states, const i16* __restrict__ pcm, u8* __restrict__ bits, int cap,
-                                                           i16* __restrict__ nbytes, int n) {
+// Encoder = three kernels per packet wave (stream s, scratch slot s):
+//   A  sb_enc_analysis_kernel : one thread per stream  -- QMF split, VAD .. gain processing of both frames, high-band analysis
+//   B  sb_enc_nsq_kernel      : one WARP per stream    -- MD delayed-decision noise-shaping quantiser, state in shared memory
+//   C  sb_enc_finish_kernel   : one thread per stream  -- range coding of both descriptions, high-band gains, payload assembly
+__global__ void __launch_bounds__(SB_TPB) sb_enc_analysis_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ pcm, int n) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    EncPacketWork W;
+    EncAnalysisWork W;
     i16 x[PACKET];
     // 128-bit loads of this stream's 1280-byte PCM row
     const int4* src = reinterpret_cast<const int4*>(pcm + (size_t)s * PACKET);
     int4* dst = reinterpret_cast<int4*>(x);
 #pragma unroll 4
     for (int i = 0; i < PACKET * 2 / 16; i++) dst[i] = src[i];
+    enc_packet_analysis(&states[s], &W, x, &scratch[s]);
+}
+
+#define SB_NSQ_WARPS 4
+__global__ void __launch_bounds__(SB_NSQ_WARPS * 32) sb_enc_nsq_kernel(EncState* states, EncScratch* scratch, int n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NsqSmem* S = reinterpret_cast<NsqSmem*>(smem_raw) + (threadIdx.x >> 5);
+    int s = blockIdx.x * SB_NSQ_WARPS + (threadIdx.x >> 5);
+    if (s >= n) return;
+    EncScratch* scr = &scratch[s];
+    for (int f = 0; f < 2; f++)
+        nsq_del_dec_warp(*S, states[s].nsq, &scr->c[f], scr->xfw[f], scr->q_md[f][0], scr->q_md[f][1], scr->r16[f]);
+}
+
+__global__ void __launch_bounds__(SB_TPB) sb_enc_finish_kernel(EncState* states, const EncScratch* scratch, u8* __restrict__ bits, int cap,
+                                                               i16* __restrict__ nbytes, int n) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    u8 rcbuf[MAX_PAYLOAD];
     i16 nb[2];
-    enc_packet(&states[s], &W, x, bits + (size_t)s * cap, cap, nb);
+    enc_packet_finish(&states[s], &scratch[s], rcbuf, bits + (size_t)s * cap, cap, nb);
     nbytes[2 * s] = nb[0];
     nbytes[2 * s + 1] = nb[1];
 }
@@ -109,6 +132,7 @@ static void count_launch() {
 struct solo_b200_enc_batch {
     int n, device;
     EncState* d_states;
+    EncScratch* d_scratch;
     // staging for the *_host entry points
     i16* d_pcm; u8* d_bits; i16* d_nbytes; int bits_cap;
     cudaStream_t stream;
@@ -158,9 +182,10 @@ void solo_b200_profile_enable(int on) {
     for (auto& p : g_events) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     g_events.clear();
 }
-int solo_b200_profile_read(double* enc_ms, long long* enc_n, double* dec_ms, long long* dec_n) {
+int solo_b200_profile_read(double* ms_total, long long* launches) {
+    // index 0 = encoder analysis kernel, 1 = encoder NSQ kernel, 2 = encoder finish kernel, 3 = decode kernel
     std::lock_guard<std::mutex> lk(g_mu);
-    double t[2] = {0, 0}; long long c[2] = {0, 0};
+    double t[4] = {0, 0, 0, 0}; long long c[4] = {0, 0, 0, 0};
     for (auto& p : g_events) {
         if (cudaEventSynchronize(p.b) != cudaSuccess) continue;
         float ms = 0;
@@ -168,10 +193,7 @@ int solo_b200_profile_read(double* enc_ms, long long* enc_n, double* dec_ms, lon
         cudaEventDestroy(p.a); cudaEventDestroy(p.b);
     }
     g_events.clear();
-    if (enc_ms) *enc_ms = t[0];
-    if (enc_n) *enc_n = c[0];
-    if (dec_ms) *dec_ms = t[1];
-    if (dec_n) *dec_n = c[1];
+    for (int i = 0; i < 4; i++) { if (ms_total) ms_total[i] = t[i]; if (launches) launches[i] = c[i]; }
     return 0;
 }
 
@@ -183,7 +205,9 @@ solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_e
     memset(b, 0, sizeof *b);
     b->n = n_streams; b->device = device;
     if (cudaMalloc(&b->d_states, sizeof(EncState) * (size_t)n_streams) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaMalloc(&b->d_scratch, sizeof(EncScratch) * (size_t)n_streams) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaFuncSetAttribute(sb_enc_nsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SB_NSQ_WARPS * sizeof(NsqSmem))) != cudaSuccess) {
         fail("enc_batch_create", cudaGetLastError());
         delete b; return nullptr;
     }
@@ -198,10 +222,17 @@ solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_e
 int solo_b200_enc_batch_encode_device(solo_b200_enc_batch* b, const int16_t* d_pcm, uint8_t* d_bits, int cap, int16_t* d_nbytes, void* cuda_stream) {
     if (!b || !d_pcm || !d_bits || !d_nbytes || cap < 16) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    EvPair ev; prof_begin(st, 0, &ev);
-    sb_encode_kernel<<<(b->n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states, d_pcm, d_bits, cap, d_nbytes, b->n);
+    EvPair ev;
+    prof_begin(st, 0, &ev);
+    sb_enc_analysis_kernel<<<(b->n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states, b->d_scratch, d_pcm, b->n);
     prof_end(st, &ev);
-    count_launch();
+    prof_begin(st, 1, &ev);
+    sb_enc_nsq_kernel<<<(b->n + SB_NSQ_WARPS - 1) / SB_NSQ_WARPS, SB_NSQ_WARPS * 32, SB_NSQ_WARPS * sizeof(NsqSmem), st>>>(b->d_states, b->d_scratch, b->n);
+    prof_end(st, &ev);
+    prof_begin(st, 2, &ev);
+    sb_enc_finish_kernel<<<(b->n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states, b->d_scratch, d_bits, cap, d_nbytes, b->n);
+    prof_end(st, &ev);
+    count_launch(); count_launch(); count_launch();
     CK(cudaGetLastError());
     return 0;
 }
@@ -236,7 +267,7 @@ void solo_b200_enc_batch_destroy(solo_b200_enc_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
-    cudaFree(b->d_states); cudaFree(b->d_pcm); cudaFree(b->d_bits); cudaFree(b->d_nbytes);
+    cudaFree(b->d_states); cudaFree(b->d_scratch); cudaFree(b->d_pcm); cudaFree(b->d_bits); cudaFree(b->d_nbytes);
     cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -264,7 +295,7 @@ int solo_b200_dec_batch_decode_device(solo_b200_dec_batch* b, int16_t* d_pcm, co
                                       const int32_t* d_lostflag, int32_t* d_ret, void* cuda_stream) {
     if (!b || !d_pcm || !d_bits || !d_nbytes || !d_lostflag || cap < 16) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    EvPair ev; prof_begin(st, 1, &ev);
+    EvPair ev; prof_begin(st, 3, &ev);
     sb_decode_kernel<<<(b->n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states, d_pcm, d_bits, cap, d_nbytes, d_lostflag, d_ret, b->n);
     prof_end(st, &ev);
     count_launch();

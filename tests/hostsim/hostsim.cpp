@@ -20,7 +20,7 @@ void hs_enc_destroy(void* p) { free(p); }
 int hs_enc_state_size() { return (int)sizeof(sb::EncState); }
 int hs_enc_work_size() { return (int)sizeof(sb::EncPacketWork); }
 void* hs_enc_state(void* p) { return &((HsEnc*)p)->st; }
-void* hs_enc_ctrl(void* p) { return &((HsEnc*)p)->w.f.c; }
+void* hs_enc_ctrl(void* p) { return &((HsEnc*)p)->w.scr.c[1]; }
 
 struct HsDec { sb::DecState st; sb::DecPacketWork w; };
 void* hs_dec_create(int mdi) {
