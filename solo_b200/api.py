@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsolo_b200.so")
+# SOLO_B200_LIB: load another build of the same CUDA library (kernel-variant experiments); never a CPU path
+LIB_PATH = os.environ.get("SOLO_B200_LIB") or os.path.join(_HERE, "libsolo_b200.so")
 PACKET = 640
 
 

@@ -70,26 +70,57 @@ SB_HD i32 smulbt(i32 a, i32 b) { return (i32)(i16)a * (b >> 16); }
 SB_HD i32 smlabt(i32 a, i32 b, i32 c) { return addw(a, smulbt(b, c)); }
 SB_HD i32 smultt(i32 a, i32 b) { return (a >> 16) * (b >> 16); }
 // (a * (int16)b) >> 16, exact (macros.h:34)
-SB_HD i32 smulwb(i32 a, i32 b) { return (i32)(((i64)a * (i64)(i16)b) >> 16); }
+// Device form: (a * b16) >> 16 == high word of a * (b16 << 16); one IMAD.HI instead of a 64-bit product.
+SB_HD i32 smulwb(i32 a, i32 b) {
+#ifdef __CUDA_ARCH__
+    return __mulhi(a, (i32)((u32)b << 16));
+#else
+    return (i32)(((i64)a * (i64)(i16)b) >> 16);
+#endif
+}
 SB_HD i32 smlawb(i32 a, i32 b, i32 c) { return addw(a, smulwb(b, c)); }
-SB_HD i32 smulwt(i32 a, i32 b) { return (i32)(((i64)a * (i64)(b >> 16)) >> 16); }
+SB_HD i32 smulwt(i32 a, i32 b) {
+#ifdef __CUDA_ARCH__
+    return __mulhi(a, (i32)((u32)b & 0xFFFF0000u));
+#else
+    return (i32)(((i64)a * (i64)(b >> 16)) >> 16);
+#endif
+}
 SB_HD i32 smlawt(i32 a, i32 b, i32 c) { return addw(a, smulwt(b, c)); }
 SB_HD i32 rshift_round(i32 a, int s) { return s == 1 ? (a >> 1) + (a & 1) : ((a >> (s - 1)) + 1) >> 1; }
 SB_HD i64 rshift_round64(i64 a, int s) { return s == 1 ? (a >> 1) + (a & 1) : ((a >> (s - 1)) + 1) >> 1; }
 // SMULWW = SMULWB(a,b) + a * RSHIFT_ROUND(b,16)  (macros.h:61) == low 32 bits of (a*b)>>16
 SB_HD i32 smulww(i32 a, i32 b) { return (i32)(u32)(u64)(((i64)a * (i64)b) >> 16); }
 SB_HD i32 smlaww(i32 a, i32 b, i32 c) { return addw(a, smulww(b, c)); }
-SB_HD i32 smmul(i32 a, i32 b) { return (i32)(((i64)a * (i64)b) >> 32); }
+SB_HD i32 smmul(i32 a, i32 b) {
+#ifdef __CUDA_ARCH__
+    return __mulhi(a, b);
+#else
+    return (i32)(((i64)a * (i64)b) >> 32);
+#endif
+}
 SB_HD i64 smull(i32 a, i32 b) { return (i64)a * (i64)b; }
 
 // ---- saturating arithmetic (macros.h:69-75, SigProc_FIX.h:560-580) -----------------------------------
 SB_HD i32 add_sat32(i32 a, i32 b) {
+#ifdef __CUDA_ARCH__
+    i32 r;
+    asm("add.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#else
     i64 s = (i64)a + (i64)b;
     return s > SB_I32_MAX ? SB_I32_MAX : (s < (i64)SB_I32_MIN ? SB_I32_MIN : (i32)s);
+#endif
 }
 SB_HD i32 sub_sat32(i32 a, i32 b) {
+#ifdef __CUDA_ARCH__
+    i32 r;
+    asm("sub.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#else
     i64 s = (i64)a - (i64)b;
     return s > SB_I32_MAX ? SB_I32_MAX : (s < (i64)SB_I32_MIN ? SB_I32_MIN : (i32)s);
+#endif
 }
 SB_HD i32 add_pos_sat32(i32 a, i32 b) { i32 s = addw(a, b); return (s & 0x80000000) ? SB_I32_MAX : s; }
 SB_HD i32 lshift_sat32(i32 a, int s) {

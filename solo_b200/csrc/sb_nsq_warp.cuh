@@ -15,16 +15,18 @@
 
 namespace sb {
 
+// Row paddings keep the three quantisers' rows in different shared-memory banks (the 12 lanes address
+// [qz][same index][state]); the pad words are never read.
 struct NsqSmem {
-    i32 sLTP_Q16[3][2 * FRAME];
+    i32 sLTP_Q16[3][2 * FRAME + 1];
     i32 sLTP_shp_Q10[3][2 * FRAME + 2];
-    i16 xq[3][2 * FRAME];
-    i32 tabRand[3][DD_DELAY][N_DD];
-    i32 tabXq[3][DD_DELAY][N_DD];
-    i32 tabPred[3][DD_DELAY][N_DD];
-    i32 tabShape[3][DD_DELAY][N_DD];
+    i16 xq[3][2 * FRAME + 2];
+    i32 tabRand[3][DD_DELAY + 1][N_DD];
+    i32 tabXq[3][DD_DELAY + 1][N_DD];
+    i32 tabPred[3][DD_DELAY + 1][N_DD];
+    i32 tabShape[3][DD_DELAY + 1][N_DD];
     i32 tabExc[DD_DELAY][N_DD];
-    i8 tabQ[3][DD_DELAY][N_DD];
+    i8 tabQ[3][DD_DELAY + 1][N_DD];
     i32 Gain_Q16[DD_DELAY];
     i32 x_sc_Q10[SUBFR];
 };

@@ -25,6 +25,12 @@ using namespace sb;
 // kernels
 // ---------------------------------------------------------------------------------------------------
 #define SB_TPB 64
+#ifndef SB_ANALYSIS_MINB
+#define SB_ANALYSIS_MINB 1   // min resident blocks per SM of the analysis / decode kernels (register cap = 65536 / (64 * MINB))
+#endif
+#ifndef SB_DECODE_MINB
+#define SB_DECODE_MINB 1
+#endif
 
 __global__ void __launch_bounds__(SB_TPB) sb_enc_init_kernel(EncState* states, int n, int rate, int dtx, int mdi) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -35,7 +41,7 @@ __global__ void __launch_bounds__(SB_TPB) sb_enc_init_kernel(EncState* states, i
 //   A  sb_enc_analysis_kernel : one thread per stream  -- QMF split, VAD .. gain processing of both frames, high-band analysis
 //   B  sb_enc_nsq_kernel      : one WARP per stream    -- MD delayed-decision noise-shaping quantiser, state in shared memory
 //   C  sb_enc_finish_kernel   : one thread per stream  -- range coding of both descriptions, high-band gains, payload assembly
-__global__ void __launch_bounds__(SB_TPB) sb_enc_analysis_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ pcm, int n) {
+__global__ void __launch_bounds__(SB_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ pcm, int n) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     EncAnalysisWork W;
@@ -75,7 +81,7 @@ __global__ void __launch_bounds__(SB_TPB) sb_dec_init_kernel(DecState* states, i
     if (s < n) dec_state_init(&states[s], mdi);
 }
 
-__global__ void __launch_bounds__(SB_TPB) sb_decode_kernel(DecState* states, i16* __restrict__ pcm, const u8* __restrict__ bits, int cap,
+__global__ void __launch_bounds__(SB_TPB, SB_DECODE_MINB) sb_decode_kernel(DecState* states, i16* __restrict__ pcm, const u8* __restrict__ bits, int cap,
                                                            const i16* __restrict__ nbytes, const i32* __restrict__ lostflag,
                                                            i32* __restrict__ ret, int n) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,0 +1,66 @@
+"""ctypes driver of tests/_hostsim/libsb_hostsim.so: the per-stream kernel source (solo_b200/csrc/*.cuh) compiled by g++.
+
+TEST INFRASTRUCTURE ONLY.  It exists so that the CPU-only container can check the kernel arithmetic bit for bit; the
+product (libsolo_b200.so) never links or loads it.  Same call shapes as oracle/ref.py so tests can swap the two."""
+import ctypes as C
+
+import numpy as np
+
+from . import build_hostsim
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build_hostsim.build())
+        L.hs_enc_create.restype = C.c_void_p
+        L.hs_enc_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.hs_enc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.hs_enc_destroy.argtypes = [C.c_void_p]
+        L.hs_dec_create.restype = C.c_void_p
+        L.hs_dec_create.argtypes = [C.c_int]
+        L.hs_dec_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.hs_dec_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class SimEncoder:
+    def __init__(self, rate=13600, dtx=0, use_md_index=0, cap=1024):
+        self.L = lib()
+        self.h = self.L.hs_enc_create(rate, dtx, use_md_index)
+        self.cap = cap
+        self.out = np.zeros(cap, np.uint8)
+        self.nb = np.zeros(6, np.int16)
+
+    def encode(self, pcm640):
+        x = np.ascontiguousarray(pcm640, np.int16)
+        assert x.size == 640
+        n = self.L.hs_enc_encode(self.h, x.ctypes.data, self.out.ctypes.data, self.cap, self.nb.ctypes.data)
+        return bytes(self.out[:max(n, 0)]), (int(self.nb[0]), int(self.nb[1])), n
+
+    def close(self):
+        if self.h:
+            self.L.hs_enc_destroy(self.h)
+            self.h = None
+
+
+class SimDecoder:
+    def __init__(self, use_md_index=0):
+        self.L = lib()
+        self.h = self.L.hs_dec_create(use_md_index)
+        self.pcm = np.zeros(640, np.int16)
+
+    def decode(self, payload, nbytes, lostflag):
+        buf = np.zeros(max(len(payload), 1), np.uint8)
+        buf[:len(payload)] = np.frombuffer(payload, np.uint8)
+        nb = np.array([nbytes[0], nbytes[1]], np.int16)
+        r = self.L.hs_dec_decode(self.h, self.pcm.ctypes.data, buf.ctypes.data, len(buf), nb.ctypes.data, int(lostflag))
+        return self.pcm.copy(), r
+
+    def close(self):
+        if self.h:
+            self.L.hs_dec_destroy(self.h)
+            self.h = None

@@ -1,0 +1,142 @@
+"""Kernel arithmetic on the CPU: solo_b200/csrc/*.cuh compiled by g++ (tests/hostsim) against the golden fixtures and,
+where oracle/_ref is built, against the unmodified reference on inputs the fixtures do not cover.
+
+The headers are written once as __host__ __device__ code, so what passes here is the same source nvcc compiles into
+libsolo_b200.so (the warp-per-stream quantiser sb_nsq_warp.cuh is device-only; its scalar model sb_nsq.cuh runs here and
+the `-m gpu` suite pins the device version).  Bar: payloads and length fields byte-identical to the FIX build, PCM
+identical to the FLP build (north star allows +-1 LSB)."""
+import hashlib
+import struct
+
+import numpy as np
+import pytest
+
+from tests.util import load_clip, load_golden, loss_flags, speech_replay, synth_inputs, trim_payload
+
+PCM_TOL = 0
+
+
+@pytest.fixture(scope="module")
+def sim():
+    from tests.hostsim import sim as s
+    s.lib()
+    return s
+
+
+def bitfile(pk):
+    return b"".join(struct.pack("<hh", *nb) + (b if nb[0] else b"") for b, nb, n in pk)
+
+
+def encode(mod_enc, pcm, **kw):
+    e = mod_enc(**kw)
+    pk = [e.encode(pcm[i * 640:(i + 1) * 640]) for i in range(len(pcm) // 640)]
+    e.close()
+    return pk
+
+
+def test_encoder_matches_golden_bitstream(sim):
+    g = load_golden()
+    pk = encode(sim.SimEncoder, load_clip(), rate=13600)
+    assert hashlib.md5(bitfile(pk)).hexdigest() == str(g["fix_bitfile_md5"])
+    for i, (b, nb, n) in enumerate(pk):
+        assert nb == tuple(g["fix_nbytes"][i]) and n == nb[0]
+        assert b == bytes(g["fix_bits"][i, :n])
+
+
+@pytest.mark.parametrize("mode", [4, 2, 3, "loss50"])
+def test_decoder_matches_golden_pcm(sim, mode):
+    g = load_golden()
+    n = g["fix_nbytes"].shape[0]
+    flags = list(g["loss50_flags"]) if mode == "loss50" else [mode] * n
+    key = "flp_pcm_loss50" if mode == "loss50" else "flp_pcm_mode%d" % mode
+    d = sim.SimDecoder()
+    out = []
+    for i in range(n):
+        nb = tuple(int(v) for v in g["fix_nbytes"][i])
+        pb, pnb = trim_payload(bytes(g["fix_bits"][i, :nb[0]]), nb, int(flags[i]))
+        x, r = d.decode(pb, pnb, int(flags[i]))
+        assert r == 0
+        out.append(x)
+    d.close()
+    pcm = np.concatenate(out)
+    assert np.abs(pcm.astype(np.int32) - g[key].astype(np.int32)).max() <= PCM_TOL
+
+
+def test_encoder_matches_synthetic_hashes(sim):
+    """Other rates, scaled / clipped speech, noise, silence, DC, full-scale square, sine, DTX, MD index flag."""
+    g = load_golden()
+    for name, x, kw in synth_inputs(load_clip()):
+        kw = dict(kw)
+        if "mdi" in kw:
+            kw["use_md_index"] = kw.pop("mdi")
+        assert hashlib.md5(bitfile(encode(sim.SimEncoder, x, **kw))).hexdigest() == str(g["synth_" + name]), name
+
+
+def test_empty_and_error_inputs(sim):
+    """Reference behaviour at the edges of the decode contract (AGR_BWE_SDK_API.c:268-270, decode_frame.c:303-324):
+    nBytes[0] <= 0 is an error (-1) whatever the flag; a lost packet (flag 1) never reads its payload, and concealment
+    from the initial state is silence."""
+    d = sim.SimDecoder()
+    for flag in (1, 2, 3, 4):
+        x, r = d.decode(b"", (0, 0), flag)
+        assert r == -1
+    x, r = d.decode(bytes(16), (16, 8), 1)
+    assert r == 0 and not x.any()
+    d.close()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref as r
+    if not r.available():
+        pytest.skip("oracle/_ref not built")
+    return r
+
+
+def test_speech_replay_streams_match_reference(sim, ref):
+    """SURVEY.md 8(d) batch (i), 12 streams x 30 packets, each stream with its own loss pattern (seed 1 + s, 50 %):
+    encoder bytes vs FIX, decoder PCM vs FLP fed the same payloads and flags."""
+    S, P = 12, 30
+    x = speech_replay(load_clip(), S, P)
+    for s in range(S):
+        e_ref, e_sim = ref.RefEncoder("fix", rate=13600), sim.SimEncoder(rate=13600)
+        d_ref, d_sim = ref.RefDecoder("flp"), sim.SimDecoder()
+        flags = loss_flags(P, 50, seed=1 + s)
+        for p in range(P):
+            b0, nb0, n0 = e_ref.encode(x[p, s])
+            b1, nb1, n1 = e_sim.encode(x[p, s])
+            assert (b0[:n0], nb0, n0) == (b1[:n1], nb1, n1), (s, p)
+            pb, pnb = trim_payload(b0, nb0, flags[p])
+            y0, r0 = d_ref.decode(pb, pnb, flags[p])
+            y1, r1 = d_sim.decode(pb, pnb, flags[p])
+            assert r0 == r1 == 0
+            assert np.abs(y0.astype(np.int32) - y1.astype(np.int32)).max() <= PCM_TOL, (s, p, flags[p])
+        for o in (e_ref, e_sim, d_ref, d_sim):
+            o.close()
+
+
+def test_random_rates_and_signals_match_reference(sim, ref):
+    """Seeded sweep over target rates and signal classes that the fixtures do not hold."""
+    rng = np.random.Generator(np.random.PCG64(99))
+    clip = load_clip()
+    t = np.arange(640 * 25)
+    for rate, mdi, dtx in ((8000, 0, 0), (11000, 1, 0), (13600, 0, 1), (20000, 0, 0), (40000, 1, 1)):
+        off = int(rng.integers(0, len(clip) - 640 * 25))
+        sigs = [clip[off:off + 640 * 25],
+                (clip[off:off + 640 * 25].astype(np.int32) * 3 // 2).clip(-32768, 32767).astype(np.int16),
+                (6000 * np.sin(2 * np.pi * (80 + 3e-3 * t) * t / 16000)).astype(np.int16),
+                np.clip(rng.normal(0, 500, 640 * 25), -32768, 32767).astype(np.int16)]
+        for x in sigs:
+            a = encode(lambda **kw: ref.RefEncoder("fix", **kw), x, rate=rate, dtx=dtx, use_md_index=mdi)
+            b = encode(sim.SimEncoder, x, rate=rate, dtx=dtx, use_md_index=mdi)
+            assert [(p[0][:max(p[2], 0)], p[1], p[2]) for p in a] == [(p[0][:max(p[2], 0)], p[1], p[2]) for p in b], (rate, mdi, dtx)
+            d0, d1 = ref.RefDecoder("flp", use_md_index=mdi), sim.SimDecoder(use_md_index=mdi)
+            for (pb, nb, n) in a:
+                if nb[0] <= 0:        # DTX: nothing was sent, the receiver conceals
+                    y0, _ = d0.decode(bytes(16), (16, 8), 1)
+                    y1, _ = d1.decode(bytes(16), (16, 8), 1)
+                else:
+                    y0, _ = d0.decode(pb[:n], nb, 4)
+                    y1, _ = d1.decode(pb[:n], nb, 4)
+                assert np.abs(y0.astype(np.int32) - y1.astype(np.int32)).max() <= PCM_TOL
+            d0.close(); d1.close()
