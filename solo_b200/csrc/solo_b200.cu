@@ -26,10 +26,10 @@ using namespace sb;
 // ---------------------------------------------------------------------------------------------------
 #define SB_TPB 64
 #ifndef SB_ANALYSIS_MINB
-#define SB_ANALYSIS_MINB 1   // min resident blocks per SM of the analysis / decode kernels (register cap = 65536 / (64 * MINB))
+#define SB_ANALYSIS_MINB 8   // min resident blocks per SM of the thread-per-stream kernels (register cap = 65536 / (64 * MINB))
 #endif
 #ifndef SB_DECODE_MINB
-#define SB_DECODE_MINB 1
+#define SB_DECODE_MINB 8
 #endif
 
 __global__ void __launch_bounds__(SB_TPB) sb_enc_init_kernel(EncState* states, int n, int rate, int dtx, int mdi) {
