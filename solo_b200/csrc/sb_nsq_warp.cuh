@@ -17,10 +17,13 @@ namespace sb {
 
 // Row paddings keep the three quantisers' rows in different shared-memory banks (the 12 lanes address
 // [qz][same index][state]); the pad words are never read.
+// The three long buffers are 160-entry rings: logical index j of the reference's 2*frame_length arrays (old frame
+// [0,160), frame being written [160,320)) lives at j mod 160.  Nothing older than lag + 2 <= 146 samples behind the write
+// position is ever read, so the ring holds exactly the persistent state on entry and on exit.
 struct NsqSmem {
-    i32 sLTP_Q16[3][2 * FRAME + 1];
-    i32 sLTP_shp_Q10[3][2 * FRAME + 2];
-    i16 xq[3][2 * FRAME + 2];
+    i32 sLTP_Q16[3][FRAME + 1];
+    i32 sLTP_shp_Q10[3][FRAME + 2];
+    i16 xq[3][FRAME + 2];
     i32 tabRand[3][DD_DELAY + 1][N_DD];
     i32 tabXq[3][DD_DELAY + 1][N_DD];
     i32 tabPred[3][DD_DELAY + 1][N_DD];
@@ -28,13 +31,17 @@ struct NsqSmem {
     i32 tabExc[DD_DELAY][N_DD];
     i8 tabQ[3][DD_DELAY + 1][N_DD];
     i32 Gain_Q16[DD_DELAY];
-    i32 x_sc_Q10[SUBFR];
 };
 
-#define SB_FULL 0xffffffffu
-__device__ __forceinline__ i32 shfl(i32 v, int src) { return __shfl_sync(SB_FULL, v, src); }
-__device__ __forceinline__ u64 shfl64(u64 v, int src) {
-    u32 lo = __shfl_sync(SB_FULL, (u32)v, src), hi = __shfl_sync(SB_FULL, (u32)(v >> 32), src);
+// Lane group = the SB_NSQ_GW lanes that work on one stream (16: two streams per warp, 32: one).  Every collective below
+// names its own group (mask gm, width SB_NSQ_GW), so the two halves of a warp may diverge freely.
+#ifndef SB_NSQ_GW
+#define SB_NSQ_GW 16
+#endif
+__device__ __forceinline__ int cix(int j) { return j >= FRAME ? j - FRAME : j; }   // ring index, 0 <= j <= 2*FRAME
+__device__ __forceinline__ i32 shfl(unsigned gm, i32 v, int src) { return __shfl_sync(gm, v, src, SB_NSQ_GW); }
+__device__ __forceinline__ u64 shfl64(unsigned gm, u64 v, int src) {
+    u32 lo = __shfl_sync(gm, (u32)v, src, SB_NSQ_GW), hi = __shfl_sync(gm, (u32)(v >> 32), src, SB_NSQ_GW);
     return ((u64)hi << 32) | lo;
 }
 
@@ -44,30 +51,34 @@ struct NsqLane {            // registers of one (quantiser, state) recurrence
     i32 LF_AR, Seed, Seed2, SeedInit2, RD;
     u64 path;
 };
+// acc + (x * c16) >> 16 with the coefficient already moved to the high half-word (one IMAD.HI, no shift in the loop)
+__device__ __forceinline__ i32 mlahi(i32 acc, i32 x, i32 c_hi) { return addw(acc, __mulhi(x, c_hi)); }
 struct NsqCand { i32 Q_Q0, Q_Q10, RD, Rd_ind, xq_Q14, LF_AR, shp, exc16, exc; };
 
-// flush `n` delayed samples of the winner of quantiser qz to the outputs; lane i handles sample i (n <= 32)
-__device__ __forceinline__ void nsqw_flush(NsqSmem& S, int lane, int qz_, u64 wpath, int smpl_buf_idx, int n, int sig_off, int shp_idx,
+// flush `n` delayed samples of the winner of quantiser qz to the outputs, samples spread over the group's lanes (n <= 32)
+__device__ __forceinline__ void nsqw_flush(NsqSmem& S, int gl, int qz_, u64 wpath, int smpl_buf_idx, int n, int sig_off, int shp_idx,
                                            int ltp_idx, i8* q, i16* r16, int write_pred) {
-    if (lane < n) {
+    for (int lane = gl; lane < n; lane += SB_NSQ_GW) {
         const int last = (smpl_buf_idx + n - 1 - lane) & DD_MASK;
         const int sl = (int)((wpath >> (2 * last)) & 3);
         const int o = sig_off + lane - n;
         if (q) q[o] = S.tabQ[qz_][last][sl];
         if (r16) r16[o] = (i16)(S.tabExc[last][sl] >> 10);
-        S.xq[qz_][FRAME + o] = (i16)sat16(rshift_round(smulww(S.tabXq[qz_][last][sl], S.Gain_Q16[last]), 10));
-        S.sLTP_shp_Q10[qz_][shp_idx - n + lane] = S.tabShape[qz_][last][sl];
-        if (write_pred) S.sLTP_Q16[qz_][ltp_idx - n + lane] = S.tabPred[qz_][last][sl];
+        S.xq[qz_][o] = (i16)sat16(rshift_round(smulww(S.tabXq[qz_][last][sl], S.Gain_Q16[last]), 10));
+        S.sLTP_shp_Q10[qz_][cix(shp_idx - n + lane)] = S.tabShape[qz_][last][sl];
+        if (write_pred) S.sLTP_Q16[qz_][cix(ltp_idx - n + lane)] = S.tabPred[qz_][last][sl];
     }
 }
 
 // One 20 ms frame.  st: persistent quantiser states (global); c: frame control from the analysis stage (global, Seed is
 // updated); x: prefiltered input; outputs: pulses of the two descriptions, (int16)(centre excitation >> 10).
 __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i16* __restrict__ x, i8* q_md0, i8* q_md1, i16* r16) {
-    const int lane = threadIdx.x & 31;
-    const bool act = lane < 12;
-    const int qz = act ? (lane >> 2) : 2;
-    const int s = lane & 3;
+    const int gl = threadIdx.x & (SB_NSQ_GW - 1);                 // gl inside the group
+    const int gsh = (threadIdx.x & 31) & ~(SB_NSQ_GW - 1);         // first warp gl of the group
+    const unsigned gm = SB_NSQ_GW == 32 ? 0xffffffffu : (0xffffu << gsh);
+    const bool act = gl < 12;
+    const int qz = act ? (gl >> 2) : 2;
+    const int s = gl & 3;
     i8* const Qout = qz == 0 ? (i8*)0 : (qz == 1 ? q_md0 : q_md1);
 
     const int sigtype = c->sigtype;
@@ -76,7 +87,7 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
     const int LSF_flag = c->NLSFInterpCoef_Q2 == 4 ? 0 : 1;
     const i32 seed0 = c->Seed;
     int lag0 = ns3[0].lagPrev;         // centre lag (gates the harmonic shaping of all three quantisers)
-    int lagq = ns3[qz].lagPrev;        // this lane's quantiser lag
+    int lagq = ns3[qz].lagPrev;        // this gl's quantiser lag
     int decisionDelay = imin(DD_DELAY, SUBFR);
     if (sigtype == 0) {
         for (int k = 0; k < NB_SUBFR; k++) decisionDelay = imin(decisionDelay, c->pitchL[k] - LTP_ORDER / 2 - 1);
@@ -87,18 +98,18 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
     // ---- load persistent state into shared memory / registers ----
     for (int qq = 0; qq < 3; qq++) {
         const NsqState* ns = &ns3[qq];
-        for (int i = lane; i < FRAME; i += 32) { S.xq[qq][i] = ns->xq[i]; S.xq[qq][FRAME + i] = 0; S.sLTP_shp_Q10[qq][i] = ns->sLTP_shp_Q10[i]; S.sLTP_shp_Q10[qq][FRAME + i] = 0; }
-        for (int i = lane; i < 2 * FRAME; i += 32) S.sLTP_Q16[qq][i] = 0;
-        if (lane < 2) S.sLTP_shp_Q10[qq][2 * FRAME + lane] = 0;
-        for (int i = lane; i < DD_DELAY * N_DD; i += 32) {
+        for (int i = gl; i < FRAME; i += SB_NSQ_GW) { S.xq[qq][i] = ns->xq[i]; S.sLTP_shp_Q10[qq][i] = ns->sLTP_shp_Q10[i]; S.sLTP_Q16[qq][i] = 0; }
+        if (gl < 2) { S.sLTP_shp_Q10[qq][FRAME + gl] = 0; S.xq[qq][FRAME + gl] = 0; }
+        if (gl == 0) S.sLTP_Q16[qq][FRAME] = 0;
+        for (int i = gl; i < DD_DELAY * N_DD; i += SB_NSQ_GW) {
             (&S.tabRand[qq][0][0])[i] = 0; (&S.tabXq[qq][0][0])[i] = 0; (&S.tabPred[qq][0][0])[i] = 0; (&S.tabShape[qq][0][0])[i] = 0;
             (&S.tabQ[qq][0][0])[i] = 0;
             if (qq == 0) (&S.tabExc[0][0])[i] = 0;
         }
     }
-    S.Gain_Q16[lane] = 0;
-    __syncwarp();
-    if (lane < N_DD) for (int qq = 0; qq < 3; qq++) S.tabShape[qq][0][lane] = ns3[qq].sLTP_shp_Q10[FRAME - 1];
+    for (int i = gl; i < DD_DELAY; i += SB_NSQ_GW) S.Gain_Q16[i] = 0;
+    __syncwarp(gm);
+    if (gl < N_DD) for (int qq = 0; qq < 3; qq++) S.tabShape[qq][0][gl] = ns3[qq].sLTP_shp_Q10[FRAME - 1];
     NsqLane L;
     {
         const NsqState* ns = &ns3[qz];
@@ -114,7 +125,7 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
         L.path = 0x5555555555555555ull * (u64)s;
     }
     i32 prev_inv_gain = ns3[qz].prev_inv_gain_Q16;
-    __syncwarp();
+    __syncwarp(gm);
 
     int smpl_buf_idx = 0, shp_idx = FRAME, ltp_idx = FRAME, subfr = 0;
 
@@ -123,10 +134,14 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
         i32 A_Q12[LPC_ORDER], AR_shp[SHAPE_ORDER], B_Q14[LTP_ORDER];
 #pragma unroll
         for (int j = 0; j < LPC_ORDER; j++) A_Q12[j] = A_Q12p[j];
+        // coefficients of the per-sample filters, pre-shifted into the high half-word for mlahi()
+        i32 A_hi[LPC_ORDER];
 #pragma unroll
-        for (int j = 0; j < SHAPE_ORDER; j++) AR_shp[j] = c->AR2_Q13[k * SHAPE_ORDER + j];
+        for (int j = 0; j < LPC_ORDER; j++) A_hi[j] = shl(A_Q12[j], 16);
 #pragma unroll
-        for (int j = 0; j < LTP_ORDER; j++) B_Q14[j] = c->LTPCoef_Q14[k * LTP_ORDER + j];
+        for (int j = 0; j < SHAPE_ORDER; j++) AR_shp[j] = shl(c->AR2_Q13[k * SHAPE_ORDER + j], 16);
+#pragma unroll
+        for (int j = 0; j < LTP_ORDER; j++) B_Q14[j] = shl(c->LTPCoef_Q14[k * LTP_ORDER + j], 16);
         i32 HarmShapeFIRPacked_Q14 = c->HarmShapeGain_Q14[k] >> 2;
         HarmShapeFIRPacked_Q14 |= shl(c->HarmShapeGain_Q14[k] >> 1, 16);
         const int sig_off = k * SUBFR;
@@ -140,18 +155,18 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                 if (k == 2) {
                     subfr = 0;
                     // reset of the delayed decisions: centre winner by its own RD, others penalised, delayed samples flushed
-                    i32 rd0 = shfl(L.RD, 0), rd1 = shfl(L.RD, 1), rd2 = shfl(L.RD, 2), rd3 = shfl(L.RD, 3);
+                    i32 rd0 = shfl(gm, L.RD, 0), rd1 = shfl(gm, L.RD, 1), rd2 = shfl(gm, L.RD, 2), rd3 = shfl(gm, L.RD, 3);
                     int Winner = 0; i32 RDmin = rd0;
                     if (rd1 < RDmin) { RDmin = rd1; Winner = 1; }
                     if (rd2 < RDmin) { RDmin = rd2; Winner = 2; }
                     if (rd3 < RDmin) { RDmin = rd3; Winner = 3; }
                     if (s != Winner) L.RD = addw(L.RD, SB_I32_MAX >> 4);
                     for (int qq = 0; qq < 3; qq++) {
-                        u64 wpath = shfl64(L.path, qq * 4 + Winner);
-                        nsqw_flush(S, lane, qq, wpath, smpl_buf_idx, decisionDelay, sig_off, shp_idx, ltp_idx,
+                        u64 wpath = shfl64(gm, L.path, qq * 4 + Winner);
+                        nsqw_flush(S, gl, qq, wpath, smpl_buf_idx, decisionDelay, sig_off, shp_idx, ltp_idx,
                                    qq == 0 ? (i8*)0 : (qq == 1 ? q_md0 : q_md1), qq == 0 ? r16 : (i16*)0, 0);
                     }
-                    __syncwarp();
+                    __syncwarp(gm);
                 }
                 // rewhitening of the LTP state with the new short-term predictor, scaled on the fly (decision of the
                 // reference: MA_Prediction over [start_idx, FRAME), of which only [FRAME - lag - 2, FRAME) is kept)
@@ -160,34 +175,34 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                 const int lagk = c->pitchL[k];
                 const int n0 = FRAME - lagk - LTP_ORDER / 2;
                 for (int qq = 0; qq < 3; qq++) {
-                    const i16* in = &S.xq[qq][k * SUBFR];
-                    for (int n = n0 + lane; n < FRAME; n += 32) {
+                    const i16* in = S.xq[qq];
+                    for (int n = n0 + gl; n < FRAME; n += SB_NSQ_GW) {
+                        const int j = k * SUBFR + n;   // logical position in [old frame | this frame]
                         i32 pred = 0;
 #pragma unroll
-                        for (int d = 0; d < LPC_ORDER; d++) pred = addw(pred, (i32)in[n - 1 - d] * A_Q12[d]);
-                        i32 o = sat16(rshift_round(subw(shl((i32)in[n], 12), pred), 12));
+                        for (int d = 0; d < LPC_ORDER; d++) pred = addw(pred, (i32)in[cix(j - 1 - d)] * A_Q12[d]);
+                        i32 o = sat16(rshift_round(subw(shl((i32)in[cix(j)], 12), pred), 12));
                         S.sLTP_Q16[qq][n] = smulwb(inv_gain_Q32, o);
                     }
                 }
                 ltp_idx = FRAME;
                 rewhite = 1;
-                __syncwarp();
+                __syncwarp(gm);
             }
         }
         // input scaling + state rescaling for the new gain
-        for (int i = lane; i < SUBFR; i += 32) S.x_sc_Q10[i] = smulbb(x[sig_off + i], inv_gain_Q16) >> 6;
         {
-            // prev_inv_gain is per quantiser; gather the three values so that every lane can scale every buffer
-            const i32 pg0 = shfl(prev_inv_gain, 0), pg1 = shfl(prev_inv_gain, 4), pg2 = shfl(prev_inv_gain, 8);
+            // prev_inv_gain is per quantiser; gather the three values so that every gl can scale every buffer
+            const i32 pg0 = shfl(gm, prev_inv_gain, 0), pg1 = shfl(gm, prev_inv_gain, 4), pg2 = shfl(gm, prev_inv_gain, 8);
             const int lagk = c->pitchL[k];
             for (int qq = 0; qq < 3; qq++) {
                 const i32 pg = qq == 0 ? pg0 : (qq == 1 ? pg1 : pg2);
                 if (inv_gain_Q16 != pg) {
                     const i32 gain_adj_Q16 = div32_varq(inv_gain_Q16, pg, 16);
-                    for (int i = shp_idx - SUBFR * NB_SUBFR + lane; i < shp_idx; i += 32) S.sLTP_shp_Q10[qq][i] = smulww(gain_adj_Q16, S.sLTP_shp_Q10[qq][i]);
+                    for (int i = gl; i < FRAME; i += SB_NSQ_GW) S.sLTP_shp_Q10[qq][i] = smulww(gain_adj_Q16, S.sLTP_shp_Q10[qq][i]);  // whole ring
                     if (!rewhite)
-                        for (int i = ltp_idx - lagk - LTP_ORDER / 2 + lane; i < ltp_idx; i += 32) S.sLTP_Q16[qq][i] = smulww(gain_adj_Q16, S.sLTP_Q16[qq][i]);
-                    for (int i = lane; i < DD_DELAY * N_DD; i += 32) {
+                        for (int i = ltp_idx - lagk - LTP_ORDER / 2 + gl; i < ltp_idx; i += SB_NSQ_GW) S.sLTP_Q16[qq][cix(i)] = smulww(gain_adj_Q16, S.sLTP_Q16[qq][cix(i)]);
+                    for (int i = gl; i < DD_DELAY * N_DD; i += SB_NSQ_GW) {
                         (&S.tabPred[qq][0][0])[i] = smulww(gain_adj_Q16, (&S.tabPred[qq][0][0])[i]);
                         (&S.tabShape[qq][0][0])[i] = smulww(gain_adj_Q16, (&S.tabShape[qq][0][0])[i]);
                     }
@@ -202,7 +217,7 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
             }
             prev_inv_gain = inv_gain_Q16;
         }
-        __syncwarp();
+        __syncwarp(gm);
 
         // ---- sub-frame constants of the description split ----
         const i32 Tilt_Q14 = c->Tilt_Q14[k], LF_shp_Q14 = c->LF_shp_Q14[k];
@@ -212,7 +227,7 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
         const i32 DeltaGains_p2 = inverse32_varq(imax(inv_gain_p2, 1), 32);
         const i32 offset_p1 = smulww(inv_gain_p1, offset_Q10), offset_p2 = smulww(inv_gain_p2, offset_Q10);
         const int swap = (subfr % 2) >= 1;
-        const int role1 = (qz == 1) != (swap != 0);  // this side lane plays "p1"
+        const int role1 = (qz == 1) != (swap != 0);  // this side gl plays "p1"
         const i32 ig = role1 ? inv_gain_p1 : inv_gain_p2;
         const i32 dg = role1 ? DeltaGains_p1 : DeltaGains_p2;
         const i32 of = role1 ? offset_p1 : offset_p2;
@@ -222,40 +237,40 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
         const i32 JL = 90000;
 
         for (int i = 0; i < SUBFR; i++) {
-            // ---- long-term prediction / harmonic shaping of this lane's quantiser ----
+            // ---- long-term prediction / harmonic shaping of this gl's quantiser ----
             i32 LTP_pred_Q14 = 0, n_LTP_Q14 = 0;
             if (sigtype == 0) {
-                const i32* pl = &S.sLTP_Q16[qz][pred_lag];
+                const i32* pl = S.sLTP_Q16[qz];
 #pragma unroll
-                for (int j = 0; j < LTP_ORDER; j++) LTP_pred_Q14 = smlawb(LTP_pred_Q14, pl[-j], B_Q14[j]);
+                for (int j = 0; j < LTP_ORDER; j++) LTP_pred_Q14 = mlahi(LTP_pred_Q14, pl[cix(pred_lag - j)], B_Q14[j]);
                 pred_lag++;
             }
             if (lag0 > 0) {
-                const i32* sl = &S.sLTP_shp_Q10[qz][shp_lag];
-                n_LTP_Q14 = smulwb(addw(sl[0], sl[-2]), HarmShapeFIRPacked_Q14);
-                n_LTP_Q14 = smlawt(n_LTP_Q14, sl[-1], HarmShapeFIRPacked_Q14);
+                const i32* sl = S.sLTP_shp_Q10[qz];
+                n_LTP_Q14 = smulwb(addw(sl[cix(shp_lag)], sl[cix(shp_lag - 2)]), HarmShapeFIRPacked_Q14);
+                n_LTP_Q14 = smlawt(n_LTP_Q14, sl[cix(shp_lag - 1)], HarmShapeFIRPacked_Q14);
                 n_LTP_Q14 = shl(n_LTP_Q14, 6);
                 shp_lag++;
             }
             // ---- short-term prediction, warped noise-shape feedback, low-frequency shaping ----
             i32 LPC_pred_Q10 = 0;
 #pragma unroll
-            for (int j = 0; j < LPC_ORDER; j++) LPC_pred_Q10 = smlawb(LPC_pred_Q10, L.lpc[j], A_Q12[j]);
+            for (int j = 0; j < LPC_ORDER; j++) LPC_pred_Q10 = mlahi(LPC_pred_Q10, L.lpc[j], A_hi[j]);
             i32 tmp2 = smlawb(L.lpc[0], L.sAR2[0], WARPING_Q16);
             i32 tmp1 = smlawb(L.sAR2[0], subw(L.sAR2[1], tmp2), WARPING_Q16);
             L.sAR2[0] = tmp2;
-            i32 n_AR_Q10 = smulwb(tmp2, AR_shp[0]);
+            i32 n_AR_Q10 = __mulhi(tmp2, AR_shp[0]);
 #pragma unroll
             for (int j = 2; j < SHAPE_ORDER; j += 2) {
                 tmp2 = smlawb(L.sAR2[j - 1], subw(L.sAR2[j], tmp1), WARPING_Q16);
                 L.sAR2[j - 1] = tmp1;
-                n_AR_Q10 = smlawb(n_AR_Q10, tmp1, AR_shp[j - 1]);
+                n_AR_Q10 = mlahi(n_AR_Q10, tmp1, AR_shp[j - 1]);
                 tmp1 = smlawb(L.sAR2[j], subw(L.sAR2[j + 1], tmp2), WARPING_Q16);
                 L.sAR2[j] = tmp2;
-                n_AR_Q10 = smlawb(n_AR_Q10, tmp2, AR_shp[j]);
+                n_AR_Q10 = mlahi(n_AR_Q10, tmp2, AR_shp[j]);
             }
             L.sAR2[SHAPE_ORDER - 1] = tmp1;
-            n_AR_Q10 = smlawb(n_AR_Q10, tmp1, AR_shp[SHAPE_ORDER - 1]);
+            n_AR_Q10 = mlahi(n_AR_Q10, tmp1, AR_shp[SHAPE_ORDER - 1]);
             n_AR_Q10 = n_AR_Q10 >> 1;
             n_AR_Q10 = smlawb(n_AR_Q10, L.LF_AR, Tilt_Q14);
             const i32 shape_new = S.tabShape[qz][smpl_buf_idx][(int)((L.path >> (2 * smpl_buf_idx)) & 3)];
@@ -266,65 +281,47 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
             t = addw(t, LPC_pred_Q10);
             t = subw(t, n_AR_Q10);
             t = subw(t, n_LF_Q10);
-            i32 r_Q10 = subw(S.x_sc_Q10[i], t);
+            i32 r_Q10 = subw(smulbb(x[sig_off + i], inv_gain_Q16) >> 6, t);   // x_sc_Q10, same address for the whole group
             L.Seed2 = lcg_rand(L.Seed2);
             L.Seed = lcg_rand(L.Seed);
             const i32 dither = L.Seed2 >> 31;
             r_Q10 = subw(r_Q10 ^ dither, dither);
 
-            // ---- side quantisers: two candidate levels each (Agora_Silk_RDCx1) ----
-            const i32 r_c = shfl(r_Q10, s);
+            // ---- side quantisers: two candidate levels each (Agora_Silk_RDCx1), branch-free ----
+            const i32 r_c = shfl(gm, r_Q10, s);   // the centre residual of this state column
             NsqCand c0, c1;
             c0.Q_Q0 = c0.Q_Q10 = c0.RD = c0.Rd_ind = 0; c1 = c0;
-            if (qz != 0) {
-                i32 q1, q2, rd1, rd2, rr;
-                i32 rq = smulww(ig, r_c);
-                i32 r_p = smulww(rdc_inv, r_Q10);
-                rq = subw(rq, of);
-                r_p = subw(r_p, of);
+            {
+                i32 rq = subw(smulww(ig, r_c), of);
+                const i32 r_p = subw(smulww(rdc_inv, r_Q10), of);
                 rq = limit(rq, -(64 << 10), 64 << 10);
-                if (rq < -1536) {
-                    q1 = shl(rshift_round(rq, 10), 10);
-                    rr = subw(r_p, q1);
-                    rd1 = smlabb(mulw(negw(addw(q1, of)), Lambda_Q10), rr, rr) >> 10;
-                    q2 = addw(q1, 1024);
-                    rr = subw(r_p, q2);
-                    rd2 = smlabb(mulw(negw(addw(q2, of)), Lambda_Q10), rr, rr) >> 10;
-                } else if (rq > 512) {
-                    q1 = shl(rshift_round(rq, 10), 10);
-                    rr = subw(r_p, q1);
-                    rd1 = smlabb(mulw(addw(q1, of), Lambda_Q10), rr, rr) >> 10;
-                    q2 = subw(q1, 1024);
-                    rr = subw(r_p, q2);
-                    rd2 = smlabb(mulw(addw(q2, of), Lambda_Q10), rr, rr) >> 10;
-                } else {
-                    q2 = 0;
-                    rr = r_p;
-                    rd2 = smlabb(mulw(of, Lambda_Q10), rr, rr) >> 10;
-                    q1 = -1024;
-                    rr = subw(r_p, q1);
-                    rd1 = smlabb(mulw(negw(addw(q1, of)), Lambda_Q10), rr, rr) >> 10;
-                }
-                if (rd1 < rd2) {
-                    c0.RD = addw(L.RD, rd1); c1.RD = addw(L.RD, rd2);
-                    c0.Q_Q0 = (i8)(q1 >> 10); c1.Q_Q0 = (i8)(q2 >> 10);
-                    c0.Q_Q10 = addw(of, q1); c1.Q_Q10 = addw(of, q2);
-                    c0.Rd_ind = rd1; c1.Rd_ind = rd2;
-                } else {
-                    c0.RD = addw(L.RD, rd2); c1.RD = addw(L.RD, rd1);
-                    c0.Q_Q0 = (i8)(q2 >> 10); c1.Q_Q0 = (i8)(q1 >> 10);
-                    c0.Q_Q10 = addw(of, q2); c1.Q_Q10 = addw(of, q1);
-                    c0.Rd_ind = rd2; c1.Rd_ind = rd1;
+                const bool lo = rq < -1536, hi = rq > 512;
+                const i32 qr = shl(rshift_round(rq, 10), 10);
+                const i32 q1 = (lo || hi) ? qr : -1024;
+                const i32 q2 = lo ? addw(q1, 1024) : (hi ? subw(q1, 1024) : 0);
+                i32 t1 = addw(q1, of), t2 = addw(q2, of);      // rate term: |level + offset| with the sign the level implies
+                if (!hi) t1 = negw(t1);
+                if (lo) t2 = negw(t2);
+                const i32 rr1 = subw(r_p, q1), rr2 = subw(r_p, q2);
+                const i32 rd1 = smlabb(mulw(t1, Lambda_Q10), rr1, rr1) >> 10;
+                const i32 rd2 = smlabb(mulw(t2, Lambda_Q10), rr2, rr2) >> 10;
+                if (qz != 0) {
+                    const bool f = rd1 < rd2;
+                    const i32 qa = f ? q1 : q2, qb = f ? q2 : q1, ra = f ? rd1 : rd2, rb = f ? rd2 : rd1;
+                    c0.RD = addw(L.RD, ra); c1.RD = addw(L.RD, rb);
+                    c0.Q_Q0 = qa >> 10; c1.Q_Q0 = qb >> 10;
+                    c0.Q_Q10 = addw(of, qa); c1.Q_Q10 = addw(of, qb);
+                    c0.Rd_ind = ra; c1.Rd_ind = rb;
                 }
             }
-            // ---- centre: the four composites of the side candidates (Agora_Silk_CenterRD) ----
-            int w12;  // w1 | w2 << 2, defined on centre lanes
+            // ---- the four composites of the side candidates (Agora_Silk_CenterRD), evaluated by all three lanes of the
+            //      column so that the sides know the two surviving composites without a round trip ----
             {
-                const i32 a0 = shfl(c0.Q_Q10, 4 + s), a1 = shfl(c1.Q_Q10, 4 + s), b0 = shfl(c0.Q_Q10, 8 + s), b1 = shfl(c1.Q_Q10, 8 + s);
-                const i32 ra0 = shfl(c0.Rd_ind, 4 + s), ra1 = shfl(c1.Rd_ind, 4 + s), rb0 = shfl(c0.Rd_ind, 8 + s), rb1 = shfl(c1.Rd_ind, 8 + s);
+                const i32 a0 = shfl(gm, c0.Q_Q10, 4 + s), a1 = shfl(gm, c1.Q_Q10, 4 + s), b0 = shfl(gm, c0.Q_Q10, 8 + s), b1 = shfl(gm, c1.Q_Q10, 8 + s);
+                const i32 ra0 = shfl(gm, c0.Rd_ind, 4 + s), ra1 = shfl(gm, c1.Rd_ind, 4 + s), rb0 = shfl(gm, c0.Rd_ind, 8 + s), rb1 = shfl(gm, c1.Rd_ind, 8 + s);
                 i32 qx[4], rdx[4];
                 qx[0] = addw(a0, b0); qx[1] = addw(a1, b1); qx[2] = addw(a0, b1); qx[3] = addw(a1, b0);
-                const i32 r_temp = subw(r_Q10, offset_c);
+                const i32 r_temp = subw(r_c, offset_c);
 #pragma unroll
                 for (int m = 0; m < 4; m++) {
                     i32 rr = subw(r_temp, qx[m]);
@@ -332,10 +329,11 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                     if (qx[m] < 0) tt = negw(tt);
                     rdx[m] = smlabb(mulw(tt, Lambda_Q10), rr, rr) >> 10;
                 }
-                rdx[0] = addw(addw(rdx[0], smulww(JL, ra0)), smulww(JL, rb0));
-                rdx[1] = addw(addw(rdx[1], smulww(JL, ra1)), smulww(JL, rb1));
-                rdx[2] = addw(addw(rdx[2], smulww(JL, ra0)), smulww(JL, rb1));
-                rdx[3] = addw(addw(rdx[3], smulww(JL, ra1)), smulww(JL, rb0));
+                const i32 ja0 = smulww(JL, ra0), ja1 = smulww(JL, ra1), jb0 = smulww(JL, rb0), jb1 = smulww(JL, rb1);
+                rdx[0] = addw(addw(rdx[0], ja0), jb0);
+                rdx[1] = addw(addw(rdx[1], ja1), jb1);
+                rdx[2] = addw(addw(rdx[2], ja0), jb1);
+                rdx[3] = addw(addw(rdx[3], ja1), jb0);
                 i32 mn = rdx[0]; int w1 = 0, w2;
                 if (rdx[1] < mn) { mn = rdx[1]; w1 = 1; }
                 if (rdx[2] < mn) { mn = rdx[2]; w1 = 2; }
@@ -350,7 +348,6 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                     if (rdx[2] < mn && w1 != 2) { mn = rdx[2]; w2 = 2; }
                     if (rdx[3] < mn && w1 != 3) { mn = rdx[3]; w2 = 3; }
                 }
-                w12 = w1 | (w2 << 2);
                 if (qz == 0) {
                     const i32 qw1 = w1 == 0 ? qx[0] : (w1 == 1 ? qx[1] : (w1 == 2 ? qx[2] : qx[3]));
                     const i32 qw2 = w2 == 0 ? qx[0] : (w2 == 1 ? qx[1] : (w2 == 2 ? qx[2] : qx[3]));
@@ -360,13 +357,8 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                     c0.Q_Q0 = qw1 >> 10; c1.Q_Q0 = qw2 >> 10;
                     c0.Q_Q10 = qw1; c1.Q_Q10 = qw2;
                     c0.Rd_ind = rw1; c1.Rd_ind = rw2;
-                }
-            }
-            {
-                // side lanes re-order their candidates to match the two surviving composites
-                const int ww = shfl(w12, s);
-                if (qz != 0) {
-                    const int w1 = ww & 3, w2 = (ww >> 2) & 3;
+                } else {
+                    // side lanes re-order their candidates to match the two surviving composites
                     const int sel = qz == 1 ? 0xA : 0x6;  // a(c) / b(c): candidate index inside composite c
                     const int i1 = (sel >> w1) & 1, i2 = (sel >> w2) & 1;
                     const NsqCand o0 = c0, o1 = c1;
@@ -393,78 +385,91 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
             smpl_buf_idx = (smpl_buf_idx - 1) & DD_MASK;
             const int last_smple_idx = (smpl_buf_idx + decisionDelay) & DD_MASK;
 
-            // ---- Agora_Silk_JudgeWinner: joint winner, de-synchronised states penalised, worst-first / best-second swap ----
+            // ---- Agora_Silk_JudgeWinner + Agora_Silk_GetWinner.  The joint RD of every column (first and second
+            //      candidates) and the centre RDs are gathered once; penalties and replacements are then tracked in
+            //      registers by every lane, so the loop and the final winner need no further exchange. ----
+            int Winner;
             {
-                i32 jr = qz == 0 ? c0.RD : smulww(c0.RD, JL);
-                i32 joint = addw(addw(jr, __shfl_down_sync(SB_FULL, jr, 4)), __shfl_down_sync(SB_FULL, jr, 8));
-                const i32 j0 = shfl(joint, 0), j1 = shfl(joint, 1), j2 = shfl(joint, 2), j3 = shfl(joint, 3);
-                int Winner = 0; i32 RDmin = j0;
-                if (j1 < RDmin) { RDmin = j1; Winner = 1; }
-                if (j2 < RDmin) { RDmin = j2; Winner = 2; }
-                if (j3 < RDmin) { RDmin = j3; Winner = 3; }
+                const i32 jr0 = qz == 0 ? c0.RD : smulww(c0.RD, JL);
+                const i32 jr1 = qz == 0 ? c1.RD : smulww(c1.RD, JL);
+                const i32 jn0 = addw(addw(jr0, __shfl_down_sync(gm, jr0, 4, SB_NSQ_GW)), __shfl_down_sync(gm, jr0, 8, SB_NSQ_GW));
+                const i32 jn1 = addw(addw(jr1, __shfl_down_sync(gm, jr1, 4, SB_NSQ_GW)), __shfl_down_sync(gm, jr1, 8, SB_NSQ_GW));
+                i32 j0[4], j1[4], ra[4], rb[4];   // joint RD via first / second candidate; centre RD of first / second candidate
+#pragma unroll
+                for (int m = 0; m < 4; m++) { j0[m] = shfl(gm, jn0, m); j1[m] = shfl(gm, jn1, m); ra[m] = shfl(gm, c0.RD, m); rb[m] = shfl(gm, c1.RD, m); }
+                int W0 = 0; i32 RDmin = j0[0];
+                if (j0[1] < RDmin) { RDmin = j0[1]; W0 = 1; }
+                if (j0[2] < RDmin) { RDmin = j0[2]; W0 = 2; }
+                if (j0[3] < RDmin) { RDmin = j0[3]; W0 = 3; }
                 const i32 rs = S.tabRand[qz][last_smple_idx][(int)((L.path >> (2 * last_smple_idx)) & 3)];
-                const i32 wrs = shfl(rs, qz * 4 + Winner);
-                const unsigned bal = __ballot_sync(SB_FULL, act && rs != wrs);
+                const i32 wrs = shfl(gm, rs, qz * 4 + W0);
+                const unsigned bal = (__ballot_sync(gm, act && rs != wrs) >> gsh) & 0xffffu;
                 const unsigned mstate = (bal | (bal >> 4) | (bal >> 8)) & 0xF;
                 int RandSyncCtl = __popc(mstate);
-                if (qz == 0 && ((mstate >> s) & 1)) { c0.RD = addw(c0.RD, SB_I32_MAX >> 4); c1.RD = addw(c1.RD, SB_I32_MAX >> 4); }
+                const i32 PEN = SB_I32_MAX >> 4;
+#pragma unroll
+                for (int m = 0; m < 4; m++)
+                    if ((mstate >> m) & 1) { j0[m] = addw(j0[m], PEN); j1[m] = addw(j1[m], PEN); ra[m] = addw(ra[m], PEN); rb[m] = addw(rb[m], PEN); }
+                if (qz == 0 && ((mstate >> s) & 1)) { c0.RD = addw(c0.RD, PEN); c1.RD = addw(c1.RD, PEN); }
                 do {
-                    const i32 a0 = shfl(c0.RD, 0), a1 = shfl(c0.RD, 1), a2 = shfl(c0.RD, 2), a3 = shfl(c0.RD, 3);
-                    const i32 b0 = shfl(c1.RD, 0), b1 = shfl(c1.RD, 1), b2 = shfl(c1.RD, 2), b3 = shfl(c1.RD, 3);
-                    i32 RDmax = a0, RDmin2 = b0; int imx = 0, imn = 0;
-                    if (a1 > RDmax) { RDmax = a1; imx = 1; }
-                    if (a2 > RDmax) { RDmax = a2; imx = 2; }
-                    if (a3 > RDmax) { RDmax = a3; imx = 3; }
-                    if (b1 < RDmin2) { RDmin2 = b1; imn = 1; }
-                    if (b2 < RDmin2) { RDmin2 = b2; imn = 2; }
-                    if (b3 < RDmin2) { RDmin2 = b3; imn = 3; }
+                    i32 RDmax = ra[0], RDmin2 = rb[0]; int imx = 0, imn = 0;
+                    if (ra[1] > RDmax) { RDmax = ra[1]; imx = 1; }
+                    if (ra[2] > RDmax) { RDmax = ra[2]; imx = 2; }
+                    if (ra[3] > RDmax) { RDmax = ra[3]; imx = 3; }
+                    if (rb[1] < RDmin2) { RDmin2 = rb[1]; imn = 1; }
+                    if (rb[2] < RDmin2) { RDmin2 = rb[2]; imn = 2; }
+                    if (rb[3] < RDmin2) { RDmin2 = rb[3]; imn = 3; }
                     if (RDmin2 < RDmax) {
                         const int src = qz * 4 + imn;
                         const bool tgt = (s == imx);
-                        i32 v;
+                        const int from = tgt ? src : gl;   // everybody else reads itself: no select after the shuffle
 #pragma unroll
-                        for (int j = 0; j < SHAPE_ORDER; j++) { v = shfl(L.sAR2[j], src); if (tgt) L.sAR2[j] = v; }
+                        for (int j = 0; j < SHAPE_ORDER; j++) L.sAR2[j] = shfl(gm, L.sAR2[j], from);
 #pragma unroll
-                        for (int j = 0; j < LPC_ORDER; j++) { v = shfl(L.lpc[j], src); if (tgt) L.lpc[j] = v; }
-                        v = shfl(L.LF_AR, src); if (tgt) L.LF_AR = v;
-                        v = shfl(L.Seed, src); if (tgt) L.Seed = v;
-                        v = shfl(L.Seed2, src); if (tgt) L.Seed2 = v;
-                        v = shfl(L.SeedInit2, src); if (tgt) L.SeedInit2 = v;
-                        v = shfl(L.RD, src); if (tgt) L.RD = v;
-                        { u64 p = shfl64(L.path, src); if (tgt) L.path = p; }
+                        for (int j = 0; j < LPC_ORDER; j++) L.lpc[j] = shfl(gm, L.lpc[j], from);
+                        L.LF_AR = shfl(gm, L.LF_AR, from);
+                        L.Seed = shfl(gm, L.Seed, from);
+                        L.Seed2 = shfl(gm, L.Seed2, from);
+                        L.SeedInit2 = shfl(gm, L.SeedInit2, from);
+                        L.RD = shfl(gm, L.RD, from);
+                        L.path = shfl64(gm, L.path, from);
                         // first candidate of the replaced state <- second candidate of the survivor
-                        v = shfl(c1.Q_Q0, src); if (tgt) c0.Q_Q0 = v;
-                        v = shfl(c1.RD, src); if (tgt) c0.RD = v;
-                        v = shfl(c1.xq_Q14, src); if (tgt) c0.xq_Q14 = v;
-                        v = shfl(c1.LF_AR, src); if (tgt) c0.LF_AR = v;
-                        v = shfl(c1.shp, src); if (tgt) c0.shp = v;
-                        v = shfl(c1.exc16, src); if (tgt) c0.exc16 = v;
-                        v = shfl(c1.exc, src); if (tgt) c0.exc = v;
+                        i32 v;
+                        v = shfl(gm, c1.Q_Q0, src); if (tgt) c0.Q_Q0 = v;
+                        v = shfl(gm, c1.RD, src); if (tgt) c0.RD = v;
+                        v = shfl(gm, c1.xq_Q14, src); if (tgt) c0.xq_Q14 = v;
+                        v = shfl(gm, c1.LF_AR, src); if (tgt) c0.LF_AR = v;
+                        v = shfl(gm, c1.shp, src); if (tgt) c0.shp = v;
+                        v = shfl(gm, c1.exc16, src); if (tgt) c0.exc16 = v;
+                        v = shfl(gm, c1.exc, src); if (tgt) c0.exc = v;
+                        // what every lane knows about the columns afterwards
+#pragma unroll
+                        for (int m = 0; m < 4; m++) if (m == imx) {
+                            ra[m] = imn == 0 ? rb[0] : (imn == 1 ? rb[1] : (imn == 2 ? rb[2] : rb[3]));
+                            j0[m] = imn == 0 ? j1[0] : (imn == 1 ? j1[1] : (imn == 2 ? j1[2] : j1[3]));
+                        }
                     }
                 } while (--RandSyncCtl > 0);
+                Winner = 0; RDmin = j0[0];
+                if (j0[1] < RDmin) { RDmin = j0[1]; Winner = 1; }
+                if (j0[2] < RDmin) { RDmin = j0[2]; Winner = 2; }
+                if (j0[3] < RDmin) { RDmin = j0[3]; Winner = 3; }
             }
-            // ---- Agora_Silk_GetWinner: emit the sample that is decisionDelay old from the joint winner ----
+            // ---- emit the sample that is decisionDelay old from the joint winner ----
             {
-                i32 jr = qz == 0 ? c0.RD : smulww(c0.RD, JL);
-                i32 joint = addw(addw(jr, __shfl_down_sync(SB_FULL, jr, 4)), __shfl_down_sync(SB_FULL, jr, 8));
-                const i32 j0 = shfl(joint, 0), j1 = shfl(joint, 1), j2 = shfl(joint, 2), j3 = shfl(joint, 3);
-                int Winner = 0; i32 RDmin = j0;
-                if (j1 < RDmin) { RDmin = j1; Winner = 1; }
-                if (j2 < RDmin) { RDmin = j2; Winner = 2; }
-                if (j3 < RDmin) { RDmin = j3; Winner = 3; }
                 if ((subfr > 0 || i >= decisionDelay) && act && s == Winner) {
                     const int sl = (int)((L.path >> (2 * last_smple_idx)) & 3);
                     const int o = sig_off + i - decisionDelay;
                     if (Qout) Qout[o] = S.tabQ[qz][last_smple_idx][sl];
                     if (qz == 0) r16[o] = (i16)(S.tabExc[last_smple_idx][sl] >> 10);
-                    S.xq[qz][FRAME + o] = (i16)sat16(rshift_round(smulww(S.tabXq[qz][last_smple_idx][sl], S.Gain_Q16[last_smple_idx]), 10));
-                    S.sLTP_shp_Q10[qz][shp_idx - decisionDelay] = S.tabShape[qz][last_smple_idx][sl];
-                    S.sLTP_Q16[qz][ltp_idx - decisionDelay] = S.tabPred[qz][last_smple_idx][sl];
+                    S.xq[qz][o] = (i16)sat16(rshift_round(smulww(S.tabXq[qz][last_smple_idx][sl], S.Gain_Q16[last_smple_idx]), 10));
+                    S.sLTP_shp_Q10[qz][cix(shp_idx - decisionDelay)] = S.tabShape[qz][last_smple_idx][sl];
+                    S.sLTP_Q16[qz][cix(ltp_idx - decisionDelay)] = S.tabPred[qz][last_smple_idx][sl];
                 }
                 shp_idx++;
                 ltp_idx++;
             }
-            __syncwarp();  // history reads of this sample (position last_smple_idx may alias smpl_buf_idx) before the writes below
+            __syncwarp(gm);  // history reads of this sample (position last_smple_idx may alias smpl_buf_idx) before the writes below
             // ---- Agora_Silk_Update_DelDecState ----
             {
                 L.LF_AR = c0.LF_AR;
@@ -482,28 +487,28 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                     if (qz == 0) S.tabExc[smpl_buf_idx][s] = c0.exc;
                 }
                 L.path = (L.path & ~((u64)3 << (2 * smpl_buf_idx))) | ((u64)s << (2 * smpl_buf_idx));
-                if (lane == 0) S.Gain_Q16[smpl_buf_idx] = Gain_Q16;
+                if (gl == 0) S.Gain_Q16[smpl_buf_idx] = Gain_Q16;
             }
-            __syncwarp();
+            __syncwarp(gm);
         }
         subfr++;
     }
 
     // ---- frame end: winner by the centre's own RD, flush, write the persistent state back ----
     {
-        i32 rd0 = shfl(L.RD, 0), rd1 = shfl(L.RD, 1), rd2 = shfl(L.RD, 2), rd3 = shfl(L.RD, 3);
+        i32 rd0 = shfl(gm, L.RD, 0), rd1 = shfl(gm, L.RD, 1), rd2 = shfl(gm, L.RD, 2), rd3 = shfl(gm, L.RD, 3);
         int Winner = 0; i32 RDmin = rd0;
         if (rd1 < RDmin) { RDmin = rd1; Winner = 1; }
         if (rd2 < RDmin) { RDmin = rd2; Winner = 2; }
         if (rd3 < RDmin) { RDmin = rd3; Winner = 3; }
-        const i32 seed_out = shfl(L.SeedInit2, Winner);
-        if (lane == 0) c->Seed = seed_out;
+        const i32 seed_out = shfl(gm, L.SeedInit2, Winner);
+        if (gl == 0) c->Seed = seed_out;
         for (int qq = 0; qq < 3; qq++) {
-            u64 wpath = shfl64(L.path, qq * 4 + Winner);
-            nsqw_flush(S, lane, qq, wpath, smpl_buf_idx, decisionDelay, FRAME, shp_idx, ltp_idx,
+            u64 wpath = shfl64(gm, L.path, qq * 4 + Winner);
+            nsqw_flush(S, gl, qq, wpath, smpl_buf_idx, decisionDelay, FRAME, shp_idx, ltp_idx,
                        qq == 0 ? (i8*)0 : (qq == 1 ? q_md0 : q_md1), qq == 0 ? r16 : (i16*)0, 1);
         }
-        __syncwarp();
+        __syncwarp(gm);
         if (act && s == Winner) {
             NsqState* ns = &ns3[qz];
 #pragma unroll
@@ -516,9 +521,9 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
         }
         for (int qq = 0; qq < 3; qq++) {
             NsqState* ns = &ns3[qq];
-            for (int i = lane; i < FRAME; i += 32) { ns->xq[i] = S.xq[qq][FRAME + i]; ns->sLTP_shp_Q10[i] = S.sLTP_shp_Q10[qq][FRAME + i]; }
+            for (int i = gl; i < FRAME; i += SB_NSQ_GW) { ns->xq[i] = S.xq[qq][i]; ns->sLTP_shp_Q10[i] = S.sLTP_shp_Q10[qq][i]; }
         }
-        __syncwarp();
+        __syncwarp(gm);
     }
 }
 

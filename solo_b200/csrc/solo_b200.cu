@@ -54,12 +54,19 @@ __global__ void __launch_bounds__(SB_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_kern
     enc_packet_analysis(&states[s], &W, x, &scratch[s]);
 }
 
-#define SB_NSQ_WARPS 4
-__global__ void __launch_bounds__(SB_NSQ_WARPS * 32) sb_enc_nsq_kernel(EncState* states, EncScratch* scratch, int n) {
+#ifndef SB_NSQ_WARPS
+#define SB_NSQ_WARPS 1      // one warp = two streams = 2 x 12.2 KB of shared memory; 9 blocks (18 streams) per SM
+#endif
+#ifndef SB_NSQ_MINB
+#define SB_NSQ_MINB 1
+#endif
+#define SB_NSQ_SPB (SB_NSQ_WARPS * (32 / SB_NSQ_GW))   // streams per block
+__global__ void __launch_bounds__(SB_NSQ_WARPS * 32, SB_NSQ_MINB) sb_enc_nsq_kernel(EncState* states, EncScratch* scratch, int n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    NsqSmem* S = reinterpret_cast<NsqSmem*>(smem_raw) + (threadIdx.x >> 5);
-    int s = blockIdx.x * SB_NSQ_WARPS + (threadIdx.x >> 5);
-    if (s >= n) return;
+    const int g = threadIdx.x / SB_NSQ_GW;                  // lane group inside the block = stream slot
+    NsqSmem* S = reinterpret_cast<NsqSmem*>(smem_raw) + g;
+    int s = blockIdx.x * SB_NSQ_SPB + g;
+    if (s >= n) return;                                     // whole groups leave; collectives name their own group
     EncScratch* scr = &scratch[s];
     for (int f = 0; f < 2; f++)
         nsq_del_dec_warp(*S, states[s].nsq, &scr->c[f], scr->xfw[f], scr->q_md[f][0], scr->q_md[f][1], scr->r16[f]);
@@ -213,7 +220,7 @@ solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_e
     if (cudaMalloc(&b->d_states, sizeof(EncState) * (size_t)n_streams) != cudaSuccess ||
         cudaMalloc(&b->d_scratch, sizeof(EncScratch) * (size_t)n_streams) != cudaSuccess ||
         cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaFuncSetAttribute(sb_enc_nsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SB_NSQ_WARPS * sizeof(NsqSmem))) != cudaSuccess) {
+        cudaFuncSetAttribute(sb_enc_nsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SB_NSQ_SPB * sizeof(NsqSmem))) != cudaSuccess) {
         fail("enc_batch_create", cudaGetLastError());
         delete b; return nullptr;
     }
@@ -233,7 +240,7 @@ int solo_b200_enc_batch_encode_device(solo_b200_enc_batch* b, const int16_t* d_p
     sb_enc_analysis_kernel<<<(b->n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states, b->d_scratch, d_pcm, b->n);
     prof_end(st, &ev);
     prof_begin(st, 1, &ev);
-    sb_enc_nsq_kernel<<<(b->n + SB_NSQ_WARPS - 1) / SB_NSQ_WARPS, SB_NSQ_WARPS * 32, SB_NSQ_WARPS * sizeof(NsqSmem), st>>>(b->d_states, b->d_scratch, b->n);
+    sb_enc_nsq_kernel<<<(b->n + SB_NSQ_SPB - 1) / SB_NSQ_SPB, SB_NSQ_WARPS * 32, SB_NSQ_SPB * sizeof(NsqSmem), st>>>(b->d_states, b->d_scratch, b->n);
     prof_end(st, &ev);
     prof_begin(st, 2, &ev);
     sb_enc_finish_kernel<<<(b->n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states, b->d_scratch, d_bits, cap, d_nbytes, b->n);
