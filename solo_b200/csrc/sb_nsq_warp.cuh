@@ -334,29 +334,21 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                 rdx[1] = addw(addw(rdx[1], ja1), jb1);
                 rdx[2] = addw(addw(rdx[2], ja0), jb1);
                 rdx[3] = addw(addw(rdx[3], ja1), jb0);
-                i32 mn = rdx[0]; int w1 = 0, w2;
-                if (rdx[1] < mn) { mn = rdx[1]; w1 = 1; }
-                if (rdx[2] < mn) { mn = rdx[2]; w1 = 2; }
-                if (rdx[3] < mn) { mn = rdx[3]; w1 = 3; }
-                if (w1 == 0) {
-                    mn = rdx[1]; w2 = 1;
-                    if (rdx[2] < mn) { mn = rdx[2]; w2 = 2; }
-                    if (rdx[3] < mn) { mn = rdx[3]; w2 = 3; }
-                } else {
-                    mn = rdx[0]; w2 = 0;
-                    if (rdx[1] < mn && w1 != 1) { mn = rdx[1]; w2 = 1; }
-                    if (rdx[2] < mn && w1 != 2) { mn = rdx[2]; w2 = 2; }
-                    if (rdx[3] < mn && w1 != 3) { mn = rdx[3]; w2 = 3; }
-                }
+                // best and second-best composite (strict "<": the lowest index wins ties, as in the reference's scans)
+                i32 mn = rdx[0], q_w1 = qx[0]; int w1 = 0;
+                if (rdx[1] < mn) { mn = rdx[1]; w1 = 1; q_w1 = qx[1]; }
+                if (rdx[2] < mn) { mn = rdx[2]; w1 = 2; q_w1 = qx[2]; }
+                if (rdx[3] < mn) { mn = rdx[3]; w1 = 3; q_w1 = qx[3]; }
+                const bool e0 = w1 == 0;
+                i32 mn2 = e0 ? rdx[1] : rdx[0], q_w2 = e0 ? qx[1] : qx[0]; int w2 = e0 ? 1 : 0;
+                if (w1 != 1 && rdx[1] < mn2) { mn2 = rdx[1]; w2 = 1; q_w2 = qx[1]; }
+                if (w1 != 2 && rdx[2] < mn2) { mn2 = rdx[2]; w2 = 2; q_w2 = qx[2]; }
+                if (w1 != 3 && rdx[3] < mn2) { mn2 = rdx[3]; w2 = 3; q_w2 = qx[3]; }
                 if (qz == 0) {
-                    const i32 qw1 = w1 == 0 ? qx[0] : (w1 == 1 ? qx[1] : (w1 == 2 ? qx[2] : qx[3]));
-                    const i32 qw2 = w2 == 0 ? qx[0] : (w2 == 1 ? qx[1] : (w2 == 2 ? qx[2] : qx[3]));
-                    const i32 rw1 = w1 == 0 ? rdx[0] : (w1 == 1 ? rdx[1] : (w1 == 2 ? rdx[2] : rdx[3]));
-                    const i32 rw2 = w2 == 0 ? rdx[0] : (w2 == 1 ? rdx[1] : (w2 == 2 ? rdx[2] : rdx[3]));
-                    c0.RD = addw(L.RD, rw1); c1.RD = addw(L.RD, rw2);
-                    c0.Q_Q0 = qw1 >> 10; c1.Q_Q0 = qw2 >> 10;
-                    c0.Q_Q10 = qw1; c1.Q_Q10 = qw2;
-                    c0.Rd_ind = rw1; c1.Rd_ind = rw2;
+                    c0.RD = addw(L.RD, mn); c1.RD = addw(L.RD, mn2);
+                    c0.Q_Q0 = q_w1 >> 10; c1.Q_Q0 = q_w2 >> 10;
+                    c0.Q_Q10 = q_w1; c1.Q_Q10 = q_w2;
+                    c0.Rd_ind = mn; c1.Rd_ind = mn2;
                 } else {
                     // side lanes re-order their candidates to match the two surviving composites
                     const int sel = qz == 1 ? 0xA : 0x6;  // a(c) / b(c): candidate index inside composite c
