@@ -18,7 +18,7 @@
 
 #ifdef __CUDACC__
 #define SB_HD __host__ __device__ __forceinline__
-#define SB_FN __host__ __device__
+#define SB_FN __host__ __device__ inline
 #else
 #define SB_HD inline
 #define SB_FN inline

@@ -9,6 +9,7 @@
 #include "sb_enc_pred.cuh"
 #include "sb_enc_shape.cuh"
 #include "sb_nsq.cuh"
+#include "sb_par.cuh"
 
 namespace sb {
 
@@ -107,7 +108,7 @@ SB_FN i32 hb_lsp_quant(i32* lsp) {
 // ---- AGR_Bwe_encode_frame_FIX (AGR_BWE_encode_frame_FIX.c:8-82), split in two because the gain needs the low-band
 // excitation produced by the noise-shaping quantiser: (1) buffer update, LPC analysis, LSP VQ, per-sub-frame residual
 // energy of the high band; (2) gain = 16*sqrt(E_hb)/sqrt(E_lb_exc), 32-level VQ, bit packing (12 + 4*5 bits, MSB first).
-SB_FN void hb_analyse_frame(EncState* st, const i16* high, i32* lsp_idx_out, i32* nrg0_out) {
+SB_FN void hb_analyse_frame(EncCore* st, const i16* high, i32* lsp_idx_out, i32* nrg0_out) {
     const int LPCF = 80;
     for (int i = 0; i < HB_FRAME; i++) st->x_hb_buf[HB_FRAME + 40 + i] = high[i];
     // AGR_Sate_find_HB_LPC_FIX: 4 blocks of (80 + 8) samples, hop 80, starting 8 samples before the frame
@@ -173,49 +174,77 @@ struct EncScratch {
     i32 dtx_drop;
 };
 
+// Working set of stage A for one stream.  Warp-per-stream kernel: shared memory; thread-per-stream / host: local memory.
+#ifndef SB_ANA_ARENA
+#define SB_ANA_ARENA 8192
+#endif
 struct EncAnalysisWork {
     i16 low[PACKET / 2], high[PACKET / 2];
     i16 pIn_HP[FRAME];
     i16 res_pitch[2 * FRAME + LA_PITCH];
+    EncCtrl c;                 // control of the frame being analysed (copied to EncScratch when the frame is done)
+    i16 xfw[FRAME];
+    i32 vadFlag;
+    alignas(16) unsigned char arena_mem[SB_ANA_ARENA];
 };
 
-// SKP_Silk_encode_frame_FIX (encode_frame_FIX.c:34-131, 151-165, 199-208) up to the quantiser, for one frame
-SB_FN void encode_frame_analysis(EncState* st, EncAnalysisWork* W, EncCtrl* c, i16* xfw, i32* vadFlag_out, const i16* pIn, int frame_in_packet) {
-    c->Seed = st->frameCounter++ & 3;
+// SKP_Silk_encode_frame_FIX (encode_frame_FIX.c:34-131, 151-165, 199-208) up to the quantiser, for one frame.
+// Cooperative: called by every lane of the stream; routines that are still single-lane are wrapped in SB_SERIAL.
+SB_FN void encode_frame_analysis(EncCore* st, EncAnalysisWork* W, Arena* A, const i16* pIn, int frame_in_packet) {
+    EncCtrl* c = &W->c;
     i16* x_frame = st->x_buf + FRAME;
-    vad_get_sa_q8(&st->vad, &st->speech_activity_Q8, c->input_quality_bands_Q15, &c->input_tilt_Q15, pIn);
-    hp_variable_cutoff(st, c, W->pIn_HP, pIn);
-    for (int i = 0; i < FRAME; i++) x_frame[LA_SHAPE + i] = W->pIn_HP[i];  // LP_variable_cutoff is a copy (transition_frame_no == 0)
-    find_pitch_lags(st, c, W->res_pitch, x_frame);
-    noise_shape_analysis(st, c, W->res_pitch + FRAME, x_frame);
-    prefilter(st, c, xfw, x_frame);
-    find_pred_coefs(st, c, W->res_pitch, frame_in_packet);
-    process_gains(st, c, frame_in_packet);
-    if (st->speech_activity_Q8 < SB_FIXC(0.1f, 8)) {
-        st->vadFlag = 0;
-        st->noSpeechCounter++;
-        if (st->noSpeechCounter > 5) st->inDTX = 1;
-        if (st->noSpeechCounter > 20 + 5) { st->noSpeechCounter = 5; st->inDTX = 0; }
-    } else {
-        st->noSpeechCounter = 0; st->inDTX = 0; st->vadFlag = 1;
-    }
-    *vadFlag_out = st->vadFlag;
-    for (int i = 0; i < FRAME + LA_SHAPE; i++) st->x_buf[i] = st->x_buf[FRAME + i];
-    st->prev_sigtype = c->sigtype;
-    st->prevLag = c->pitchL[NB_SUBFR - 1];
-    st->first_frame_after_reset = 0;
+    SB_SERIAL(
+        c->Seed = st->frameCounter++ & 3;
+        vad_get_sa_q8(&st->vad, &st->speech_activity_Q8, c->input_quality_bands_Q15, &c->input_tilt_Q15, pIn);
+        hp_variable_cutoff(st, c, W->pIn_HP, pIn);
+        for (int i = 0; i < FRAME; i++) x_frame[LA_SHAPE + i] = W->pIn_HP[i];  // LP_variable_cutoff is a copy (transition_frame_no == 0)
+        find_pitch_lags(st, c, W->res_pitch, x_frame);
+        noise_shape_analysis(st, c, W->res_pitch + FRAME, x_frame);
+        prefilter(st, c, W->xfw, x_frame);
+        find_pred_coefs(st, c, W->res_pitch, frame_in_packet);
+        process_gains(st, c, frame_in_packet);
+        if (st->speech_activity_Q8 < SB_FIXC(0.1f, 8)) {
+            st->vadFlag = 0;
+            st->noSpeechCounter++;
+            if (st->noSpeechCounter > 5) st->inDTX = 1;
+            if (st->noSpeechCounter > 20 + 5) { st->noSpeechCounter = 5; st->inDTX = 0; }
+        } else {
+            st->noSpeechCounter = 0; st->inDTX = 0; st->vadFlag = 1;
+        }
+        W->vadFlag = st->vadFlag;
+        for (int i = 0; i < FRAME + LA_SHAPE; i++) st->x_buf[i] = st->x_buf[FRAME + i];
+        st->prev_sigtype = c->sigtype;
+        st->prevLag = c->pitchL[NB_SUBFR - 1];
+        st->first_frame_after_reset = 0;
+    );
+    (void)A;
 }
 
-// stage A
-SB_FN void enc_packet_analysis(EncState* st, EncAnalysisWork* W, const i16* pcm, EncScratch* scr) {
-    qmf_decomp(pcm, W->low, W->high, st->qmf_mem);
-    for (int f = 0; f < 2; f++) encode_frame_analysis(st, W, &scr->c[f], scr->xfw[f], &scr->vadFlag[f], W->low + f * FRAME, f);
-    scr->dtx_drop = (st->useDTX && st->inDTX) ? 1 : 0;
-    for (int f = 0; f < 2; f++) hb_analyse_frame(st, W->high + f * HB_FRAME, &scr->hb_lsp_idx[f], scr->hb_nrg0[f]);
+// stage A (cooperative).  st and W: shared memory in the warp-per-stream kernel; pcm and scr: global memory.
+SB_FN void enc_packet_analysis(EncCore* st, EncAnalysisWork* W, const i16* pcm, EncScratch* scr) {
+    Arena A;
+    arena_init(&A, W->arena_mem, SB_ANA_ARENA);
+    SB_SERIAL(qmf_decomp(pcm, W->low, W->high, st->qmf_mem));
+    for (int f = 0; f < 2; f++) {
+        encode_frame_analysis(st, W, &A, W->low + f * FRAME, f);
+        // hand the frame over to stages B / C (32-bit words; EncCtrl and xfw are both 4-byte multiples)
+        {
+            const i32* src = reinterpret_cast<const i32*>(&W->c);
+            i32* dst = reinterpret_cast<i32*>(&scr->c[f]);
+            SB_PARFOR(i, 0, (int)(sizeof(EncCtrl) / 4)) dst[i] = src[i];
+            const i32* xs = reinterpret_cast<const i32*>(W->xfw);
+            i32* xd = reinterpret_cast<i32*>(scr->xfw[f]);
+            SB_PARFOR(i, 0, FRAME / 2) xd[i] = xs[i];
+            if (SB_LANE0) scr->vadFlag[f] = W->vadFlag;
+        }
+        SB_SYNC();
+    }
+    if (SB_LANE0) scr->dtx_drop = (st->useDTX && st->inDTX) ? 1 : 0;
+    for (int f = 0; f < 2; f++) SB_SERIAL(hb_analyse_frame(st, W->high + f * HB_FRAME, &scr->hb_lsp_idx[f], scr->hb_nrg0[f]));
 }
 
 // stage C: AGR_Sate_Encoder_Encode tail -- returns the byte count; nBytesOut[0] = total, nBytesOut[1] = len(MD2) + 8
-SB_FN i32 enc_packet_finish(EncState* st, const EncScratch* scr, u8* rcbuf /* MAX_PAYLOAD scratch */, u8* out, i32 out_cap, i16* nBytesOut) {
+SB_FN i32 enc_packet_finish(EncCore* st, const EncScratch* scr, u8* rcbuf /* MAX_PAYLOAD scratch */, u8* out, i32 out_cap, i16* nBytesOut) {
     int nb[2];
     int ok = 1;
     int written = 0;
@@ -256,13 +285,17 @@ struct EncPacketWork {
     i32 r[FRAME];
     u8 rcbuf[MAX_PAYLOAD];
 };
-SB_FN i32 enc_packet(EncState* st, EncPacketWork* W, const i16* pcm, u8* out, i32 out_cap, i16* nBytesOut) {
-    enc_packet_analysis(st, &W->a, pcm, &W->scr);
+// stages B (scalar model of the quantiser) + C on one thread
+SB_FN i32 enc_packet_quantise_and_code(EncState* st, EncPacketWork* W, u8* out, i32 out_cap, i16* nBytesOut) {
     for (int f = 0; f < 2; f++) {
         nsq_del_dec(st, &W->scr.c[f], &W->nsq, W->scr.xfw[f], (i8*)0, W->scr.q_md[f][0], W->scr.q_md[f][1], W->r);
         for (int i = 0; i < FRAME; i++) W->scr.r16[f][i] = (i16)(W->r[i] >> 10);
     }
     return enc_packet_finish(st, &W->scr, W->rcbuf, out, out_cap, nBytesOut);
+}
+SB_FN i32 enc_packet(EncState* st, EncPacketWork* W, const i16* pcm, u8* out, i32 out_cap, i16* nBytesOut) {
+    enc_packet_analysis(st, &W->a, pcm, &W->scr);
+    return enc_packet_quantise_and_code(st, W, out, out_cap, nBytesOut);
 }
 
 }  // namespace sb

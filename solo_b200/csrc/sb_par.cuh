@@ -1,0 +1,164 @@
+// solo_b200 -- "one stream = one warp" execution model for the analysis stage.
+//
+// The analysis routines are written ONCE against this small vocabulary and compiled in three ways:
+//
+//   SB_COOP on the device  : 32 lanes of a warp cooperate on one stream.  SB_PARFOR spreads independent loop iterations
+//                            over the lanes, SB_SYNC() is __syncwarp(), the w* reductions are shuffle trees.  Every array
+//                            that more than one lane touches lives in shared memory (state, work area, Arena).
+//   serial (default)       : SB_PARFOR is a plain loop, SB_SYNC() and the reductions are no-ops -- this is what the
+//                            thread-per-stream kernels, and the host build used by the CPU test-suite, compile.
+//   SB_EMU on the host     : tests/hostsim runs 32 OS threads per stream with a barrier for SB_SYNC() and a shared
+//                            scratch line for the reductions, so that races and missing barriers in the cooperative code
+//                            show up on a machine without a GPU (test infrastructure only).
+//
+// Rules the routines follow:
+//   * scalars are computed redundantly by every lane from shared data ("uniform" code: no divergence, no broadcast);
+//   * a lane writes shared data either inside SB_PARFOR (its own iterations) or under SB_LANE0;
+//   * SB_SYNC() separates a write from any read by another lane;
+//   * integer sums that the reference accumulates with wrap-around (no saturation, no intermediate shift) may be split
+//     across lanes and combined with wsum(): addition modulo 2^32 / 2^64 is associative, so the result is bit-identical.
+#pragma once
+#include "sb_common.cuh"
+
+#if defined(__CUDA_ARCH__) && defined(SB_COOP)
+#define SB_COOP_ACTIVE 1
+#define SB_NLANES 32
+#define SB_LANE ((int)(threadIdx.x & 31))
+#define SB_SYNC() __syncwarp()
+#elif defined(SB_EMU) && !defined(__CUDA_ARCH__)
+#define SB_COOP_ACTIVE 1
+#define SB_NLANES 32
+namespace sb { namespace emu {
+extern thread_local int lane;
+void barrier();
+long long* scratch();   // 32 x 8-byte slots shared by the lanes of the current stream
+} }
+#define SB_LANE (::sb::emu::lane)
+#define SB_SYNC() ::sb::emu::barrier()
+#else
+#define SB_COOP_ACTIVE 0
+#define SB_NLANES 1
+#define SB_LANE 0
+#define SB_SYNC() ((void)0)
+#endif
+
+#define SB_LANE0 (SB_LANE == 0)
+// iterations lo <= i < hi, spread over the lanes (all of them on the single lane of a serial build)
+#define SB_PARFOR(i, lo, hi) for (int i = (lo) + SB_LANE; i < (hi); i += SB_NLANES)
+// run a statement block on lane 0 only, then make its effects visible to the other lanes
+#define SB_SERIAL(...) do { if (SB_LANE0) { __VA_ARGS__; } SB_SYNC(); } while (0)
+
+namespace sb {
+
+// ---- reductions / broadcasts over the lanes of a stream (identity in serial builds) --------------------------------
+#if defined(__CUDA_ARCH__) && defined(SB_COOP)
+__device__ __forceinline__ i32 wsum(i32 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = (i32)((u32)v + (u32)__shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ i64 wsum64(i64 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u32 lo = __shfl_xor_sync(0xffffffffu, (u32)v, o), hi = __shfl_xor_sync(0xffffffffu, (u32)((u64)v >> 32), o);
+        v = (i64)((u64)v + (((u64)hi << 32) | lo));
+    }
+    return v;
+}
+__device__ __forceinline__ i32 wmax(i32 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { i32 t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    return v;
+}
+__device__ __forceinline__ i32 wmin(i32 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { i32 t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+    return v;
+}
+__device__ __forceinline__ i32 wbcast(i32 v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+// minimum value and, among equal values, the smallest index (what a first-minimum-wins scan returns)
+__device__ __forceinline__ void wargmin(i32& v, i32& idx) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        i32 tv = __shfl_xor_sync(0xffffffffu, v, o), ti = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (tv < v || (tv == v && ti < idx)) { v = tv; idx = ti; }
+    }
+}
+__device__ __forceinline__ void wargmax(i32& v, i32& idx) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        i32 tv = __shfl_xor_sync(0xffffffffu, v, o), ti = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (tv > v || (tv == v && ti < idx)) { v = tv; idx = ti; }
+    }
+}
+#elif defined(SB_EMU) && !defined(__CUDA_ARCH__)
+template <class T, class F> inline T emu_reduce(T v, F f) {
+    long long* s = emu::scratch();
+    s[emu::lane] = (long long)v;
+    emu::barrier();
+    T r = (T)s[0];
+    for (int i = 1; i < 32; i++) r = f(r, (T)s[i]);
+    emu::barrier();
+    return r;
+}
+inline i32 wsum(i32 v) { return emu_reduce<i32>(v, [](i32 a, i32 b) { return (i32)((u32)a + (u32)b); }); }
+inline i64 wsum64(i64 v) { return emu_reduce<i64>(v, [](i64 a, i64 b) { return (i64)((u64)a + (u64)b); }); }
+inline i32 wmax(i32 v) { return emu_reduce<i32>(v, [](i32 a, i32 b) { return a > b ? a : b; }); }
+inline i32 wmin(i32 v) { return emu_reduce<i32>(v, [](i32 a, i32 b) { return a < b ? a : b; }); }
+inline i32 wbcast(i32 v, int src) {
+    long long* s = emu::scratch();
+    s[emu::lane] = v;
+    emu::barrier();
+    i32 r = (i32)s[src];
+    emu::barrier();
+    return r;
+}
+inline void wargmin(i32& v, i32& idx) {
+    long long* s = emu::scratch();
+    s[emu::lane] = ((long long)v << 32) | (u32)idx;
+    emu::barrier();
+    i32 bv = (i32)(s[0] >> 32), bi = (i32)(u32)s[0];
+    for (int i = 1; i < 32; i++) { i32 tv = (i32)(s[i] >> 32), ti = (i32)(u32)s[i]; if (tv < bv || (tv == bv && ti < bi)) { bv = tv; bi = ti; } }
+    emu::barrier();
+    v = bv; idx = bi;
+}
+inline void wargmax(i32& v, i32& idx) {
+    long long* s = emu::scratch();
+    s[emu::lane] = ((long long)v << 32) | (u32)idx;
+    emu::barrier();
+    i32 bv = (i32)(s[0] >> 32), bi = (i32)(u32)s[0];
+    for (int i = 1; i < 32; i++) { i32 tv = (i32)(s[i] >> 32), ti = (i32)(u32)s[i]; if (tv > bv || (tv == bv && ti < bi)) { bv = tv; bi = ti; } }
+    emu::barrier();
+    v = bv; idx = bi;
+}
+#else
+SB_HD i32 wsum(i32 v) { return v; }
+SB_HD i64 wsum64(i64 v) { return v; }
+SB_HD i32 wmax(i32 v) { return v; }
+SB_HD i32 wmin(i32 v) { return v; }
+SB_HD i32 wbcast(i32 v, int) { return v; }
+SB_HD void wargmin(i32&, i32&) {}
+SB_HD void wargmax(i32&, i32&) {}
+#endif
+
+// ---- Arena: LIFO scratch shared by the lanes of a stream (shared memory on the device) ------------------------------
+// Every lane executes the same alloc / release sequence, so the pointers are uniform without any communication.
+struct Arena {
+    unsigned char* base;
+    int cap, top, peak;
+};
+SB_HD void arena_init(Arena* a, void* mem, int cap) { a->base = (unsigned char*)mem; a->cap = cap; a->top = 0; a->peak = 0; }
+SB_HD int arena_mark(const Arena* a) { return a->top; }
+SB_HD void arena_release(Arena* a, int mark) { a->top = mark; }
+template <class T> SB_HD T* arena_alloc(Arena* a, int count) {
+    int off = (a->top + 15) & ~15;
+    int end = off + count * (int)sizeof(T);
+    a->top = end;
+    if (end > a->peak) a->peak = end;
+#if !defined(__CUDA_ARCH__)
+    if (end > a->cap) { __builtin_trap(); }
+#endif
+    return (T*)(a->base + off);
+}
+
+}  // namespace sb

@@ -2,7 +2,7 @@
 // Every routine cites the reference routine whose integer behaviour it reproduces; paths are
 // relative to /root/reference/JC1_SDK_SRC_ARM/src/libSATECodec/.
 #pragma once
-#include "sb_common.cuh"
+#include "sb_par.cuh"
 #include "sb_tables.cuh"
 
 namespace sb {

@@ -55,7 +55,9 @@ struct VadState {
     i16 HPstate;
 };
 
-struct EncState {
+// EncCore: everything the analysis (stage A) and entropy-coding (stage C) kernels keep between packets; the warp-per-stream
+// analysis kernel stages exactly this struct in shared memory.  EncState adds the three quantiser states of stage B.
+struct alignas(16) EncCore {
     // --- per-stream constants fixed at Init (control_codec_FIX.c:319-389) ---
     i32 SNR_dB_Q7;
     i32 SNRPerMD_dB_Q7;
@@ -79,10 +81,12 @@ struct EncState {
     i32 LTPCorr_Q15, avgGain_Q16, speech_activity_Q8, prevLTPredCodGain_Q7, HPLTPredCodGain_Q7;
     i32 prev_sigtype, prevLag, typeOffsetPrev_md[2], frameCounter, first_frame_after_reset;
     i32 noSpeechCounter, inDTX, vadFlag;
-    NsqState nsq[3];  // 0 = centre, 1 = description 1, 2 = description 2
     // --- high band (AGR_BWE_structs.h:14-19) ---
     i16 x_hb_buf[2 * HB_FRAME + 40 + 120];  // tail [360,480) is read by the LPC analysis and stays zero (App. A Q26)
     i32 hb_first;
+};
+struct EncState : EncCore {
+    NsqState nsq[3];  // 0 = centre, 1 = description 1, 2 = description 2
 };
 
 // Per-frame encoder control (SKP_Silk_encoder_control{,_FIX}: structs.h:262-290, structs_FIX.h:112-153)

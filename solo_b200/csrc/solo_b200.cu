@@ -25,6 +25,10 @@ using namespace sb;
 // kernels
 // ---------------------------------------------------------------------------------------------------
 #define SB_TPB 64
+#ifndef SB_ANALYSIS_WARP
+#define SB_ANALYSIS_WARP 0   // 1: stage A runs as the warp-per-stream kernel of sb_analysis.cu
+#endif
+extern "C" int sb_launch_enc_analysis_warp(void* states, void* scratch, const void* pcm, int n, void* stream);
 #ifndef SB_ANALYSIS_MINB
 #define SB_ANALYSIS_MINB 8   // min resident blocks per SM of the thread-per-stream kernels (register cap = 65536 / (64 * MINB))
 #endif
@@ -237,7 +241,11 @@ int solo_b200_enc_batch_encode_device(solo_b200_enc_batch* b, const int16_t* d_p
     cudaStream_t st = (cudaStream_t)cuda_stream;
     EvPair ev;
     prof_begin(st, 0, &ev);
+#if SB_ANALYSIS_WARP
+    { int e = sb_launch_enc_analysis_warp(b->d_states, b->d_scratch, d_pcm, b->n, st); if (e) { fail("analysis launch", (cudaError_t)e); return -2; } }
+#else
     sb_enc_analysis_kernel<<<(b->n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states, b->d_scratch, d_pcm, b->n);
+#endif
     prof_end(st, &ev);
     prof_begin(st, 1, &ev);
     sb_enc_nsq_kernel<<<(b->n + SB_NSQ_SPB - 1) / SB_NSQ_SPB, SB_NSQ_WARPS * 32, SB_NSQ_SPB * sizeof(NsqSmem), st>>>(b->d_states, b->d_scratch, b->n);

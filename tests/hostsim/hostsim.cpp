@@ -1,6 +1,23 @@
 // Host build of the per-stream kernel source (solo_b200/csrc/*.cuh compiled by g++).
 // TEST INFRASTRUCTURE ONLY: lets the CPU-only container check the kernel logic bit-for-bit against the
 // compiled reference (oracle/_ref).  Never linked into libsolo_b200.so.
+// With -DSB_EMU the analysis stage runs in its cooperative form on 32 OS threads per stream (sb_par.cuh), so that
+// races / missing barriers of the warp-per-stream kernel can be caught without a GPU.
+#ifdef SB_EMU
+#include <pthread.h>
+#include <thread>
+#include <vector>
+#include "../../solo_b200/csrc/sb_common.cuh"
+namespace sb { namespace emu {
+thread_local int lane = 0;
+static pthread_barrier_t bar;
+static long long scr[32];
+static bool inited = false;
+void barrier() { pthread_barrier_wait(&bar); }
+long long* scratch() { return scr; }
+static void init() { if (!inited) { pthread_barrier_init(&bar, nullptr, 32); inited = true; } }
+} }
+#endif
 #include "../../solo_b200/csrc/sb_enc.cuh"
 #include "../../solo_b200/csrc/sb_dec.cuh"
 #include <stdlib.h>
@@ -14,9 +31,26 @@ void* hs_enc_create(int rate, int dtx, int mdi) {
 }
 int hs_enc_encode(void* p, const short* pcm, unsigned char* out, int cap, short* nb) {
     HsEnc* h = (HsEnc*)p;
+#ifdef SB_EMU
+    sb::emu::init();
+    std::vector<std::thread> th;
+    for (int l = 0; l < 32; l++)
+        th.emplace_back([=]() { sb::emu::lane = l; sb::enc_packet_analysis(&h->st, &h->w.a, pcm, &h->w.scr); });
+    for (auto& t : th) t.join();
+    sb::emu::lane = 0;
+    return sb::enc_packet_quantise_and_code(&h->st, &h->w, out, cap, nb);
+#else
     return sb::enc_packet(&h->st, &h->w, pcm, out, cap, nb);
+#endif
 }
 void hs_enc_destroy(void* p) { free(p); }
+int hs_is_emu() {
+#ifdef SB_EMU
+    return 1;
+#else
+    return 0;
+#endif
+}
 int hs_enc_state_size() { return (int)sizeof(sb::EncState); }
 int hs_enc_work_size() { return (int)sizeof(sb::EncPacketWork); }
 void* hs_enc_state(void* p) { return &((HsEnc*)p)->st; }

@@ -8,13 +8,14 @@ import numpy as np
 
 from . import build_hostsim
 
-_lib = None
+_libs = {}
+EMU = False   # set tests.hostsim.sim.EMU = True (or use emu=True) to drive the 32-thread cooperative build
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        L = C.CDLL(build_hostsim.build())
+def lib(emu=None):
+    emu = EMU if emu is None else emu
+    if emu not in _libs:
+        L = C.CDLL(build_hostsim.build(emu=emu))
         L.hs_enc_create.restype = C.c_void_p
         L.hs_enc_create.argtypes = [C.c_int, C.c_int, C.c_int]
         L.hs_enc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -23,13 +24,13 @@ def lib():
         L.hs_dec_create.argtypes = [C.c_int]
         L.hs_dec_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.hs_dec_destroy.argtypes = [C.c_void_p]
-        _lib = L
-    return _lib
+        _libs[emu] = L
+    return _libs[emu]
 
 
 class SimEncoder:
-    def __init__(self, rate=13600, dtx=0, use_md_index=0, cap=1024):
-        self.L = lib()
+    def __init__(self, rate=13600, dtx=0, use_md_index=0, cap=1024, emu=None):
+        self.L = lib(emu)
         self.h = self.L.hs_enc_create(rate, dtx, use_md_index)
         self.cap = cap
         self.out = np.zeros(cap, np.uint8)
