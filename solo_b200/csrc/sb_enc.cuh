@@ -176,7 +176,7 @@ struct EncScratch {
 
 // Working set of stage A for one stream.  Warp-per-stream kernel: shared memory; thread-per-stream / host: local memory.
 #ifndef SB_ANA_ARENA
-#define SB_ANA_ARENA 8192
+#define SB_ANA_ARENA 16     // grows when routines move their scratch arrays into the shared arena
 #endif
 struct EncAnalysisWork {
     i16 low[PACKET / 2], high[PACKET / 2];

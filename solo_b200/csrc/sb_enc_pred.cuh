@@ -409,10 +409,14 @@ SB_FN void find_lpc(i32* NLSF_Q15, i32* interpIndex, const i32* prev_NLSFq_Q15, 
 SB_FN void nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb, const i32* pNLSF_q_Q15_prev, const i32* pW_Q6,
                             i32 NLSF_mu_Q15, i32 NLSF_mu_fluc_red_Q16, int deactivate_fluc_red) {
     enum { SURV = 16, NST = 6, ORD = 10 };
-    i32 pRateDist_Q18[SURV * 16 > 64 ? SURV * 16 : 64];
-    i32 pRate_Q5[SURV], pRate_new_Q5[SURV], pTempIndices[SURV];
-    i32 pPath[SURV * NST], pPath_new[SURV * NST];
-    i32 pRes_Q15[SURV * ORD], pRes_new_Q15[SURV * ORD];
+    i32 pRateDist_Q18[SURV];
+    // survivor sets of two consecutive stages: ping-pong buffers instead of the reference's copy-back (:224-229)
+    i32 rate_buf[2][SURV], pTempIndices[SURV];
+    i32 path_buf[2][SURV * NST];
+    i32 res_buf[2][SURV * ORD];
+    i32 *pRate_Q5 = rate_buf[0], *pRate_new_Q5 = rate_buf[1];
+    i32 *pPath = path_buf[0], *pPath_new = path_buf[1];
+    i32 *pRes_Q15 = res_buf[0], *pRes_new_Q15 = res_buf[1];
     for (int i = 0; i < SURV; i++) pRate_Q5[i] = 0;
     for (int i = 0; i < ORD; i++) pRes_Q15[i] = pNLSF_Q15[i];
     int prev_survivors = 1, cur_survivors = 0;
@@ -423,22 +427,43 @@ SB_FN void nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb, 
         const i16* CB = cb.cb_q15 + cb_off * ORD;
         const i16* Rates = cb.rates_q5 + cb_off;
         cur_survivors = imin(SURV, smulbb(prev_survivors, nVec));
-        // weighted errors + rate cost
+        // weighted errors + rate cost, with the 16 best kept sorted on the fly.  Equivalent to filling
+        // pRateDist_Q18[prev_survivors * nVec] and running SKP_Silk_insertion_sort_increasing (sort.c:34-76) over it:
+        // ascending, an element goes behind equal values that came earlier.  The list lives in registers (static indices
+        // only), a slot is empty while its index is negative.
+        i32 ka[SURV], ki[SURV];
+#pragma unroll
+        for (int j = 0; j < SURV; j++) { ka[j] = SB_I32_MAX; ki[j] = -1; }
         for (int n = 0; n < prev_survivors; n++) {
-            const i32* in = &pRes_Q15[n * ORD];
-            i32* out = &pRateDist_Q18[n * nVec];
+            i32 in[ORD];
+#pragma unroll
+            for (int m = 0; m < ORD; m++) in[m] = pRes_Q15[n * ORD + m];
+            const i32 rate_n = pRate_Q5[n];
             const i16* v = CB;
             for (int i = 0; i < nVec; i++) {
                 i32 sum_error = 0;
+#pragma unroll
                 for (int m = 0; m < ORD; m++) {
                     i32 diff = in[m] - (i32)v[m];
                     sum_error = smlawb(sum_error, smulbb(diff, diff), pW_Q6[m]);
                 }
                 v += ORD;
-                out[i] = smlabb(sum_error, pRate_Q5[n] + Rates[i], NLSF_mu_Q15);
+                const i32 val = smlabb(sum_error, rate_n + Rates[i], NLSF_mu_Q15);
+                const int e = n * nVec + i;
+                if (ki[SURV - 1] < 0 || val < ka[SURV - 1]) {
+#pragma unroll
+                    for (int j = SURV - 1; j >= 1; j--) {
+                        const bool up = ki[j - 1] < 0 || val < ka[j - 1];   // slot j-1 moves up into j
+                        const bool here = ki[j] < 0 || val < ka[j];        // ... else the new element lands in j
+                        ka[j] = up ? ka[j - 1] : (here ? val : ka[j]);
+                        ki[j] = up ? ki[j - 1] : (here ? e : ki[j]);
+                    }
+                    if (ki[0] < 0 || val < ka[0]) { ka[0] = val; ki[0] = e; }
+                }
             }
         }
-        insertion_sort_increasing(pRateDist_Q18, pTempIndices, prev_survivors * nVec, cur_survivors);
+#pragma unroll
+        for (int j = 0; j < SURV; j++) { pRateDist_Q18[j] = ka[j]; pTempIndices[j] = ki[j]; }
         if (pRateDist_Q18[0] < SB_I32_MAX / SURV) {
             i32 thr = smlawb(pRateDist_Q18[0], mulw(SURV, pRateDist_Q18[0]), SB_FIXC(0.1f, 16));
             while (pRateDist_Q18[cur_survivors - 1] > thr && cur_survivors > min_survivors) cur_survivors--;
@@ -460,9 +485,10 @@ SB_FN void nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb, 
             pn[s] = cb_index;
         }
         if (s < NST - 1) {
-            for (int i = 0; i < cur_survivors * ORD; i++) pRes_Q15[i] = pRes_new_Q15[i];
-            for (int i = 0; i < cur_survivors; i++) pRate_Q5[i] = pRate_new_Q5[i];
-            for (int i = 0; i < cur_survivors * NST; i++) pPath[i] = pPath_new[i];
+            i32* t;
+            t = pRes_Q15; pRes_Q15 = pRes_new_Q15; pRes_new_Q15 = t;
+            t = pRate_Q5; pRate_Q5 = pRate_new_Q5; pRate_new_Q5 = t;
+            t = pPath; pPath = pPath_new; pPath_new = t;
         }
         prev_survivors = cur_survivors;
         cb_off += nVec;

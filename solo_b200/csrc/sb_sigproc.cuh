@@ -179,27 +179,43 @@ SB_FN int lpc_inv_pred_gain_q24(i32* invGain_Q30, const i32* A_Q24, int order) {
     return lpc_inv_pred_gain_qa(invGain_Q30, A, order);
 }
 
-// ---- SKP_Silk_MA.c:41-62 (MA_Prediction with zero initial state == direct-form FIR, all sums mod 2^32)
-// out[k] = sat16(rshift_round((in[k]<<12) - sum_d B[d]*in[k-1-d], 12)), samples before in[0] taken as 0.
-SB_FN void ma_prediction_zero_state(const i16* in, const i16* B_Q12, i16* out, int len, int order) {
+// ---- SKP_Silk_MA.c:41-62 (MA_Prediction) and :65-118 (LPC_analysis_filter), both only ever called with a zeroed state
+// on this path == direct-form FIR whose taps before in[0] are zero:
+//   out[k] = sat16(rshift_round((in[k] << 12) - sum_d B[d] * in[k-1-d], 12))
+// MA_Prediction subtracts with wrap-around, LPC_analysis_filter with saturation.  The sum is taken mod 2^32, so missing
+// taps may be added as zeros: the last ORD inputs slide through registers and the coefficients are loaded once.
+template <int ORD, bool SAT> SB_FN void fir_zero_state(const i16* in, const i16* B_Q12, i16* out, int len) {
+    i32 b[ORD], w[ORD];
+#pragma unroll
+    for (int d = 0; d < ORD; d++) { b[d] = B_Q12[d]; w[d] = 0; }
     for (int k = 0; k < len; k++) {
-        i32 pred = 0;
-        int dmax = imin(order, k);
-        for (int d = 0; d < dmax; d++) pred = addw(pred, (i32)in[k - 1 - d] * (i32)B_Q12[d]);
-        i32 o = subw(shl((i32)in[k], 12), pred);
+        i32 acc = 0;
+#pragma unroll
+        for (int d = 0; d < ORD; d++) acc = addw(acc, w[d] * b[d]);
+        const i32 x = in[k];
+        const i32 o = SAT ? sub_sat32(shl(x, 12), acc) : subw(shl(x, 12), acc);
         out[k] = (i16)sat16(rshift_round(o, 12));
+#pragma unroll
+        for (int d = ORD - 1; d > 0; d--) w[d] = w[d - 1];
+        w[0] = x;
     }
 }
-
-// ---- SKP_Silk_MA.c:65-118 (LPC_analysis_filter, called with a zeroed state everywhere on this path)
-SB_FN void lpc_analysis_filter_zero_state(const i16* in, const i16* B_Q12, i16* out, int len, int order) {
+template <bool SAT> SB_FN void fir_zero_state_any(const i16* in, const i16* B_Q12, i16* out, int len, int order) {
+    if (order == 10) { fir_zero_state<10, SAT>(in, B_Q12, out, len); return; }
+    if (order == 8) { fir_zero_state<8, SAT>(in, B_Q12, out, len); return; }
     for (int k = 0; k < len; k++) {
         i32 acc = 0;
         int dmax = imin(order, k);
         for (int d = 0; d < dmax; d++) acc = addw(acc, (i32)in[k - 1 - d] * (i32)B_Q12[d]);
-        i32 o = sub_sat32(shl((i32)in[k], 12), acc);
+        i32 o = SAT ? sub_sat32(shl((i32)in[k], 12), acc) : subw(shl((i32)in[k], 12), acc);
         out[k] = (i16)sat16(rshift_round(o, 12));
     }
+}
+SB_FN void ma_prediction_zero_state(const i16* in, const i16* B_Q12, i16* out, int len, int order) {
+    fir_zero_state_any<false>(in, B_Q12, out, len, order);
+}
+SB_FN void lpc_analysis_filter_zero_state(const i16* in, const i16* B_Q12, i16* out, int len, int order) {
+    fir_zero_state_any<true>(in, B_Q12, out, len, order);
 }
 
 // ---- SKP_Silk_apply_sine_window.c:47-118 (scalar form; identical numerics on little-endian, Q24)

@@ -30,7 +30,7 @@ using namespace sb;
 #endif
 extern "C" int sb_launch_enc_analysis_warp(void* states, void* scratch, const void* pcm, int n, void* stream);
 #ifndef SB_ANALYSIS_MINB
-#define SB_ANALYSIS_MINB 8   // min resident blocks per SM of the thread-per-stream kernels (register cap = 65536 / (64 * MINB))
+#define SB_ANALYSIS_MINB 4   // min resident blocks per SM of the analysis kernel (register cap = 65536 / (64 * MINB) = 255)
 #endif
 #ifndef SB_DECODE_MINB
 #define SB_DECODE_MINB 8
