@@ -62,11 +62,14 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
+def ncu_traffic(streams_per_launch):
+    """DRAM bytes (read + write) of the dominant kernel from the committed `ncu --set full` capture, scaled from the
+    number of streams that capture's launch processed to the launches of this run (traffic is per stream: state + I/O)."""
     p = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("encode_kernel_dram_bytes_per_launch")
+            d = json.load(open(p))
+            return d["encode_kernel_dram_bytes_per_launch"] / d["encode_kernel_streams_per_launch"] * streams_per_launch
         except Exception:
             return None
     return None
@@ -202,6 +205,9 @@ def main():
     # Each step consumes a different 84 MB PCM wave (inputs + 0.9 GB of codec state >> 126 MB L2: no L2 flush needed).
     host_pcm = torch.from_numpy(speech_replay(clip, sids, T)).pin_memory()      # [T, N, 640] int16
     d_pcm = host_pcm.to(dev, non_blocking=True)
+    # Encoder wave then decoder wave on one CUDA stream.  (Running the two batch objects on separate streams so that
+    # decode(t) overlaps encode(t+1) was measured and is slower: all four kernels are latency-bound at a fixed number of
+    # resident warps and slow each other down when co-resident -- DESIGN.md section 6.)
     d_bits = torch.zeros((N, CAP), dtype=torch.uint8, device=dev)
     d_nb = torch.zeros((N, 2), dtype=torch.int16, device=dev)
     d_flags = torch.full((N,), 4, dtype=torch.int32, device=dev)
@@ -243,6 +249,9 @@ def main():
 
     # ---------------- end-to-end through the host entry points (`e2e`) ----------------
     # fresh codec objects are not needed: the streams simply continue with the next packets of the same input
+    # Public host API (solo_b200_enc_batch_encode_host / solo_b200_dec_batch_decode_host): every call copies its step's
+    # inputs from pinned host memory, runs the kernels, and copies the results back before it returns (inside the call
+    # the wave is pipelined in chunks, so most of the copy time hides behind the kernels of the neighbouring chunk).
     h_bits = torch.zeros((N, CAP), dtype=torch.uint8).pin_memory()
     h_nb = torch.zeros((N, 2), dtype=torch.int16).pin_memory()
     h_flags = torch.full((N,), 4, dtype=torch.int32).pin_memory()
@@ -275,11 +284,14 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
+        # per launch: a packet wave is processed as `chunks` launches of each kernel (solo_b200_set_chunks)
         kms = {k: (v[0] / max(v[1], 1)) for k, v in prof.items()}
+        kms_wave = {k: v[0] / K for k, v in prof.items()}        # summed launch durations per packet wave (launches overlap)
+        n_launch = max(prof["enc_nsq"][1], 1)
         enc_ms = kms["enc_nsq"]
-        dec_ms = kms["decode"]
-        alg_bytes_enc = N * (1280.0 + mean_payload + 4.0)          # encode reads 1280 B PCM, writes B_out + 4 B
-        alg_bytes_dec = N * (mean_payload + 4.0 + 4.0 + 1280.0 + 2.0)
+        streams_per_launch = N * K / n_launch
+        alg_bytes_enc = streams_per_launch * (1280.0 + mean_payload + 4.0)   # encode reads 1280 B PCM, writes B_out + 4 B
+        alg_bytes_dec = N * K / max(prof["decode"][1], 1) * (mean_payload + 4.0 + 4.0 + 1280.0 + 2.0)
         achieved = alg_bytes_enc / (enc_ms / 1e3) / 1e9 if enc_ms > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -296,9 +308,10 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "sb_enc_nsq_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(streams_per_launch), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes_enc, "kernel_ms": enc_ms,
-                         "kernel_ms_all": kms, "decode_algorithmic_bytes_per_launch": alg_bytes_dec,
+                         "kernel_ms_all": kms, "kernel_ms_per_wave": kms_wave, "streams_per_launch": streams_per_launch,
+                         "decode_algorithmic_bytes_per_launch": alg_bytes_dec,
                          "note": "integer-issue / latency bound codec: HBM fraction is small by construction (SURVEY 7.3-1)"},
             "decode_ret_ok": ret_ok,
         }

@@ -5,5 +5,5 @@ The product is ``libsolo_b200.so`` (hand-written sm_100a CUDA behind the referen
 and benchmarks; it contains no codec arithmetic and no CPU fallback: importing the binding without the built
 library, or creating a codec without a GPU, raises.
 """
-from .api import (DecoderBatch, EncoderBatch, SoloDecoder, SoloEncoder, SoloError, kernel_launches, lib,  # noqa: F401
+from .api import (DecoderBatch, EncoderBatch, SoloDecoder, SoloEncoder, SoloError, kernel_launches, lib, set_chunks,  # noqa: F401
                   profile_enable, profile_read, state_bytes)

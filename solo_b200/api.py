@@ -43,6 +43,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         vp, i32p = C.c_void_p, C.c_void_p
         L.solo_b200_last_error.restype = C.c_char_p
+        L.solo_b200_set_chunks.argtypes = [C.c_int]
         L.solo_b200_kernel_launches.restype = C.c_longlong
         L.solo_b200_enc_batch_create.restype = vp
         L.solo_b200_enc_batch_create.argtypes = [C.c_int, C.POINTER(EncCtrl), C.c_int]
@@ -233,3 +234,8 @@ class DecoderBatch:
             self.h = None
 
     __del__ = close
+
+
+def set_chunks(n):
+    """Number of stream groups a packet wave is pipelined as (see include/solo_b200.h); 1 = plain single launches."""
+    lib().solo_b200_set_chunks(int(n))

@@ -10,6 +10,7 @@
 // warp-cooperative NSQ.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <vector>
@@ -146,6 +147,51 @@ static void count_launch() {
     g_launches++;
 }
 
+// A packet wave is cut into chunks of streams that run on a few internal CUDA streams: the copies of one chunk overlap
+// the kernels of another (host entry points), and the blocks of one chunk's kernel fill the SMs that the tail of another
+// chunk's kernel leaves idle (all four kernels are latency-bound at a fixed number of resident warps per SM).
+#define SB_PIPE_STREAMS 4
+struct Pipe {
+    cudaStream_t st[SB_PIPE_STREAMS];
+    cudaEvent_t fork, join[SB_PIPE_STREAMS];
+    bool ok;
+};
+static int g_chunks = -1;   // -1: SOLO_B200_CHUNKS or the default below
+static int pipe_chunks(int n) {
+    if (g_chunks < 0) {
+        const char* e = getenv("SOLO_B200_CHUNKS");
+        g_chunks = e ? atoi(e) : 2;
+        if (g_chunks < 1) g_chunks = 1;
+        if (g_chunks > 64) g_chunks = 64;
+    }
+    int c = g_chunks;
+    while (c > 1 && n / c < 2048) c--;   // small batches: fewer, larger chunks
+    return c;
+}
+static int pipe_create(Pipe* p) {
+    p->ok = false;
+    for (int i = 0; i < SB_PIPE_STREAMS; i++) {
+        if (cudaStreamCreateWithFlags(&p->st[i], cudaStreamNonBlocking) != cudaSuccess) return -2;
+        if (cudaEventCreateWithFlags(&p->join[i], cudaEventDisableTiming) != cudaSuccess) return -2;
+    }
+    if (cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) != cudaSuccess) return -2;
+    p->ok = true;
+    return 0;
+}
+static void pipe_destroy(Pipe* p) {
+    if (!p->ok) return;
+    for (int i = 0; i < SB_PIPE_STREAMS; i++) { cudaStreamSynchronize(p->st[i]); cudaStreamDestroy(p->st[i]); cudaEventDestroy(p->join[i]); }
+    cudaEventDestroy(p->fork);
+}
+// chunk c of C over n streams, boundaries on multiples of 64 streams (block size of the thread-per-stream kernels)
+static void chunk_bounds(int n, int C, int c, int* lo, int* hi) {
+    long long per = ((long long)n + C - 1) / C;
+    per = (per + 63) / 64 * 64;
+    long long a = per * c, b = per * (c + 1);
+    *lo = (int)(a > n ? n : a);
+    *hi = (int)(b > n ? n : b);
+}
+
 struct solo_b200_enc_batch {
     int n, device;
     EncState* d_states;
@@ -153,12 +199,14 @@ struct solo_b200_enc_batch {
     // staging for the *_host entry points
     i16* d_pcm; u8* d_bits; i16* d_nbytes; int bits_cap;
     cudaStream_t stream;
+    Pipe pipe;
 };
 struct solo_b200_dec_batch {
     int n, device;
     DecState* d_states;
     i16* d_pcm; u8* d_bits; i16* d_nbytes; i32* d_flags; i32* d_ret; int bits_cap;
     cudaStream_t stream;
+    Pipe pipe;
 };
 
 static int check_enc_ctrl(const USER_Ctrl_enc* c) {
@@ -193,6 +241,7 @@ const char* solo_b200_last_error(void) { return g_err; }
 long long solo_b200_kernel_launches(void) { std::lock_guard<std::mutex> lk(g_mu); return g_launches; }
 int solo_b200_enc_state_bytes(void) { return (int)sizeof(EncState); }
 int solo_b200_dec_state_bytes(void) { return (int)sizeof(DecState); }
+void solo_b200_set_chunks(int chunks) { g_chunks = chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks); }
 void solo_b200_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_profile = on;
@@ -223,7 +272,7 @@ solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_e
     b->n = n_streams; b->device = device;
     if (cudaMalloc(&b->d_states, sizeof(EncState) * (size_t)n_streams) != cudaSuccess ||
         cudaMalloc(&b->d_scratch, sizeof(EncScratch) * (size_t)n_streams) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || pipe_create(&b->pipe) != 0 ||
         cudaFuncSetAttribute(sb_enc_nsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SB_NSQ_SPB * sizeof(NsqSmem))) != cudaSuccess) {
         fail("enc_batch_create", cudaGetLastError());
         delete b; return nullptr;
@@ -236,25 +285,50 @@ solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_e
     return b;
 }
 
-int solo_b200_enc_batch_encode_device(solo_b200_enc_batch* b, const int16_t* d_pcm, uint8_t* d_bits, int cap, int16_t* d_nbytes, void* cuda_stream) {
-    if (!b || !d_pcm || !d_bits || !d_nbytes || cap < 16) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
-    cudaStream_t st = (cudaStream_t)cuda_stream;
+// the three encoder kernels for streams [lo, lo + n) on one CUDA stream
+static int enc_launch(solo_b200_enc_batch* b, int lo, int n, const i16* d_pcm, u8* d_bits, int cap, i16* d_nbytes, cudaStream_t st) {
+    if (n <= 0) return 0;
+    EncState* states = b->d_states + lo;
+    EncScratch* scratch = b->d_scratch + lo;
+    const i16* pcm = d_pcm + (size_t)lo * PACKET;
     EvPair ev;
     prof_begin(st, 0, &ev);
 #if SB_ANALYSIS_WARP
-    { int e = sb_launch_enc_analysis_warp(b->d_states, b->d_scratch, d_pcm, b->n, st); if (e) { fail("analysis launch", (cudaError_t)e); return -2; } }
+    { int e = sb_launch_enc_analysis_warp(states, scratch, pcm, n, st); if (e) return fail("analysis launch", (cudaError_t)e); }
 #else
-    sb_enc_analysis_kernel<<<(b->n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states, b->d_scratch, d_pcm, b->n);
+    sb_enc_analysis_kernel<<<(n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(states, scratch, pcm, n);
 #endif
     prof_end(st, &ev);
     prof_begin(st, 1, &ev);
-    sb_enc_nsq_kernel<<<(b->n + SB_NSQ_SPB - 1) / SB_NSQ_SPB, SB_NSQ_WARPS * 32, SB_NSQ_SPB * sizeof(NsqSmem), st>>>(b->d_states, b->d_scratch, b->n);
+    sb_enc_nsq_kernel<<<(n + SB_NSQ_SPB - 1) / SB_NSQ_SPB, SB_NSQ_WARPS * 32, SB_NSQ_SPB * sizeof(NsqSmem), st>>>(states, scratch, n);
     prof_end(st, &ev);
     prof_begin(st, 2, &ev);
-    sb_enc_finish_kernel<<<(b->n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states, b->d_scratch, d_bits, cap, d_nbytes, b->n);
+    sb_enc_finish_kernel<<<(n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(states, scratch, d_bits + (size_t)lo * cap, cap, d_nbytes + 2 * (size_t)lo, n);
     prof_end(st, &ev);
     count_launch(); count_launch(); count_launch();
     CK(cudaGetLastError());
+    return 0;
+}
+
+int solo_b200_enc_batch_encode_device(solo_b200_enc_batch* b, const int16_t* d_pcm, uint8_t* d_bits, int cap, int16_t* d_nbytes, void* cuda_stream) {
+    if (!b || !d_pcm || !d_bits || !d_nbytes || cap < 16) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
+    cudaStream_t user = (cudaStream_t)cuda_stream;
+    const int C = pipe_chunks(b->n);
+    if (C == 1) return enc_launch(b, 0, b->n, d_pcm, d_bits, cap, d_nbytes, user);
+    // fork from the caller's stream onto the internal ones, join back: the caller sees ordinary stream semantics
+    CK(cudaEventRecord(b->pipe.fork, user));
+    const int S = C < SB_PIPE_STREAMS ? C : SB_PIPE_STREAMS;
+    for (int i = 0; i < S; i++) CK(cudaStreamWaitEvent(b->pipe.st[i], b->pipe.fork, 0));
+    for (int c = 0; c < C; c++) {
+        int lo, hi;
+        chunk_bounds(b->n, C, c, &lo, &hi);
+        int r = enc_launch(b, lo, hi - lo, d_pcm, d_bits, cap, d_nbytes, b->pipe.st[c % S]);
+        if (r) return r;
+    }
+    for (int i = 0; i < S; i++) {
+        CK(cudaEventRecord(b->pipe.join[i], b->pipe.st[i]));
+        CK(cudaStreamWaitEvent(user, b->pipe.join[i], 0));
+    }
     return 0;
 }
 
@@ -275,12 +349,21 @@ int solo_b200_enc_batch_encode_host(solo_b200_enc_batch* b, const int16_t* pcm, 
     CK(cudaSetDevice(b->device));
     int r = enc_staging(b, cap);
     if (r) return r;
-    CK(cudaMemcpyAsync(b->d_pcm, pcm, sizeof(i16) * PACKET * (size_t)b->n, cudaMemcpyHostToDevice, b->stream));
-    r = solo_b200_enc_batch_encode_device(b, b->d_pcm, b->d_bits, cap, b->d_nbytes, b->stream);
-    if (r) return r;
-    CK(cudaMemcpyAsync(bits, b->d_bits, (size_t)cap * b->n, cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaMemcpyAsync(nbytes, b->d_nbytes, sizeof(i16) * 2 * (size_t)b->n, cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
+    const int C = pipe_chunks(b->n);
+    const int S = C < SB_PIPE_STREAMS ? C : SB_PIPE_STREAMS;
+    for (int c = 0; c < C; c++) {   // per chunk: H2D, three kernels, D2H -- chunks alternate over the internal streams
+        int lo, hi;
+        chunk_bounds(b->n, C, c, &lo, &hi);
+        if (hi <= lo) continue;
+        cudaStream_t st = b->pipe.st[c % S];
+        const size_t m = (size_t)(hi - lo);
+        CK(cudaMemcpyAsync(b->d_pcm + (size_t)lo * PACKET, pcm + (size_t)lo * PACKET, sizeof(i16) * PACKET * m, cudaMemcpyHostToDevice, st));
+        r = enc_launch(b, lo, hi - lo, b->d_pcm, b->d_bits, cap, b->d_nbytes, st);
+        if (r) return r;
+        CK(cudaMemcpyAsync(bits + (size_t)lo * cap, b->d_bits + (size_t)lo * cap, (size_t)cap * m, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(nbytes + 2 * (size_t)lo, b->d_nbytes + 2 * (size_t)lo, sizeof(i16) * 2 * m, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < S; i++) CK(cudaStreamSynchronize(b->pipe.st[i]));
     return 0;
 }
 
@@ -288,6 +371,7 @@ void solo_b200_enc_batch_destroy(solo_b200_enc_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
+    pipe_destroy(&b->pipe);
     cudaFree(b->d_states); cudaFree(b->d_scratch); cudaFree(b->d_pcm); cudaFree(b->d_bits); cudaFree(b->d_nbytes);
     cudaStreamDestroy(b->stream);
     delete b;
@@ -301,7 +385,7 @@ solo_b200_dec_batch* solo_b200_dec_batch_create(int n_streams, const USER_Ctrl_d
     memset(b, 0, sizeof *b);
     b->n = n_streams; b->device = device;
     if (cudaMalloc(&b->d_states, sizeof(DecState) * (size_t)n_streams) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || pipe_create(&b->pipe) != 0) {
         fail("dec_batch_create", cudaGetLastError());
         delete b; return nullptr;
     }
@@ -312,15 +396,37 @@ solo_b200_dec_batch* solo_b200_dec_batch_create(int n_streams, const USER_Ctrl_d
     return b;
 }
 
-int solo_b200_dec_batch_decode_device(solo_b200_dec_batch* b, int16_t* d_pcm, const uint8_t* d_bits, int cap, const int16_t* d_nbytes,
-                                      const int32_t* d_lostflag, int32_t* d_ret, void* cuda_stream) {
-    if (!b || !d_pcm || !d_bits || !d_nbytes || !d_lostflag || cap < 16) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
-    cudaStream_t st = (cudaStream_t)cuda_stream;
+static int dec_launch(solo_b200_dec_batch* b, int lo, int n, i16* d_pcm, const u8* d_bits, int cap, const i16* d_nbytes, const i32* d_lostflag,
+                      i32* d_ret, cudaStream_t st) {
+    if (n <= 0) return 0;
     EvPair ev; prof_begin(st, 3, &ev);
-    sb_decode_kernel<<<(b->n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states, d_pcm, d_bits, cap, d_nbytes, d_lostflag, d_ret, b->n);
+    sb_decode_kernel<<<(n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states + lo, d_pcm + (size_t)lo * PACKET, d_bits + (size_t)lo * cap, cap,
+                                                                  d_nbytes + 2 * (size_t)lo, d_lostflag + lo, d_ret ? d_ret + lo : nullptr, n);
     prof_end(st, &ev);
     count_launch();
     CK(cudaGetLastError());
+    return 0;
+}
+
+int solo_b200_dec_batch_decode_device(solo_b200_dec_batch* b, int16_t* d_pcm, const uint8_t* d_bits, int cap, const int16_t* d_nbytes,
+                                      const int32_t* d_lostflag, int32_t* d_ret, void* cuda_stream) {
+    if (!b || !d_pcm || !d_bits || !d_nbytes || !d_lostflag || cap < 16) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
+    cudaStream_t user = (cudaStream_t)cuda_stream;
+    const int C = pipe_chunks(b->n);
+    if (C == 1) return dec_launch(b, 0, b->n, d_pcm, d_bits, cap, d_nbytes, d_lostflag, d_ret, user);
+    CK(cudaEventRecord(b->pipe.fork, user));
+    const int S = C < SB_PIPE_STREAMS ? C : SB_PIPE_STREAMS;
+    for (int i = 0; i < S; i++) CK(cudaStreamWaitEvent(b->pipe.st[i], b->pipe.fork, 0));
+    for (int c = 0; c < C; c++) {
+        int lo, hi;
+        chunk_bounds(b->n, C, c, &lo, &hi);
+        int r = dec_launch(b, lo, hi - lo, d_pcm, d_bits, cap, d_nbytes, d_lostflag, d_ret, b->pipe.st[c % S]);
+        if (r) return r;
+    }
+    for (int i = 0; i < S; i++) {
+        CK(cudaEventRecord(b->pipe.join[i], b->pipe.st[i]));
+        CK(cudaStreamWaitEvent(user, b->pipe.join[i], 0));
+    }
     return 0;
 }
 
@@ -344,14 +450,23 @@ int solo_b200_dec_batch_decode_host(solo_b200_dec_batch* b, int16_t* pcm, const 
     CK(cudaSetDevice(b->device));
     int r = dec_staging(b, cap);
     if (r) return r;
-    CK(cudaMemcpyAsync(b->d_bits, bits, (size_t)cap * b->n, cudaMemcpyHostToDevice, b->stream));
-    CK(cudaMemcpyAsync(b->d_nbytes, nbytes, sizeof(i16) * 2 * (size_t)b->n, cudaMemcpyHostToDevice, b->stream));
-    CK(cudaMemcpyAsync(b->d_flags, lostflag, sizeof(i32) * (size_t)b->n, cudaMemcpyHostToDevice, b->stream));
-    r = solo_b200_dec_batch_decode_device(b, b->d_pcm, b->d_bits, cap, b->d_nbytes, b->d_flags, b->d_ret, b->stream);
-    if (r) return r;
-    CK(cudaMemcpyAsync(pcm, b->d_pcm, sizeof(i16) * PACKET * (size_t)b->n, cudaMemcpyDeviceToHost, b->stream));
-    if (ret) CK(cudaMemcpyAsync(ret, b->d_ret, sizeof(i32) * (size_t)b->n, cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
+    const int C = pipe_chunks(b->n);
+    const int S = C < SB_PIPE_STREAMS ? C : SB_PIPE_STREAMS;
+    for (int c = 0; c < C; c++) {
+        int lo, hi;
+        chunk_bounds(b->n, C, c, &lo, &hi);
+        if (hi <= lo) continue;
+        cudaStream_t st = b->pipe.st[c % S];
+        const size_t m = (size_t)(hi - lo);
+        CK(cudaMemcpyAsync(b->d_bits + (size_t)lo * cap, bits + (size_t)lo * cap, (size_t)cap * m, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->d_nbytes + 2 * (size_t)lo, nbytes + 2 * (size_t)lo, sizeof(i16) * 2 * m, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->d_flags + lo, lostflag + lo, sizeof(i32) * m, cudaMemcpyHostToDevice, st));
+        r = dec_launch(b, lo, hi - lo, b->d_pcm, b->d_bits, cap, b->d_nbytes, b->d_flags, b->d_ret, st);
+        if (r) return r;
+        CK(cudaMemcpyAsync(pcm + (size_t)lo * PACKET, b->d_pcm + (size_t)lo * PACKET, sizeof(i16) * PACKET * m, cudaMemcpyDeviceToHost, st));
+        if (ret) CK(cudaMemcpyAsync(ret + lo, b->d_ret + lo, sizeof(i32) * m, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < S; i++) CK(cudaStreamSynchronize(b->pipe.st[i]));
     return 0;
 }
 
@@ -359,6 +474,7 @@ void solo_b200_dec_batch_destroy(solo_b200_dec_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
+    pipe_destroy(&b->pipe);
     cudaFree(b->d_states); cudaFree(b->d_pcm); cudaFree(b->d_bits); cudaFree(b->d_nbytes); cudaFree(b->d_flags); cudaFree(b->d_ret);
     cudaStreamDestroy(b->stream);
     delete b;

@@ -9,5 +9,5 @@ for line in sys.stdin:
         continue
     d = json.loads(line)
     r = d.get("roofline", {})
-    print("value %.0f  e2e %.0f  %s  ms/step %.2f  kernels %s  frac %.4f" % (
-        d["value"], d["e2e"]["value"], d["unit"], d["ms_per_step"], r.get("kernel_ms_all"), r.get("frac", 0)))
+    print("value %.0f  e2e %.0f  %s  ms/step %.2f  kernels/wave %s  frac %.4f" % (
+        d["value"], d["e2e"]["value"], d["unit"], d["ms_per_step"], {k: round(v, 2) for k, v in (r.get("kernel_ms_per_wave") or r.get("kernel_ms_all") or {}).items()}, r.get("frac", 0)))
