@@ -71,7 +71,12 @@ __global__ void __launch_bounds__(SB_NSQ_WARPS * 32, SB_NSQ_MINB) sb_enc_nsq_ker
     const int g = threadIdx.x / SB_NSQ_GW;                  // lane group inside the block = stream slot
     NsqSmem* S = reinterpret_cast<NsqSmem*>(smem_raw) + g;
     int s = blockIdx.x * SB_NSQ_SPB + g;
-    if (s >= n) return;                                     // whole groups leave; collectives name their own group
+    const int warp_first = blockIdx.x * SB_NSQ_SPB + (threadIdx.x >> 5) * (32 / SB_NSQ_GW);
+    if (warp_first >= n) return;                            // whole warps leave
+    // A lane group without a stream of its own (odd batch size) shadows the warp's last valid stream: same inputs, same
+    // arithmetic in its own shared-memory slot, identical values stored twice.  This keeps the sample loop's full-warp
+    // collectives valid for every warp.
+    if (s >= n) s = n - 1;
     EncScratch* scr = &scratch[s];
     for (int f = 0; f < 2; f++)
         nsq_del_dec_warp(*S, states[s].nsq, &scr->c[f], scr->xfw[f], scr->q_md[f][0], scr->q_md[f][1], scr->r16[f]);
