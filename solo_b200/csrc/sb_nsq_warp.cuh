@@ -307,13 +307,14 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                 const i32 rr1 = subw(r_p, q1), rr2 = subw(r_p, q2);
                 const i32 rd1 = smlabb(mulw(t1, Lambda_Q10), rr1, rr1) >> 10;
                 const i32 rd2 = smlabb(mulw(t2, Lambda_Q10), rr2, rr2) >> 10;
-                if (qz != 0) {
+                {   // centre lanes compute it too and overwrite it below (no branch)
                     const bool f = rd1 < rd2;
                     const i32 qa = f ? q1 : q2, qb = f ? q2 : q1, ra = f ? rd1 : rd2, rb = f ? rd2 : rd1;
                     c0.RD = addw(L.RD, ra); c1.RD = addw(L.RD, rb);
                     c0.Q_Q0 = qa >> 10; c1.Q_Q0 = qb >> 10;
                     c0.Q_Q10 = addw(of, qa); c1.Q_Q10 = addw(of, qb);
-                    c0.Rd_ind = ra; c1.Rd_ind = rb;
+                    c0.Rd_ind = qz != 0 ? ra : 0; c1.Rd_ind = qz != 0 ? rb : 0;
+                    c0.Q_Q10 = qz != 0 ? c0.Q_Q10 : 0; c1.Q_Q10 = qz != 0 ? c1.Q_Q10 : 0;
                 }
             }
             // ---- the four composites of the side candidates (Agora_Silk_CenterRD), evaluated by all three lanes of the
@@ -336,28 +337,29 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                 rdx[1] = addw(addw(rdx[1], ja1), jb1);
                 rdx[2] = addw(addw(rdx[2], ja0), jb1);
                 rdx[3] = addw(addw(rdx[3], ja1), jb0);
-                // best and second-best composite (strict "<": the lowest index wins ties, as in the reference's scans)
+                // best and second-best composite (strict "<": the lowest index wins ties, as in the reference's scans);
+                // written with selects only -- these lines sit on every lane's critical path
                 i32 mn = rdx[0], q_w1 = qx[0]; int w1 = 0;
-                if (rdx[1] < mn) { mn = rdx[1]; w1 = 1; q_w1 = qx[1]; }
-                if (rdx[2] < mn) { mn = rdx[2]; w1 = 2; q_w1 = qx[2]; }
-                if (rdx[3] < mn) { mn = rdx[3]; w1 = 3; q_w1 = qx[3]; }
+                { const bool t = rdx[1] < mn; mn = t ? rdx[1] : mn; w1 = t ? 1 : w1; q_w1 = t ? qx[1] : q_w1; }
+                { const bool t = rdx[2] < mn; mn = t ? rdx[2] : mn; w1 = t ? 2 : w1; q_w1 = t ? qx[2] : q_w1; }
+                { const bool t = rdx[3] < mn; mn = t ? rdx[3] : mn; w1 = t ? 3 : w1; q_w1 = t ? qx[3] : q_w1; }
                 const bool e0 = w1 == 0;
                 i32 mn2 = e0 ? rdx[1] : rdx[0], q_w2 = e0 ? qx[1] : qx[0]; int w2 = e0 ? 1 : 0;
-                if (w1 != 1 && rdx[1] < mn2) { mn2 = rdx[1]; w2 = 1; q_w2 = qx[1]; }
-                if (w1 != 2 && rdx[2] < mn2) { mn2 = rdx[2]; w2 = 2; q_w2 = qx[2]; }
-                if (w1 != 3 && rdx[3] < mn2) { mn2 = rdx[3]; w2 = 3; q_w2 = qx[3]; }
-                if (qz == 0) {
-                    c0.RD = addw(L.RD, mn); c1.RD = addw(L.RD, mn2);
-                    c0.Q_Q0 = q_w1 >> 10; c1.Q_Q0 = q_w2 >> 10;
-                    c0.Q_Q10 = q_w1; c1.Q_Q10 = q_w2;
-                    c0.Rd_ind = mn; c1.Rd_ind = mn2;
-                } else {
-                    // side lanes re-order their candidates to match the two surviving composites
+                { const bool t = (w1 != 1) & (rdx[1] < mn2); mn2 = t ? rdx[1] : mn2; w2 = t ? 1 : w2; q_w2 = t ? qx[1] : q_w2; }
+                { const bool t = (w1 != 2) & (rdx[2] < mn2); mn2 = t ? rdx[2] : mn2; w2 = t ? 2 : w2; q_w2 = t ? qx[2] : q_w2; }
+                { const bool t = (w1 != 3) & (rdx[3] < mn2); mn2 = t ? rdx[3] : mn2; w2 = t ? 3 : w2; q_w2 = t ? qx[3] : q_w2; }
+                {
+                    // centre: the two surviving composites; sides: their own candidates re-ordered to match them
+                    const bool ctr = qz == 0;
                     const int sel = qz == 1 ? 0xA : 0x6;  // a(c) / b(c): candidate index inside composite c
-                    const int i1 = (sel >> w1) & 1, i2 = (sel >> w2) & 1;
+                    const bool i1 = (sel >> w1) & 1, i2 = (sel >> w2) & 1;
                     const NsqCand o0 = c0, o1 = c1;
-                    c0.Q_Q0 = i1 ? o1.Q_Q0 : o0.Q_Q0; c0.Q_Q10 = i1 ? o1.Q_Q10 : o0.Q_Q10; c0.RD = i1 ? o1.RD : o0.RD;
-                    c1.Q_Q0 = i2 ? o1.Q_Q0 : o0.Q_Q0; c1.Q_Q10 = i2 ? o1.Q_Q10 : o0.Q_Q10; c1.RD = i2 ? o1.RD : o0.RD;
+                    c0.Q_Q0 = ctr ? (q_w1 >> 10) : (i1 ? o1.Q_Q0 : o0.Q_Q0);
+                    c1.Q_Q0 = ctr ? (q_w2 >> 10) : (i2 ? o1.Q_Q0 : o0.Q_Q0);
+                    c0.Q_Q10 = ctr ? q_w1 : (i1 ? o1.Q_Q10 : o0.Q_Q10);
+                    c1.Q_Q10 = ctr ? q_w2 : (i2 ? o1.Q_Q10 : o0.Q_Q10);
+                    c0.RD = ctr ? addw(L.RD, mn) : (i1 ? o1.RD : o0.RD);
+                    c1.RD = ctr ? addw(L.RD, mn2) : (i2 ? o1.RD : o0.RD);
                 }
             }
             // ---- un-dither, description gain, simulate the decoder for both candidates ----
@@ -365,7 +367,7 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                 c0.Q_Q10 = subw(c0.Q_Q10 ^ dither, dither);
                 c1.Q_Q10 = subw(c1.Q_Q10 ^ dither, dither);
                 c0.exc = c0.Q_Q10; c1.exc = c1.Q_Q10;
-                if (qz != 0) { c0.Q_Q10 = smulww(dg, c0.Q_Q10); c1.Q_Q10 = smulww(dg, c1.Q_Q10); }
+                { const i32 g0 = smulww(dg, c0.Q_Q10), g1 = smulww(dg, c1.Q_Q10); c0.Q_Q10 = qz != 0 ? g0 : c0.Q_Q10; c1.Q_Q10 = qz != 0 ? g1 : c1.Q_Q10; }
                 const i32 ltp4 = rshift_round(LTP_pred_Q14, 4);
                 i32 LPC_exc_Q10 = addw(c0.Q_Q10, ltp4);
                 i32 xq_Q10 = addw(LPC_exc_Q10, LPC_pred_Q10);
@@ -392,9 +394,8 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
 #pragma unroll
                 for (int m = 0; m < 4; m++) { j0[m] = shfl(fm, jn0, m); j1[m] = shfl(fm, jn1, m); ra[m] = shfl(fm, c0.RD, m); rb[m] = shfl(fm, c1.RD, m); }
                 int W0 = 0; i32 RDmin = j0[0];
-                if (j0[1] < RDmin) { RDmin = j0[1]; W0 = 1; }
-                if (j0[2] < RDmin) { RDmin = j0[2]; W0 = 2; }
-                if (j0[3] < RDmin) { RDmin = j0[3]; W0 = 3; }
+#pragma unroll
+                for (int m = 1; m < 4; m++) { const bool t = j0[m] < RDmin; RDmin = t ? j0[m] : RDmin; W0 = t ? m : W0; }
                 const i32 rs = S.tabRand[qz][last_smple_idx][(int)((L.path >> (2 * last_smple_idx)) & 3)];
                 const i32 wrs = shfl(fm, rs, qz * 4 + W0);
                 const unsigned bal = (__ballot_sync(fm, act && rs != wrs) >> gsh) & 0xffffu;
@@ -402,22 +403,23 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                 int RandSyncCtl = __popc(mstate);
                 const i32 PEN = SB_I32_MAX >> 4;
 #pragma unroll
-                for (int m = 0; m < 4; m++)
-                    if ((mstate >> m) & 1) { j0[m] = addw(j0[m], PEN); j1[m] = addw(j1[m], PEN); ra[m] = addw(ra[m], PEN); rb[m] = addw(rb[m], PEN); }
-                if (qz == 0 && ((mstate >> s) & 1)) { c0.RD = addw(c0.RD, PEN); c1.RD = addw(c1.RD, PEN); }
+                for (int m = 0; m < 4; m++) {
+                    const i32 pen = ((mstate >> m) & 1) ? PEN : 0;
+                    j0[m] = addw(j0[m], pen); j1[m] = addw(j1[m], pen); ra[m] = addw(ra[m], pen); rb[m] = addw(rb[m], pen);
+                }
+                { const i32 pen = ((qz == 0) & ((mstate >> s) & 1)) ? PEN : 0; c0.RD = addw(c0.RD, pen); c1.RD = addw(c1.RD, pen); }
                 // The reference repeats the replacement once per de-synchronised state (at least once).  Both streams of
                 // the warp run the same number of trips (the larger of the two) so that the shuffles below stay warp-uniform;
                 // a stream that is done (or finds nothing to replace) shuffles every lane onto itself.
                 const int my_trips = RandSyncCtl > 1 ? RandSyncCtl : 1;
                 const int trips = __reduce_max_sync(fm, my_trips);
                 for (int it = 0; it < trips; it++) {
-                    i32 RDmax = ra[0], RDmin2 = rb[0]; int imx = 0, imn = 0;
-                    if (ra[1] > RDmax) { RDmax = ra[1]; imx = 1; }
-                    if (ra[2] > RDmax) { RDmax = ra[2]; imx = 2; }
-                    if (ra[3] > RDmax) { RDmax = ra[3]; imx = 3; }
-                    if (rb[1] < RDmin2) { RDmin2 = rb[1]; imn = 1; }
-                    if (rb[2] < RDmin2) { RDmin2 = rb[2]; imn = 2; }
-                    if (rb[3] < RDmin2) { RDmin2 = rb[3]; imn = 3; }
+                    i32 RDmax = ra[0], RDmin2 = rb[0], j1n = j1[0]; int imx = 0, imn = 0;
+#pragma unroll
+                    for (int m = 1; m < 4; m++) {
+                        const bool tx = ra[m] > RDmax; RDmax = tx ? ra[m] : RDmax; imx = tx ? m : imx;
+                        const bool tn = rb[m] < RDmin2; RDmin2 = tn ? rb[m] : RDmin2; imn = tn ? m : imn; j1n = tn ? j1[m] : j1n;
+                    }
                     const bool doit = it < my_trips && RDmin2 < RDmax;
                     {
                         const int src = qz * 4 + imn;
@@ -444,16 +446,12 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                         v = shfl(fm, c1.exc, src); if (tgt) c0.exc = v;
                         // what every lane knows about the columns afterwards
 #pragma unroll
-                        for (int m = 0; m < 4; m++) if (doit && m == imx) {
-                            ra[m] = imn == 0 ? rb[0] : (imn == 1 ? rb[1] : (imn == 2 ? rb[2] : rb[3]));
-                            j0[m] = imn == 0 ? j1[0] : (imn == 1 ? j1[1] : (imn == 2 ? j1[2] : j1[3]));
-                        }
+                        for (int m = 0; m < 4; m++) { const bool t = doit & (m == imx); ra[m] = t ? RDmin2 : ra[m]; j0[m] = t ? j1n : j0[m]; }
                     }
                 }
                 Winner = 0; RDmin = j0[0];
-                if (j0[1] < RDmin) { RDmin = j0[1]; Winner = 1; }
-                if (j0[2] < RDmin) { RDmin = j0[2]; Winner = 2; }
-                if (j0[3] < RDmin) { RDmin = j0[3]; Winner = 3; }
+#pragma unroll
+                for (int m = 1; m < 4; m++) { const bool t = j0[m] < RDmin; RDmin = t ? j0[m] : RDmin; Winner = t ? m : Winner; }
             }
             // ---- emit the sample that is decisionDelay old from the joint winner ----
             {
