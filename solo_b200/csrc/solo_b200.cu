@@ -26,6 +26,12 @@ using namespace sb;
 // kernels
 // ---------------------------------------------------------------------------------------------------
 #define SB_TPB 64
+#ifndef SB_ANALYSIS_LOCAL_STATE
+#define SB_ANALYSIS_LOCAL_STATE 1   // stage the per-stream state in local memory for the duration of a packet (thread-per-stream kernels)
+#endif
+#ifndef SB_DECODE_LOCAL_STATE
+#define SB_DECODE_LOCAL_STATE 0
+#endif
 #ifndef SB_ANALYSIS_WARP
 #define SB_ANALYSIS_WARP 0   // 1: stage A runs as the warp-per-stream kernel of sb_analysis.cu
 #endif
@@ -56,7 +62,14 @@ __global__ void __launch_bounds__(SB_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_kern
     int4* dst = reinterpret_cast<int4*>(x);
 #pragma unroll 4
     for (int i = 0; i < PACKET * 2 / 16; i++) dst[i] = src[i];
+#if SB_ANALYSIS_LOCAL_STATE
+    // analysis state staged in local memory: same-offset words of the 32 streams of a warp share cache lines there
+    EncCore st = static_cast<const EncCore&>(states[s]);
+    enc_packet_analysis(&st, &W, x, &scratch[s]);
+    static_cast<EncCore&>(states[s]) = st;
+#else
     enc_packet_analysis(&states[s], &W, x, &scratch[s]);
+#endif
 }
 
 #ifndef SB_NSQ_WARPS
@@ -106,7 +119,13 @@ __global__ void __launch_bounds__(SB_TPB, SB_DECODE_MINB) sb_decode_kernel(DecSt
     DecPacketWork W;
     i16 nb[2] = {nbytes[2 * s], nbytes[2 * s + 1]};
     i16 out[PACKET];
+#if SB_DECODE_LOCAL_STATE
+    DecState st = states[s];
+    i32 r = dec_packet(&st, &W, out, bits + (size_t)s * cap, cap, nb, lostflag[s]);
+    states[s] = st;
+#else
     i32 r = dec_packet(&states[s], &W, out, bits + (size_t)s * cap, cap, nb, lostflag[s]);
+#endif
     int4* dst = reinterpret_cast<int4*>(pcm + (size_t)s * PACKET);
     const int4* src = reinterpret_cast<const int4*>(out);
 #pragma unroll 4
