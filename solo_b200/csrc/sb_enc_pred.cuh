@@ -410,6 +410,8 @@ SB_FN void nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb, 
                             i32 NLSF_mu_Q15, i32 NLSF_mu_fluc_red_Q16, int deactivate_fluc_red) {
     enum { SURV = 16, NST = 6, ORD = 10 };
     i32 pRateDist_Q18[SURV];
+    i32 log_v[SURV * 16 > 64 ? SURV * 16 : 64];   // candidates that entered the running best-16, in scan order
+    i16 log_e[SURV * 16 > 64 ? SURV * 16 : 64];
     // survivor sets of two consecutive stages: ping-pong buffers instead of the reference's copy-back (:224-229)
     i32 rate_buf[2][SURV], pTempIndices[SURV];
     i32 path_buf[2][SURV * NST];
@@ -427,13 +429,19 @@ SB_FN void nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb, 
         const i16* CB = cb.cb_q15 + cb_off * ORD;
         const i16* Rates = cb.rates_q5 + cb_off;
         cur_survivors = imin(SURV, smulbb(prev_survivors, nVec));
-        // weighted errors + rate cost, with the 16 best kept sorted on the fly.  Equivalent to filling
-        // pRateDist_Q18[prev_survivors * nVec] and running SKP_Silk_insertion_sort_increasing (sort.c:34-76) over it:
-        // ascending, an element goes behind equal values that came earlier.  The list lives in registers (static indices
-        // only), a slot is empty while its index is negative.
-        i32 ka[SURV], ki[SURV];
+        // Weighted errors + rate cost of every (survivor, code vector) pair and the 16 best of them, equivalent to filling
+        // pRateDist_Q18[prev_survivors * nVec] and running SKP_Silk_insertion_sort_increasing over it (sort.c:34-76:
+        // ascending, an element goes behind equal values that came earlier).  Written for SIMT execution, where a branch
+        // costs every stream of the warp as soon as one stream takes it:
+        //   1. the scan keeps only the sorted VALUES of the current best 16 in registers (one min/max pair per slot, no
+        //      flags, no indices) and appends every candidate that enters the list to a log;
+        //   2. afterwards the log -- in scan order -- is filtered with the final 16th value and the 16 survivors are
+        //      insertion-sorted exactly as the reference would sort them.
+        // Every element of the final best-16 was below the threshold when it was scanned, so it is in the log.
+        i32 ka[SURV];
 #pragma unroll
-        for (int j = 0; j < SURV; j++) { ka[j] = SB_I32_MAX; ki[j] = -1; }
+        for (int j = 0; j < SURV; j++) ka[j] = SB_I32_MAX;
+        int nlog = 0;
         for (int n = 0; n < prev_survivors; n++) {
             i32 in[ORD];
 #pragma unroll
@@ -450,20 +458,32 @@ SB_FN void nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb, 
                 v += ORD;
                 const i32 val = smlabb(sum_error, rate_n + Rates[i], NLSF_mu_Q15);
                 const int e = n * nVec + i;
-                if (ki[SURV - 1] < 0 || val < ka[SURV - 1]) {
+                if (e < SURV || val < ka[SURV - 1]) {
+                    log_v[nlog] = val; log_e[nlog] = (i16)e; nlog++;
 #pragma unroll
-                    for (int j = SURV - 1; j >= 1; j--) {
-                        const bool up = ki[j - 1] < 0 || val < ka[j - 1];   // slot j-1 moves up into j
-                        const bool here = ki[j] < 0 || val < ka[j];        // ... else the new element lands in j
-                        ka[j] = up ? ka[j - 1] : (here ? val : ka[j]);
-                        ki[j] = up ? ki[j - 1] : (here ? e : ki[j]);
-                    }
-                    if (ki[0] < 0 || val < ka[0]) { ka[0] = val; ki[0] = e; }
+                    for (int j = SURV - 1; j >= 1; j--) ka[j] = imin(ka[j], imax(ka[j - 1], val));
+                    ka[0] = imin(ka[0], val);
                 }
             }
         }
+        {
+            const i32 T = ka[SURV - 1];
+            int need_eq = SURV;                       // how many elements equal to T belong to the best 16
 #pragma unroll
-        for (int j = 0; j < SURV; j++) { pRateDist_Q18[j] = ka[j]; pTempIndices[j] = ki[j]; }
+            for (int j = 0; j < SURV; j++) need_eq -= (ka[j] < T) ? 1 : 0;
+            int m = 0;
+            for (int q = 0; q < nlog; q++) {
+                const i32 val = log_v[q];
+                bool take = val < T;
+                if (val == T && need_eq > 0) { take = true; need_eq--; }
+                if (take) {
+                    int j = m - 1;
+                    for (; j >= 0 && val < pRateDist_Q18[j]; j--) { pRateDist_Q18[j + 1] = pRateDist_Q18[j]; pTempIndices[j + 1] = pTempIndices[j]; }
+                    pRateDist_Q18[j + 1] = val; pTempIndices[j + 1] = log_e[q];
+                    m++;
+                }
+            }
+        }
         if (pRateDist_Q18[0] < SB_I32_MAX / SURV) {
             i32 thr = smlawb(pRateDist_Q18[0], mulw(SURV, pRateDist_Q18[0]), SB_FIXC(0.1f, 16));
             while (pRateDist_Q18[cur_survivors - 1] > thr && cur_survivors > min_survivors) cur_survivors--;
