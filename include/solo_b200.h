@@ -49,6 +49,32 @@ int solo_b200_dec_batch_decode_device(solo_b200_dec_batch *b, int16_t *d_pcm, co
                                       const int16_t *d_nbytes, const int32_t *d_lostflag, int32_t *d_ret, void *cuda_stream);
 void solo_b200_dec_batch_destroy(solo_b200_dec_batch *b);
 
+/* Stream state hand-over (checkpoint, migration between batches / GPUs, streams joining and leaving a batch): the complete
+   codec state of stream `idx` as an opaque blob of solo_b200_{enc,dec}_state_bytes() bytes.  Synchronous; a blob is only
+   meaningful to the same build of the library. */
+int solo_b200_enc_batch_export_state(solo_b200_enc_batch *b, int idx, void *blob);
+int solo_b200_enc_batch_import_state(solo_b200_enc_batch *b, int idx, const void *blob);
+int solo_b200_dec_batch_export_state(solo_b200_dec_batch *b, int idx, void *blob);
+int solo_b200_dec_batch_import_state(solo_b200_dec_batch *b, int idx, const void *blob);
+
+/* Packet framing around one payload row [MD1 | MD2 | HB] (reference drivers enc_main.c:212-234, dec_main.c:196-307, README
+   "Bitstream sending" / "Bitstream screening and synthesis at receiver").  Host functions, no GPU involved.
+     split : the two network packets of a row -- description 1 = MD1, description 2 = MD2 + 8 high-band bytes (pointers into
+             `bits`); both empty for a DTX row (nbytes[0] == 0)
+     merge : from whichever packets arrived (pass NULL / 0 for a missing one) build the decoder's row, nbytes[2] and lostflag
+             (4 both, 2 only description 1, 3 only description 2, 1 none)
+     bitfile_pack / unpack : one record of the reference's .bit file (int16 total, int16 len(MD2)+8, payload); return the
+             record size, or -1
+     apply_loss_device : the receiver-side trimming for a whole batch on the GPU (rows of `cap` bytes): lostflag 2 keeps MD1,
+             3 moves MD2 + HB to the front, 4 / 1 pass through -- feeds solo_b200_dec_batch_decode_device directly */
+int solo_b200_split_packet(const uint8_t *bits, const int16_t *nbytes, const uint8_t **p1, int *n1, const uint8_t **p2, int *n2);
+int solo_b200_merge_packets(const uint8_t *p1, int n1, const uint8_t *p2, int n2, uint8_t *bits, int cap, int16_t *nbytes,
+                            int32_t *lostflag);
+int solo_b200_bitfile_pack(const uint8_t *bits, const int16_t *nbytes, uint8_t *out, int out_cap);
+int solo_b200_bitfile_unpack(const uint8_t *in, int in_len, const uint8_t **payload, int16_t *nbytes);
+int solo_b200_apply_loss_device(const uint8_t *d_bits_in, const int16_t *d_nbytes_in, const int32_t *d_lostflag, uint8_t *d_bits_out,
+                                int16_t *d_nbytes_out, int cap, int n, void *cuda_stream);
+
 /* Bytes of device state held per stream (encoder / decoder). */
 int solo_b200_enc_state_bytes(void);
 int solo_b200_dec_state_bytes(void);

@@ -55,6 +55,17 @@ def lib():
         L.solo_b200_dec_batch_decode_host.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
         L.solo_b200_dec_batch_decode_device.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp]
         L.solo_b200_dec_batch_destroy.argtypes = [vp]
+        for f in ("solo_b200_enc_batch_export_state", "solo_b200_enc_batch_import_state", "solo_b200_dec_batch_export_state",
+                  "solo_b200_dec_batch_import_state"):
+            getattr(L, f).argtypes = [vp, C.c_int, vp]
+        pp, ip = C.POINTER(vp), C.POINTER(C.c_int)
+        L.solo_b200_split_packet.argtypes = [vp, vp, pp, ip, pp, ip]
+        L.solo_b200_merge_packets.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp]
+        L.solo_b200_bitfile_pack.argtypes = [vp, vp, vp, C.c_int]
+        L.solo_b200_bitfile_unpack.argtypes = [vp, C.c_int, pp, vp]
+        L.solo_b200_apply_loss_device.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
+        L.solo_b200_enc_state_bytes.restype = C.c_int
+        L.solo_b200_dec_state_bytes.restype = C.c_int
         L.solo_b200_profile_enable.argtypes = [C.c_int]
         L.solo_b200_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
         L.AGR_Sate_Encoder_Init.restype = vp
@@ -179,6 +190,18 @@ class EncoderBatch:
         if r:
             raise SoloError("encode_host failed (%d): %s" % (r, _err()))
 
+    def export_state(self, idx):
+        """Opaque blob with the complete state of stream idx (checkpoint / migration)."""
+        blob = np.zeros(lib().solo_b200_enc_state_bytes(), np.uint8)
+        if lib().solo_b200_enc_batch_export_state(self.h, int(idx), blob.ctypes.data):
+            raise SoloError(_err())
+        return blob
+
+    def import_state(self, idx, blob):
+        blob = np.ascontiguousarray(blob, np.uint8)
+        if blob.size != lib().solo_b200_enc_state_bytes() or lib().solo_b200_enc_batch_import_state(self.h, int(idx), blob.ctypes.data):
+            raise SoloError("import_state: " + _err())
+
     def encode_device(self, d_pcm, d_bits, cap, d_nbytes, stream=0):
         r = lib().solo_b200_enc_batch_encode_device(self.h, d_pcm, d_bits, cap, d_nbytes, stream)
         if r:
@@ -223,6 +246,17 @@ class DecoderBatch:
         if r:
             raise SoloError("decode_host failed (%d): %s" % (r, _err()))
 
+    def export_state(self, idx):
+        blob = np.zeros(lib().solo_b200_dec_state_bytes(), np.uint8)
+        if lib().solo_b200_dec_batch_export_state(self.h, int(idx), blob.ctypes.data):
+            raise SoloError(_err())
+        return blob
+
+    def import_state(self, idx, blob):
+        blob = np.ascontiguousarray(blob, np.uint8)
+        if blob.size != lib().solo_b200_dec_state_bytes() or lib().solo_b200_dec_batch_import_state(self.h, int(idx), blob.ctypes.data):
+            raise SoloError("import_state: " + _err())
+
     def decode_device(self, d_pcm, d_bits, cap, d_nbytes, d_flags, d_ret=0, stream=0):
         r = lib().solo_b200_dec_batch_decode_device(self.h, d_pcm, d_bits, cap, d_nbytes, d_flags, d_ret, stream)
         if r:
@@ -239,3 +273,59 @@ class DecoderBatch:
 def set_chunks(n):
     """Number of stream groups a packet wave is pipelined as (see include/solo_b200.h); 1 = plain single launches."""
     lib().solo_b200_set_chunks(int(n))
+
+
+# ---- packet framing (host functions of the library; no GPU involved) --------------------------------------------------
+def split_packet(bits, nbytes):
+    """(description 1, description 2) = (MD1, MD2 + 8 high-band bytes) of one payload row; (b"", b"") for a DTX row."""
+    buf = np.ascontiguousarray(np.frombuffer(bytes(bits), np.uint8))
+    nb = np.array([nbytes[0], nbytes[1]], np.int16)
+    p1, p2, n1, n2 = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
+    if lib().solo_b200_split_packet(buf.ctypes.data, nb.ctypes.data, C.byref(p1), C.byref(n1), C.byref(p2), C.byref(n2)):
+        raise SoloError("split_packet: inconsistent length fields")
+    o1 = (p1.value or buf.ctypes.data) - buf.ctypes.data
+    o2 = (p2.value or buf.ctypes.data) - buf.ctypes.data
+    return bytes(buf[o1:o1 + n1.value]), bytes(buf[o2:o2 + n2.value])
+
+
+def merge_packets(p1, p2, cap=1024):
+    """(payload row, (n0, n1), lostflag) for the decoder from whichever descriptions arrived (None / b"" = lost)."""
+    a = np.frombuffer(p1, np.uint8).copy() if p1 else None
+    b = np.frombuffer(p2, np.uint8).copy() if p2 else None
+    out = np.zeros(cap, np.uint8)
+    nb = np.zeros(2, np.int16)
+    flag = C.c_int32()
+    r = lib().solo_b200_merge_packets(a.ctypes.data if a is not None else None, len(a) if a is not None else 0,
+                                      b.ctypes.data if b is not None else None, len(b) if b is not None else 0,
+                                      out.ctypes.data, cap, nb.ctypes.data, C.byref(flag))
+    if r:
+        raise SoloError("merge_packets: packets do not fit")
+    return bytes(out[:max(int(nb[0]), 0)]), (int(nb[0]), int(nb[1])), int(flag.value)
+
+
+def bitfile_pack(bits, nbytes):
+    """One record of the reference CLI's .bit file."""
+    buf = np.frombuffer(bytes(bits) + b"\0", np.uint8).copy()
+    nb = np.array([nbytes[0], nbytes[1]], np.int16)
+    out = np.zeros(4 + max(int(nbytes[0]), 0), np.uint8)
+    n = lib().solo_b200_bitfile_pack(buf.ctypes.data, nb.ctypes.data, out.ctypes.data, out.size)
+    if n < 0:
+        raise SoloError("bitfile_pack")
+    return bytes(out[:n])
+
+
+def bitfile_unpack(data, offset=0):
+    """(payload, (n0, n1), next offset) of the record starting at `offset`."""
+    buf = np.frombuffer(data, np.uint8)
+    view = np.ascontiguousarray(buf[offset:])
+    nb = np.zeros(2, np.int16)
+    p = C.c_void_p()
+    n = lib().solo_b200_bitfile_unpack(view.ctypes.data, view.size, C.byref(p), nb.ctypes.data)
+    if n < 0:
+        raise SoloError("bitfile_unpack: truncated record")
+    return bytes(view[4:n]), (int(nb[0]), int(nb[1])), offset + n
+
+
+def apply_loss_device(d_bits_in, d_nbytes_in, d_lostflag, d_bits_out, d_nbytes_out, cap, n, stream=0):
+    if lib().solo_b200_apply_loss_device(d_bits_in, d_nbytes_in, d_lostflag, d_bits_out, d_nbytes_out, cap, n, stream):
+        raise SoloError(_err())

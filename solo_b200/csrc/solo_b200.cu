@@ -140,6 +140,26 @@ static thread_local char g_err[256] = "";
 static std::mutex g_mu;
 static long long g_launches = 0;
 static int g_profile = 0;
+// ---- sender / receiver glue around the payload row [MD1 | MD2 | HB] -----------------------------
+// What the reference's decoder driver does between the network and AGR_Sate_Decoder_Decode (dec_main.c:245-307), for a whole
+// batch on the device: lostflag 2 keeps MD1 only, 3 moves MD2 + HB to the front, 4 passes the row through, 1 (lost) leaves
+// the row alone (the decoder does not read it).  One warp per row, 16-byte aligned rows when cap is a multiple of 16.
+__global__ void __launch_bounds__(256) sb_apply_loss_kernel(const u8* __restrict__ bits_in, const i16* __restrict__ nb_in, const i32* __restrict__ flag,
+                                                           u8* __restrict__ bits_out, i16* __restrict__ nb_out, int cap, int n) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const int n0 = nb_in[2 * row], n1 = nb_in[2 * row + 1], f = flag[row];
+    int off = 0, len = n0, o0 = n0, o1 = n1;
+    if (f == 2) { len = n0 - n1; o0 = len; o1 = 0; }
+    else if (f == 3) { off = n0 - n1; len = n1; o0 = n1; o1 = 0; }
+    if (len < 0) len = 0;
+    if (len > cap - off) len = cap - off;
+    const u8* src = bits_in + (size_t)row * cap + off;
+    u8* dst = bits_out + (size_t)row * cap;
+    for (int i = lane; i < len; i += 32) dst[i] = src[i];
+    if (lane == 0) { nb_out[2 * row] = (i16)o0; nb_out[2 * row + 1] = (i16)o1; }
+}
+
 struct EvPair { cudaEvent_t a, b; int kind; };
 static std::vector<EvPair> g_events;
 
@@ -502,6 +522,89 @@ void solo_b200_dec_batch_destroy(solo_b200_dec_batch* b) {
     cudaFree(b->d_states); cudaFree(b->d_pcm); cudaFree(b->d_bits); cudaFree(b->d_nbytes); cudaFree(b->d_flags); cudaFree(b->d_ret);
     cudaStreamDestroy(b->stream);
     delete b;
+}
+
+// ---- stream state hand-over (checkpoint / migration) ----------------------------------------------
+static int state_copy(void* dev_base, size_t stride, int n, int idx, void* host, int to_host, int device, cudaStream_t st) {
+    if (!dev_base || !host || idx < 0 || idx >= n) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
+    CK(cudaSetDevice(device));
+    CK(cudaStreamSynchronize(st));
+    char* p = (char*)dev_base + stride * (size_t)idx;
+    if (to_host) CK(cudaMemcpy(host, p, stride, cudaMemcpyDeviceToHost));
+    else CK(cudaMemcpy(p, host, stride, cudaMemcpyHostToDevice));
+    return 0;
+}
+int solo_b200_enc_batch_export_state(solo_b200_enc_batch* b, int idx, void* blob) {
+    if (!b) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
+    return state_copy(b->d_states, sizeof(EncState), b->n, idx, blob, 1, b->device, b->stream);
+}
+int solo_b200_enc_batch_import_state(solo_b200_enc_batch* b, int idx, const void* blob) {
+    if (!b) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
+    return state_copy(b->d_states, sizeof(EncState), b->n, idx, (void*)blob, 0, b->device, b->stream);
+}
+int solo_b200_dec_batch_export_state(solo_b200_dec_batch* b, int idx, void* blob) {
+    if (!b) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
+    return state_copy(b->d_states, sizeof(DecState), b->n, idx, blob, 1, b->device, b->stream);
+}
+int solo_b200_dec_batch_import_state(solo_b200_dec_batch* b, int idx, const void* blob) {
+    if (!b) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
+    return state_copy(b->d_states, sizeof(DecState), b->n, idx, (void*)blob, 0, b->device, b->stream);
+}
+
+// ---- packet framing (host, no GPU involved): enc_main.c:212-234 / dec_main.c:196-307 / README "Bitstream sending" --------
+int solo_b200_split_packet(const uint8_t* bits, const int16_t* nbytes, const uint8_t** p1, int* n1, const uint8_t** p2, int* n2) {
+    if (!bits || !nbytes || !p1 || !n1 || !p2 || !n2) return -1;
+    const int t = nbytes[0], m2 = nbytes[1];
+    if (t <= 0) { *p1 = *p2 = bits; *n1 = *n2 = 0; return 0; }    // DTX: nothing to send (enc_API.c:260-265)
+    if (m2 < 8 || m2 > t) return -1;
+    *p1 = bits; *n1 = t - m2;          // description 1: low band only
+    *p2 = bits + (t - m2); *n2 = m2;   // description 2: low band + the 8 high-band bytes
+    return 0;
+}
+int solo_b200_merge_packets(const uint8_t* p1, int n1, const uint8_t* p2, int n2, uint8_t* bits, int cap, int16_t* nbytes, int32_t* lostflag) {
+    if (!bits || !nbytes || !lostflag || n1 < 0 || n2 < 0) return -1;
+    const int have1 = p1 && n1 > 0, have2 = p2 && n2 > 0;
+    if (have1 && have2) {
+        if (n1 + n2 > cap) return -1;
+        memmove(bits, p1, (size_t)n1); memmove(bits + n1, p2, (size_t)n2);
+        nbytes[0] = (int16_t)(n1 + n2); nbytes[1] = (int16_t)n2; *lostflag = 4;
+    } else if (have1) {
+        if (n1 > cap) return -1;
+        memmove(bits, p1, (size_t)n1); nbytes[0] = (int16_t)n1; nbytes[1] = 0; *lostflag = 2;
+    } else if (have2) {
+        if (n2 > cap) return -1;
+        memmove(bits, p2, (size_t)n2); nbytes[0] = (int16_t)n2; nbytes[1] = 0; *lostflag = 3;
+    } else {
+        // nothing arrived: the decoder conceals; it still wants nBytes[0] > 0 (AGR_BWE_SDK_API.c:268-270), the bytes are not read
+        nbytes[0] = 16; nbytes[1] = 8; *lostflag = 1;
+        if (cap >= 16) memset(bits, 0, 16);
+    }
+    return 0;
+}
+// one record of the reference's .bit file: int16 total, int16 len(MD2)+8, payload (little endian as written by fwrite on x86)
+int solo_b200_bitfile_pack(const uint8_t* bits, const int16_t* nbytes, uint8_t* out, int out_cap) {
+    if (!bits || !nbytes || !out) return -1;
+    const int t = nbytes[0] > 0 ? nbytes[0] : 0;
+    if (out_cap < 4 + t) return -1;
+    out[0] = (uint8_t)(nbytes[0] & 0xff); out[1] = (uint8_t)((nbytes[0] >> 8) & 0xff);
+    out[2] = (uint8_t)(nbytes[1] & 0xff); out[3] = (uint8_t)((nbytes[1] >> 8) & 0xff);
+    memcpy(out + 4, bits, (size_t)t);
+    return 4 + t;
+}
+int solo_b200_bitfile_unpack(const uint8_t* in, int in_len, const uint8_t** payload, int16_t* nbytes) {
+    if (!in || !payload || !nbytes || in_len < 4) return -1;
+    nbytes[0] = (int16_t)(in[0] | (in[1] << 8)); nbytes[1] = (int16_t)(in[2] | (in[3] << 8));
+    if (nbytes[0] < 0 || nbytes[1] < 0 || 4 + nbytes[0] > in_len) return -1;
+    *payload = in + 4;
+    return 4 + nbytes[0];
+}
+int solo_b200_apply_loss_device(const uint8_t* d_bits_in, const int16_t* d_nbytes_in, const int32_t* d_lostflag, uint8_t* d_bits_out,
+                                int16_t* d_nbytes_out, int cap, int n, void* cuda_stream) {
+    if (!d_bits_in || !d_nbytes_in || !d_lostflag || !d_bits_out || !d_nbytes_out || cap < 16 || n <= 0) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
+    sb_apply_loss_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)cuda_stream>>>(d_bits_in, d_nbytes_in, d_lostflag, d_bits_out, d_nbytes_out, cap, n);
+    count_launch();
+    CK(cudaGetLastError());
+    return 0;
 }
 
 // ---- single-stream drop-in entry points (AGR_JC1_SDK_API.h) -------------------------------------------------------

@@ -1,0 +1,130 @@
+"""On-device checks of the pieces around the hot path: pipelining invariance, ragged batch sizes, stream state hand-over
+ and receiver-side loss trimming for a whole batch on the GPU (rank 1)."""
+import numpy as np
+import pytest
+
+from tests.util import load_clip, load_golden, loss_flags, speech_replay, trim_payload
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import solo_b200
+    solo_b200.lib()
+    return solo_b200
+
+
+def run_streams(sb, N, T, cap=128, flags=None, rate=13600):
+    x = speech_replay(load_clip(), N, T)
+    eb, db = sb.EncoderBatch(N, rate=rate), sb.DecoderBatch(N)
+    out = []
+    for p in range(T):
+        bits, nb = eb.encode(x[p], cap=cap)
+        f = np.full(N, 4, np.int32) if flags is None else flags[:, p].copy()
+        pcm, ret = db.decode(bits, nb, f)
+        out.append((bits.copy(), nb.copy(), pcm.copy(), ret.copy()))
+    eb.close(); db.close()
+    return out
+
+
+def test_results_do_not_depend_on_the_number_of_pipeline_chunks(sb):
+    N, T = 8192 + 64 + 5, 3          # ragged: not a multiple of the chunk granularity, odd (a shadowed lane group in the NSQ kernel)
+    ref = None
+    for chunks in (1, 2, 3, 8):
+        sb.set_chunks(chunks)
+        got = run_streams(sb, N, T)
+        if ref is None:
+            ref = got
+            g = load_golden()            # stream 0 of the speech-replay batch reads the clip from offset 0 at gain 1
+            for p in range(T):
+                n0 = int(g["fix_nbytes"][p, 0])
+                assert tuple(got[p][1][0]) == tuple(g["fix_nbytes"][p])
+                assert bytes(got[p][0][0, :n0]) == bytes(g["fix_bits"][p, :n0])
+        else:
+            for a, b in zip(ref, got):
+                for u, v in zip(a, b):
+                    assert np.array_equal(u, v), chunks
+    sb.set_chunks(2)
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 63, 65])
+def test_small_and_odd_batches_match_the_single_stream_result(sb, N):
+    T = 4
+    got = run_streams(sb, N, T, cap=256)
+    x = speech_replay(load_clip(), N, T)
+    for s in sorted({0, N // 2, N - 1}):
+        e, d = sb.SoloEncoder(rate=13600), sb.SoloDecoder()
+        for p in range(T):
+            b, nb, n = e.encode(x[p, s])
+            assert nb == tuple(got[p][1][s]) and b == bytes(got[p][0][s, :n])
+            pcm, r = d.decode(b, nb, 4)
+            assert np.array_equal(pcm, got[p][2][s])
+        e.close(); d.close()
+
+
+def test_state_export_import_continues_bit_exactly(sb):
+    """A stream leaves one batch (slot 5 of 16) after 6 packets and joins another one (slot 2 of 4, other streams at a
+    different point of their lives): its payloads and decoded PCM continue as if nothing had happened."""
+    T0, T1, cap = 6, 6, 256
+    x = speech_replay(load_clip(), 16, T0 + T1)
+    eb, db = sb.EncoderBatch(16), sb.DecoderBatch(16)
+    want = []
+    for p in range(T0 + T1):
+        bits, nb = eb.encode(x[p], cap=cap)
+        pcm, ret = db.decode(bits, nb, np.full(16, 4, np.int32))
+        want.append((bytes(bits[5, :nb[5, 0]]), tuple(nb[5]), pcm[5].copy()))
+        if p == T0 - 1:
+            enc_blob, dec_blob = eb.export_state(5), db.export_state(5)
+    eb.close(); db.close()
+    assert enc_blob.size == sb.lib().solo_b200_enc_state_bytes() and dec_blob.size == sb.lib().solo_b200_dec_state_bytes()
+    eb2, db2 = sb.EncoderBatch(4), sb.DecoderBatch(4)
+    y = speech_replay(load_clip(), 4, 3, first_packet=40)
+    for p in range(3):                                   # the new batch already has a history
+        bits, nb = eb2.encode(y[p], cap=cap)
+        db2.decode(bits, nb, np.full(4, 4, np.int32))
+    eb2.import_state(2, enc_blob); db2.import_state(2, dec_blob)
+    for p in range(T0, T0 + T1):
+        xin = speech_replay(load_clip(), 4, 1, first_packet=50 + p)[0]
+        xin[2] = x[p, 5]
+        bits, nb = eb2.encode(xin, cap=cap)
+        pcm, ret = db2.decode(bits, nb, np.full(4, 4, np.int32))
+        assert (bytes(bits[2, :nb[2, 0]]), tuple(nb[2])) == want[p][:2], p
+        assert np.array_equal(pcm[2], want[p][2]), p
+    with pytest.raises(sb.SoloError):
+        eb2.import_state(7, enc_blob)                    # no such slot
+    eb2.close(); db2.close()
+
+
+def test_loss_trimming_on_device_matches_the_receiver_restatement(sb):
+    import torch
+    N, cap, T = 4096, 128, 3
+    x = speech_replay(load_clip(), N, T)
+    eb, db, db_ref = sb.EncoderBatch(N), sb.DecoderBatch(N), sb.DecoderBatch(N)
+    flags = np.array([loss_flags(T, 50, seed=1 + s) for s in range(N)], np.int32)
+    dev = torch.device("cuda", 0)
+    for p in range(T):
+        bits, nb = eb.encode(x[p], cap=cap)
+        f = flags[:, p].copy()
+        # host restatement of dec_main.c:245-307, row by row
+        hb, hn = np.zeros((N, cap), np.uint8), np.zeros((N, 2), np.int16)
+        for s in range(N):
+            pb, pnb = trim_payload(bytes(bits[s, :nb[s, 0]]), nb[s], f[s])
+            hb[s, :len(pb)] = np.frombuffer(pb, np.uint8)
+            hn[s] = pnb
+        want, wret = db_ref.decode(hb, hn, f)
+        # the same on the device, feeding the device decode entry point
+        d_in, d_nb, d_f = torch.from_numpy(bits).to(dev), torch.from_numpy(nb).to(dev), torch.from_numpy(f).to(dev)
+        d_out, d_onb = torch.zeros_like(d_in), torch.zeros_like(d_nb)
+        d_pcm, d_ret = torch.zeros((N, 640), dtype=torch.int16, device=dev), torch.zeros(N, dtype=torch.int32, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        sb.apply_loss_device(d_in.data_ptr(), d_nb.data_ptr(), d_f.data_ptr(), d_out.data_ptr(), d_onb.data_ptr(), cap, N, st)
+        db.decode_device(d_pcm.data_ptr(), d_out.data_ptr(), cap, d_onb.data_ptr(), d_f.data_ptr(), d_ret.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_onb.cpu().numpy(), hn)
+        keep = f != 1
+        got_rows, want_rows = d_out.cpu().numpy(), hb
+        for s in np.nonzero(keep)[0][:512]:
+            assert bytes(got_rows[s, :hn[s, 0]]) == bytes(want_rows[s, :hn[s, 0]])
+        assert np.array_equal(d_pcm.cpu().numpy(), want) and np.array_equal(d_ret.cpu().numpy(), wret)
+    eb.close(); db.close(); db_ref.close()
