@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(SB_ANA_WARPS * 32) sb_enc_analysis_warp_kernel
     copy16(&S->st, static_cast<EncCore*>(&states[s]), (int)sizeof(EncCore), lane);
     copy16(S->pcm, pcm + (size_t)s * PACKET, PACKET * 2, lane);
     __syncwarp();
+    if (lane == 0) S->W.nlsf_fast = nullptr;
+    __syncwarp();
     enc_packet_analysis(&S->st, &S->W, S->pcm, &scratch[s]);
     __syncwarp();
     copy16(static_cast<EncCore*>(&states[s]), &S->st, (int)sizeof(EncCore), lane);

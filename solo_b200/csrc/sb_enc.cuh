@@ -185,6 +185,7 @@ struct EncAnalysisWork {
     EncCtrl c;                 // control of the frame being analysed (copied to EncScratch when the frame is done)
     i16 xfw[FRAME];
     i32 vadFlag;
+    const NlsfFastTabs* nlsf_fast;   // shared-memory copies of the NLSF codebooks (null: use the global tables)
     alignas(16) unsigned char arena_mem[SB_ANA_ARENA];
 };
 
@@ -201,7 +202,7 @@ SB_FN void encode_frame_analysis(EncCore* st, EncAnalysisWork* W, Arena* A, cons
         find_pitch_lags(st, c, W->res_pitch, x_frame);
         noise_shape_analysis(st, c, W->res_pitch + FRAME, x_frame);
         prefilter(st, c, W->xfw, x_frame);
-        find_pred_coefs(st, c, W->res_pitch, frame_in_packet);
+        find_pred_coefs(st, c, W->res_pitch, frame_in_packet, W->nlsf_fast);
         process_gains(st, c, frame_in_packet);
         if (st->speech_activity_Q8 < SB_FIXC(0.1f, 8)) {
             st->vadFlag = 0;

@@ -54,8 +54,12 @@ __global__ void __launch_bounds__(SB_TPB) sb_enc_init_kernel(EncState* states, i
 //   C  sb_enc_finish_kernel   : one thread per stream  -- range coding of both descriptions, high-band gains, payload assembly
 __global__ void __launch_bounds__(SB_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ pcm, int n) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ NlsfFastTabs s_nlsf;
+    nlsf_fast_tabs_fill(&s_nlsf, threadIdx.x, blockDim.x);
+    __syncthreads();
     if (s >= n) return;
     EncAnalysisWork W;
+    W.nlsf_fast = &s_nlsf;
     i16 x[PACKET];
     // 128-bit loads of this stream's 1280-byte PCM row
     const int4* src = reinterpret_cast<const int4*>(pcm + (size_t)s * PACKET);

@@ -27,6 +27,7 @@ struct HsEnc { sb::EncState st; sb::EncPacketWork w; };
 void* hs_enc_create(int rate, int dtx, int mdi) {
     HsEnc* h = (HsEnc*)calloc(1, sizeof(HsEnc));
     sb::enc_state_init(&h->st, rate, dtx, mdi);
+    h->w.a.nlsf_fast = nullptr;
     return h;
 }
 int hs_enc_encode(void* p, const short* pcm, unsigned char* out, int cap, short* nb) {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Turn one round's ncu artefacts into the committed summaries under profiles/.
 
-usage: tools/ncu_profile_summary.py <tag> <launches.csv> <full.ncu-rep> [dominant-kernel-regex]
+usage: tools/ncu_profile_summary.py <tag> <launches.csv> <full.ncu-rep> [dominant-kernel-regex] [streams-per-launch]
   <launches.csv>  from `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ... python bench.py ...`
   <full.ncu-rep>  from `ncu --set full --clock-control none --import-source on -k regex:... -o ... python bench.py ...`
 writes profiles/<tag>_launches.txt, profiles/<tag>_full.txt and updates profiles/ncu_summary.json (read by bench.py for
@@ -17,6 +17,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]
 dom = sys.argv[4] if len(sys.argv) > 4 else "sb_enc_nsq"
+streams_per_launch = int(sys.argv[5]) if len(sys.argv) > 5 else None
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 
 # ---- launch list ----
@@ -97,5 +98,7 @@ for k, v in summary.items():
         cur["dominant_kernel"] = k
         cur["encode_kernel_dram_bytes_per_launch"] = v["dram_bytes_per_launch"]
         cur["encode_kernel_grid"] = v["grid"]
+        if streams_per_launch:
+            cur["encode_kernel_streams_per_launch"] = streams_per_launch
         cur["from"] = tag
 json.dump(cur, open(js, "w"), indent=1)
