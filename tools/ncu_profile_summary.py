@@ -15,7 +15,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]
+tag, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]   # rep: one report or several joined with ","
 dom = sys.argv[4] if len(sys.argv) > 4 else "sb_enc_nsq"
 streams_per_launch = int(sys.argv[5]) if len(sys.argv) > 5 else None
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
@@ -40,9 +40,16 @@ with open(os.path.join(ROOT, "profiles", tag + "_launches.txt"), "w") as f:
 print(open(os.path.join(ROOT, "profiles", tag + "_launches.txt")).read())
 
 # ---- full capture ----
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
-h, units, data = rr[0], rr[1], rr[2:]
+h, data, data_units = None, [], []
+for one in rep.split(","):
+    raw = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    if h is None:
+        h = rr[0]
+    pos = {n: i for i, n in enumerate(rr[0])}     # align columns (and units: they are per report) by metric name
+    for r in rr[2:]:
+        data.append([r[pos[n]] if n in pos else "" for n in h])
+        data_units.append([rr[1][pos[n]] if n in pos else "" for n in h])
 want = [
     "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
     "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
@@ -69,8 +76,12 @@ def num(s):
 
 with open(os.path.join(ROOT, "profiles", tag + "_full.txt"), "w") as f:
     f.write("# %s: ncu --set full --clock-control none --import-source on (one launch per kernel, mid-run)\n" % tag)
-    for r in data:
+    seen = set()
+    for r, units in zip(data, data_units):
         name = re.sub(r"\(.*", "", r[h.index("Kernel Name")])
+        if name in seen:
+            continue
+        seen.add(name)
         f.write("\n== %s\n" % name)
         vals = {}
         for w in want:
