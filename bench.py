@@ -279,8 +279,8 @@ def main():
     clocks = sampler.stop()
     e2e_value = world * N * K / (host_ms / 1e3)
     checksum = int(h_out.to(torch.int64).sum().item())
-    h2d = N * (1280 + CAP + 4 + 4)
-    d2h = N * (CAP + 4 + 1280 + 4)
+    h2d = world * N * (1280 + CAP + 4 + 4)      # whole job, per step: PCM in (encoder) + payload, lengths, flags in (decoder)
+    d2h = world * N * (CAP + 4 + 1280 + 4)      # payload + lengths out (encoder) + PCM, return codes out (decoder)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -296,10 +296,11 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32/int16 fixed point (encoder, SILK decoder), f32 (decoder high band + QMF)",
+            "dtype": "int32",
             "data": "synthetic (speech-replay of the codec's 16 kHz test clip, SURVEY 8(d)(i); fresh codec state)",
             "config": {"workload": "configs[2]: batch=65536 streams/GPU full encode+decode round trip (lostflag 4), 13.6 kb/s",
-                       "streams_per_gpu": N, "streams_total": world * N, "payload_cap": CAP, "mean_payload_bytes": mean_payload,
+                       "arithmetic": "int32/int16 fixed point (encoder, SILK decoder), f32 (decoder high band + QMF synthesis)",
+                       "streams_per_gpu": N, "streams_total": world * N, "pipeline_chunks": int(os.environ.get("SOLO_B200_CHUNKS", "2")), "payload_cap": CAP, "mean_payload_bytes": mean_payload,
                        "l2": "no flush: every step reads a new 84 MB PCM wave and ~0.9 GB of per-stream state (> 126 MB L2)",
                        "parallelism": "streams sharded contiguously across GPUs, no collective on the data path"},
             "streams_rt": value / 25.0,

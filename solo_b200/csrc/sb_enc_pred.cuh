@@ -414,10 +414,11 @@ SB_FN void nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb, 
     i16 log_e[SURV * 16 > 64 ? SURV * 16 : 64];
     // survivor sets of two consecutive stages: ping-pong buffers instead of the reference's copy-back (:224-229)
     i32 rate_buf[2][SURV], pTempIndices[SURV];
-    i32 path_buf[2][SURV * NST];
+    u64 path_buf[2][SURV];           // the six stage indices of a survivor, 8 bits each
     i32 res_buf[2][SURV * ORD];
     i32 *pRate_Q5 = rate_buf[0], *pRate_new_Q5 = rate_buf[1];
-    i32 *pPath = path_buf[0], *pPath_new = path_buf[1];
+    u64 *pPath = path_buf[0], *pPath_new = path_buf[1];
+    pPath[0] = 0;
     i32 *pRes_Q15 = res_buf[0], *pRes_new_Q15 = res_buf[1];
     for (int i = 0; i < SURV; i++) pRate_Q5[i] = 0;
     for (int i = 0; i < ORD; i++) pRes_Q15[i] = pNLSF_Q15[i];
@@ -471,17 +472,26 @@ SB_FN void nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb, 
             int need_eq = SURV;                       // how many elements equal to T belong to the best 16
 #pragma unroll
             for (int j = 0; j < SURV; j++) need_eq -= (ka[j] < T) ? 1 : 0;
+            // compact the 16 survivors (scan order), then place each at its rank: #{(v', pos') < (v, pos)} -- the order an
+            // insertion sort with strict comparisons produces
+            i32 tv[SURV], te[SURV];
+            for (int j = 0; j < SURV; j++) { tv[j] = SB_I32_MAX; te[j] = 0; }
             int m = 0;
             for (int q = 0; q < nlog; q++) {
                 const i32 val = log_v[q];
                 bool take = val < T;
                 if (val == T && need_eq > 0) { take = true; need_eq--; }
-                if (take) {
-                    int j = m - 1;
-                    for (; j >= 0 && val < pRateDist_Q18[j]; j--) { pRateDist_Q18[j + 1] = pRateDist_Q18[j]; pTempIndices[j + 1] = pTempIndices[j]; }
-                    pRateDist_Q18[j + 1] = val; pTempIndices[j + 1] = log_e[q];
-                    m++;
-                }
+                if (take && m < SURV) { tv[m] = val; te[m] = log_e[q]; m++; }
+            }
+            i32 rv[SURV];
+#pragma unroll
+            for (int a = 0; a < SURV; a++) rv[a] = tv[a];
+#pragma unroll
+            for (int a = 0; a < SURV; a++) {
+                int rank = 0;
+#pragma unroll
+                for (int b = 0; b < SURV; b++) rank += (rv[b] < rv[a]) | ((rv[b] == rv[a]) & (b < a));
+                pRateDist_Q18[rank] = rv[a]; pTempIndices[rank] = te[a];
             }
         }
         if (pRateDist_Q18[0] < SB_I32_MAX / SURV) {
@@ -494,21 +504,19 @@ SB_FN void nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb, 
                 if (nVec == 8) { input_index = pTempIndices[k] >> 3; cb_index = pTempIndices[k] & 7; }
                 else { input_index = pTempIndices[k] / nVec; cb_index = pTempIndices[k] - smulbb(input_index, nVec); }
             } else { input_index = 0; cb_index = pTempIndices[k]; }
-            const i32* pc = &pRes_Q15[input_index * ORD];
-            const i16* e = &CB[cb_index * ORD];
-            i32* pi = &pRes_new_Q15[k * ORD];
+            const i32* __restrict__ pc = &pRes_Q15[input_index * ORD];
+            const i16* __restrict__ e = &CB[cb_index * ORD];
+            i32* __restrict__ pi = &pRes_new_Q15[k * ORD];
+#pragma unroll
             for (int i = 0; i < ORD; i++) pi[i] = pc[i] - (i32)e[i];
             pRate_new_Q5[k] = pRate_Q5[input_index] + Rates[cb_index];
-            const i32* pp = &pPath[input_index * NST];
-            i32* pn = &pPath_new[k * NST];
-            for (int i = 0; i < s; i++) pn[i] = pp[i];
-            pn[s] = cb_index;
+            pPath_new[k] = pPath[input_index] | ((u64)(u32)cb_index << (8 * s));
         }
         if (s < NST - 1) {
             i32* t;
             t = pRes_Q15; pRes_Q15 = pRes_new_Q15; pRes_new_Q15 = t;
             t = pRate_Q5; pRate_Q5 = pRate_new_Q5; pRate_new_Q5 = t;
-            t = pPath; pPath = pPath_new; pPath_new = t;
+            { u64* tp = pPath; pPath = pPath_new; pPath_new = tp; }
         }
         prev_survivors = cur_survivors;
         cb_off += nVec;
@@ -517,7 +525,9 @@ SB_FN void nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb, 
     if (deactivate_fluc_red != 1) {
         i32 bestRateDist_Q20 = SB_I32_MAX;
         for (int s = 0; s < cur_survivors; s++) {
-            nlsf_msvq_decode(pNLSF_Q15, cb, &pPath_new[s * NST]);
+            i32 idx[NST];
+            for (int i = 0; i < NST; i++) idx[i] = (i32)((pPath_new[s] >> (8 * i)) & 0xff);
+            nlsf_msvq_decode(pNLSF_Q15, cb, idx);
             i32 wsse_Q20 = 0;
             for (int i = 0; i < ORD; i++) {
                 i32 se = pNLSF_Q15[i] - pNLSF_q_Q15_prev[i];
@@ -527,7 +537,7 @@ SB_FN void nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb, 
             if (wsse_Q20 < bestRateDist_Q20) { bestRateDist_Q20 = wsse_Q20; bestIndex = s; }
         }
     }
-    for (int i = 0; i < NST; i++) NLSFIndices[i] = pPath_new[bestIndex * NST + i];
+    for (int i = 0; i < NST; i++) NLSFIndices[i] = (i32)((pPath_new[bestIndex] >> (8 * i)) & 0xff);
     nlsf_msvq_decode(pNLSF_Q15, cb, NLSFIndices);
 }
 
