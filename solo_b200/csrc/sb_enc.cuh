@@ -62,8 +62,20 @@ SB_FN void qmf_decomp(const i16* xx, i16* y1, i16* y2, i16* mem) {
     i16 x[N + M - 1];
     const i16* aa = SB_T(qmf_fix);
     for (int i = 0; i < M - 1; i++) x[i] = mem[M - i - 2];
+#ifdef __CUDA_ARCH__
+    if ((((size_t)xx) & 15) == 0) {          // PCM rows of the batch buffers: 128-bit loads straight from global memory
+        const int4* src = reinterpret_cast<const int4*>(xx);
+#pragma unroll 2
+        for (int i = 0; i < N / 8; i++) {
+            const int4 v = src[i];
+            i16* d = &x[8 * i + M - 1];
+            d[0] = (i16)((i16)v.x >> 1); d[1] = (i16)(v.x >> 17); d[2] = (i16)((i16)v.y >> 1); d[3] = (i16)(v.y >> 17);
+            d[4] = (i16)((i16)v.z >> 1); d[5] = (i16)(v.z >> 17); d[6] = (i16)((i16)v.w >> 1); d[7] = (i16)(v.w >> 17);
+        }
+    } else
+#endif
     for (int i = 0; i < N; i++) x[i + M - 1] = (i16)(xx[i] >> 1);
-    for (int i = 0; i < M - 1; i++) mem[i] = (i16)(xx[N - i - 1] >> 1);
+    for (int i = 0; i < M - 1; i++) mem[i] = x[N + M - 2 - i];   // == xx[N - i - 1] >> 1
     const i16* x2 = x + M - 1;
     for (int i = 0, k = 0; i < N; i += 2, k++) {
         i32 y1k = 0, y2k = 0;

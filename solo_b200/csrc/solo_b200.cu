@@ -60,12 +60,7 @@ __global__ void __launch_bounds__(SB_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_kern
     if (s >= n) return;
     EncAnalysisWork W;
     W.nlsf_fast = &s_nlsf;
-    i16 x[PACKET];
-    // 128-bit loads of this stream's 1280-byte PCM row
-    const int4* src = reinterpret_cast<const int4*>(pcm + (size_t)s * PACKET);
-    int4* dst = reinterpret_cast<int4*>(x);
-#pragma unroll 4
-    for (int i = 0; i < PACKET * 2 / 16; i++) dst[i] = src[i];
+    const i16* x = pcm + (size_t)s * PACKET;   // read once, with 128-bit loads, by the QMF split
 #if SB_ANALYSIS_LOCAL_STATE
     // analysis state staged in local memory: same-offset words of the 32 streams of a warp share cache lines there
     EncCore st = static_cast<const EncCore&>(states[s]);
