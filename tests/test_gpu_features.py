@@ -128,3 +128,67 @@ def test_loss_trimming_on_device_matches_the_receiver_restatement(sb):
             assert bytes(got_rows[s, :hn[s, 0]]) == bytes(want_rows[s, :hn[s, 0]])
         assert np.array_equal(d_pcm.cpu().numpy(), want) and np.array_equal(d_ret.cpu().numpy(), wret)
     eb.close(); db.close(); db_ref.close()
+
+
+def test_config2_batch_4096_streams_50_packets_sampled_against_reference(sb):
+    """BASELINE config 2: 4 096 concurrent streams, encode only, 50 packets (2 s).  Every stream runs on the GPU; 64 of
+    them (spread over the batch, all four input gains) are replayed through libjc1_fix.so and must match byte for byte."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    N, T, cap = 4096, 50, 160
+    clip = load_clip()
+    sample = sorted(set(list(range(0, N, 67)) + [1, 2, 3, N - 1]))[:64]
+    refs = {s: ref.RefEncoder("fix", rate=13600) for s in sample}
+    eb = sb.EncoderBatch(N, rate=13600)
+    for p in range(T):
+        x = speech_replay(clip, N, 1, first_packet=p)[0]
+        bits, nb = eb.encode(x, cap=cap)
+        assert (nb[:, 0] <= cap).all()
+        for s in sample:
+            b, rnb, n = refs[s].encode(x[s])
+            assert tuple(nb[s]) == rnb and bytes(bits[s, :n]) == b, (p, s)
+    eb.close()
+
+
+def test_config5_full_batch_with_per_stream_loss_sampled_against_reference(sb):
+    """BASELINE configs 3 + 5 at full size: 65 536 streams, encode -> receiver-side trimming on the device -> decode with
+    a 50 % loss process per stream (seed 1 + stream id, dec_main.c:229-241); 48 sampled streams against libjc1_flp.so fed
+    the same payloads and flags (PCM identical; the north star allows +-1 LSB)."""
+    import torch
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    N, T, cap = 65536, 8, 128
+    clip = load_clip()
+    sample = [0, 1, 2, 3] + list(range(997, N, 1489))[:44]
+    flags = np.full((N, T), 4, np.int32)
+    for s in sample:
+        flags[s] = loss_flags(T, 50, seed=1 + s)
+    rng = np.random.Generator(np.random.PCG64(7))
+    other = rng.integers(1, 5, size=(N, T)).astype(np.int32)       # everybody else: arbitrary flags
+    mask = np.ones(N, bool); mask[sample] = False
+    flags[mask] = other[mask]
+    dev = torch.device("cuda", 0)
+    eb, db = sb.EncoderBatch(N), sb.DecoderBatch(N)
+    rdec = {s: ref.RefDecoder("flp") for s in sample}
+    d_bits, d_nb = torch.zeros((N, cap), dtype=torch.uint8, device=dev), torch.zeros((N, 2), dtype=torch.int16, device=dev)
+    d_tb, d_tnb = torch.zeros_like(d_bits), torch.zeros_like(d_nb)
+    d_pcm, d_ret = torch.zeros((N, 640), dtype=torch.int16, device=dev), torch.zeros(N, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    for p in range(T):
+        x = torch.from_numpy(speech_replay(clip, N, 1, first_packet=p)[0]).to(dev)
+        f = torch.from_numpy(flags[:, p].copy()).to(dev)
+        eb.encode_device(x.data_ptr(), d_bits.data_ptr(), cap, d_nb.data_ptr(), st)
+        sb.apply_loss_device(d_bits.data_ptr(), d_nb.data_ptr(), f.data_ptr(), d_tb.data_ptr(), d_tnb.data_ptr(), cap, N, st)
+        db.decode_device(d_pcm.data_ptr(), d_tb.data_ptr(), cap, d_tnb.data_ptr(), f.data_ptr(), d_ret.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert int((d_ret != 0).sum().item()) == 0
+        idx = torch.tensor(sample, device=dev)
+        bits, nb, pcm = d_bits[idx].cpu().numpy(), d_nb[idx].cpu().numpy(), d_pcm[idx].cpu().numpy()
+        for i, s in enumerate(sample):
+            pb, pnb = trim_payload(bytes(bits[i, :nb[i, 0]]), nb[i], int(flags[s, p]))
+            want, r = rdec[s].decode(pb, pnb, int(flags[s, p]))
+            assert r == 0
+            assert np.abs(pcm[i].astype(np.int32) - want.astype(np.int32)).max() <= 0, (p, s, int(flags[s, p]))
+    eb.close(); db.close()
