@@ -421,7 +421,7 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                         const bool tn = rb[m] < RDmin2; RDmin2 = tn ? rb[m] : RDmin2; imn = tn ? m : imn; j1n = tn ? j1[m] : j1n;
                     }
                     const bool doit = it < my_trips && RDmin2 < RDmax;
-                    {
+                    if (__any_sync(fm, doit)) {   // warp-uniform: skip the 40 shuffles when neither stream replaces a state
                         const int src = qz * 4 + imn;
                         const bool tgt = doit && (s == imx);
                         const int from = tgt ? src : gl;   // everybody else reads itself: no select after the shuffle
