@@ -1,13 +1,13 @@
 // solo_b200 -- sm_100a kernels and the C ABI of libsolo_b200.so.
 //
-// Mapping (round 1): one codec stream per thread, 32 independent streams per warp.  Every heavy loop of
-// the codec (the 160-sample x 12-recurrence MD noise-shaping quantiser, the warped autocorrelations, the
-// codebook searches) has data-independent trip counts, so the 32 streams of a warp run them in lock-step
-// with full lane utilisation and no shuffles; per-thread scratch (`EncPacketWork`, ~35 KB) lives in local
-// memory, which the hardware interleaves per lane so that the warp's accesses to the same scratch element
-// coalesce.  Persistent per-stream state lives in a device arena (array of EncState / DecState) that never
-// leaves the GPU between packets.  See DESIGN.md for the measured consequences and the plan for the
-// warp-cooperative NSQ.
+// One packet wave = four kernels:
+//   A  sb_enc_analysis_kernel  thread per stream   QMF split, VAD .. gain processing of both 20 ms frames, high-band analysis
+//   B  sb_enc_nsq_kernel       two streams / warp  MD delayed-decision noise-shaping quantiser, history in shared memory
+//   C  sb_enc_finish_kernel    thread per stream   range coding of both descriptions, high-band gains, payload assembly
+//   D  sb_decode_kernel        thread per stream   the whole decoder incl. concealment, high band and QMF synthesis
+// Persistent per-stream state lives in device arrays (EncState / DecState) that never leave the GPU between packets;
+// a wave is processed as a few chunks of streams on internal CUDA streams (Pipe).  The host code below is the C ABI:
+// the batched entry points of include/solo_b200.h and the reference's six functions of include/AGR_JC1_SDK_API.h.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
