@@ -192,3 +192,16 @@ def test_config5_full_batch_with_per_stream_loss_sampled_against_reference(sb):
             assert r == 0
             assert np.abs(pcm[i].astype(np.int32) - want.astype(np.int32)).max() <= 0, (p, s, int(flags[s, p]))
     eb.close(); db.close()
+
+
+def test_single_stream_small_output_buffer(sb):
+    """Same contract through the drop-in ABI on the GPU (the caller's buffer may be smaller than the packet)."""
+    g = load_golden()
+    clip = load_clip()
+    for cap in (64, 9):
+        e = sb.SoloEncoder(rate=13600)
+        for p in range(6):
+            b, nb, n = e.encode(clip[p * 640:(p + 1) * 640], bufsize=cap)
+            n0 = int(g["fix_nbytes"][p, 0])
+            assert nb == tuple(g["fix_nbytes"][p]) and n == min(cap, n0) and b == bytes(g["fix_bits"][p, :n])
+        e.close()

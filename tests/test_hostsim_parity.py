@@ -140,3 +140,23 @@ def test_random_rates_and_signals_match_reference(sim, ref):
                     y1, _ = d1.decode(pb[:n], nb, 4)
                 assert np.abs(y0.astype(np.int32) - y1.astype(np.int32)).max() <= PCM_TOL
             d0.close(); d1.close()
+
+
+def test_small_output_buffer_matches_reference(sim, ref):
+    """AGR_Sate_Buf_Size smaller than the packet (AGR_BWE_bits.c:166-168): the return value is min(cap, total), the length
+    fields still describe the whole packet, bytes past the cap are left alone."""
+    import ctypes as C
+    clip = load_clip()
+    for cap in (100, 64, 16, 9, 4):
+        e, s = ref.RefEncoder("fix", rate=24000), sim.SimEncoder(rate=24000, cap=cap)
+        for p in range(12):
+            pcm = np.ascontiguousarray(clip[p * 640:(p + 1) * 640])
+            bits = (C.c_uint8 * 1024)()
+            C.memset(bits, 0xAA, 1024)
+            nb = (C.c_int16 * 6)()
+            n = e.L.AGR_Sate_Encoder_Encode(e.h, pcm.ctypes.data, bits, cap, nb)
+            s.out[:] = 0xAA
+            b2, nb2, n2 = s.encode(pcm)
+            assert n == n2 == min(cap, nb[0]) and (nb[0], nb[1]) == nb2
+            assert bytes(bits[:n]) == bytes(s.out[:n]) and bytes(bits[cap:cap + 8]) == b"\xaa" * 8
+        e.close(); s.close()
