@@ -11,7 +11,10 @@
  *   *_device  : buffers are device pointers; the call only enqueues kernels on `cuda_stream`
  *               (a cudaStream_t passed as void*; NULL = legacy default stream) and does not synchronise.
  *
- * Layouts (row = stream):  pcm  int16 [N][640]        bits uint8 [N][cap]
+ * Packet size: ctrl->framesize_ms = 40 (two 20 ms codec frames per packet, 8 high-band bytes, 640 samples per row) or 20
+ * (one frame, 4 high-band bytes, 320 samples per row) -- the two packet sizes of the reference (AGR_BWE_SDK_API.c:78-110).
+ *
+ * Layouts (row = stream):  pcm  int16 [N][16 * framesize_ms]   bits uint8 [N][cap]
  *                          nbytes int16 [N][2]        ({total, len(MD2)+8} as the single-stream API)
  *                          lostflag int32 [N]         (1 lost, 2 MD1 only, 3 MD2+HB only, 4 both)
  * For decode, row i of `bits` holds the payload exactly as the caller would hand it to

@@ -62,16 +62,17 @@ def lib(kind):
 class RefEncoder:
     """One reference encoder handle (kind = 'fix' | 'flp')."""
 
-    def __init__(self, kind="fix", rate=13600, dtx=0, use_md_index=0):
+    def __init__(self, kind="fix", rate=13600, dtx=0, use_md_index=0, framesize_ms=40):
         self.L = lib(kind).lib
-        self.ctrl = EncCtrl(2, rate, 16000, dtx, 40, 0, 0, use_md_index)
+        self.samples = 16 * framesize_ms
+        self.ctrl = EncCtrl(2, rate, 16000, dtx, framesize_ms, 0, 0, use_md_index)
         self.h = self.L.AGR_Sate_Encoder_Init(C.byref(self.ctrl))
         self._bits = (C.c_uint8 * 1024)()
         self._nb = (C.c_int16 * 6)()
 
     def encode(self, pcm640):
         pcm = np.ascontiguousarray(pcm640, dtype=np.int16)
-        assert pcm.size == 640
+        assert pcm.size == self.samples
         C.memset(self._nb, 0, 12)
         n = self.L.AGR_Sate_Encoder_Encode(self.h, pcm.ctypes.data, self._bits, 1024, self._nb)
         return bytes(self._bits[:max(n, 0)]), (int(self._nb[0]), int(self._nb[1])), n
@@ -87,9 +88,10 @@ class RefEncoder:
 class RefDecoder:
     """One reference decoder handle (kind = 'flp' is the PCM parity target)."""
 
-    def __init__(self, kind="flp", use_md_index=0):
+    def __init__(self, kind="flp", use_md_index=0, framesize_ms=40):
         self.L = lib(kind).lib
-        self.ctrl = DecCtrl(0, 16000, 40, 0, 0, use_md_index)
+        self.samples = 16 * framesize_ms
+        self.ctrl = DecCtrl(0, 16000, framesize_ms, 0, 0, use_md_index)
         self.h = self.L.AGR_Sate_Decoder_Init(C.byref(self.ctrl))
         self._out = np.zeros(960, dtype=np.int16)
         self._ns = C.c_int16(0)
@@ -99,7 +101,7 @@ class RefDecoder:
         buf = (C.c_uint8 * 1024)(*payload) if payload else (C.c_uint8 * 1024)()
         nb = (C.c_int16 * 6)(int(nbytes[0]), int(nbytes[1]))
         ret = self.L.AGR_Sate_Decoder_Decode(self.h, self._out.ctypes.data, C.byref(self._ns), buf, nb, int(lostflag))
-        return self._out[:640].copy(), ret
+        return self._out[:self.samples].copy(), ret
 
     def close(self):
         if self.h:

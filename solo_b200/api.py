@@ -117,10 +117,11 @@ class SoloEncoder:
             raise SoloError("AGR_Sate_Encoder_Init returned NULL: " + _err())
         self._bits = np.zeros(1024, np.uint8)
         self._nb = np.zeros(6, np.int16)
+        self.samples = 16 * framesize_ms
 
     def encode(self, pcm640, bufsize=1024):
         pcm = np.ascontiguousarray(pcm640, dtype=np.int16)
-        assert pcm.size == PACKET
+        assert pcm.size == self.samples
         self._nb[:] = 0
         n = lib().AGR_Sate_Encoder_Encode(self.h, pcm.ctypes.data, self._bits.ctypes.data, bufsize, self._nb.ctypes.data)
         return bytes(self._bits[:max(n, 0)]), (int(self._nb[0]), int(self._nb[1])), n
@@ -143,6 +144,7 @@ class SoloDecoder:
             raise SoloError("AGR_Sate_Decoder_Init returned NULL: " + _err())
         self._out = np.zeros(960, np.int16)
         self._ns = C.c_int16(0)
+        self.samples = 16 * framesize_ms
 
     def decode(self, payload, nbytes, lostflag):
         buf = np.zeros(1040, np.uint8)
@@ -151,7 +153,7 @@ class SoloDecoder:
         ret = lib().AGR_Sate_Decoder_Decode(self.h, self._out.ctypes.data, C.byref(self._ns), buf.ctypes.data, nb.ctypes.data, int(lostflag))
         self.last_nbytes = (int(nb[0]), int(nb[1]))
         self.last_nsamples = int(self._ns.value)
-        return self._out[:PACKET].copy(), ret
+        return self._out[:self.samples].copy(), ret
 
     def close(self):
         if getattr(self, "h", None):
@@ -164,9 +166,10 @@ class SoloDecoder:
 class EncoderBatch:
     """N encoder streams resident on one GPU; one call = one 40 ms packet for every stream."""
 
-    def __init__(self, n, rate=13600, dtx=0, use_md_index=0, device=0):
+    def __init__(self, n, rate=13600, dtx=0, use_md_index=0, device=0, framesize_ms=40):
         self.n = int(n)
-        self.ctrl = EncCtrl(2, rate, 16000, dtx, 40, 0, 0, use_md_index)
+        self.samples = 16 * framesize_ms          # samples per packet and stream (row length of the PCM matrix)
+        self.ctrl = EncCtrl(2, rate, 16000, dtx, framesize_ms, 0, 0, use_md_index)
         self.h = lib().solo_b200_enc_batch_create(self.n, C.byref(self.ctrl), device)
         if not self.h:
             raise SoloError("solo_b200_enc_batch_create failed: " + _err())
@@ -174,7 +177,7 @@ class EncoderBatch:
     def encode(self, pcm, cap=256, bits=None, nbytes=None):
         """pcm: int16 [N, 640] host array -> (bits uint8 [N, cap], nbytes int16 [N, 2])."""
         pcm = np.ascontiguousarray(pcm, dtype=np.int16)
-        assert pcm.shape == (self.n, PACKET)
+        assert pcm.shape == (self.n, self.samples)
         if bits is None:
             bits = np.empty((self.n, cap), np.uint8)
         if nbytes is None:
@@ -218,9 +221,10 @@ class EncoderBatch:
 class DecoderBatch:
     """N decoder streams resident on one GPU."""
 
-    def __init__(self, n, use_md_index=0, device=0):
+    def __init__(self, n, use_md_index=0, device=0, framesize_ms=40):
         self.n = int(n)
-        self.ctrl = DecCtrl(0, 16000, 40, 0, 0, use_md_index)
+        self.samples = 16 * framesize_ms
+        self.ctrl = DecCtrl(0, 16000, framesize_ms, 0, 0, use_md_index)
         self.h = lib().solo_b200_dec_batch_create(self.n, C.byref(self.ctrl), device)
         if not self.h:
             raise SoloError("solo_b200_dec_batch_create failed: " + _err())
@@ -232,7 +236,7 @@ class DecoderBatch:
         lostflag = np.ascontiguousarray(lostflag, dtype=np.int32)
         assert bits.shape[0] == self.n and nbytes.shape == (self.n, 2) and lostflag.shape == (self.n,)
         if pcm is None:
-            pcm = np.zeros((self.n, PACKET), np.int16)
+            pcm = np.zeros((self.n, self.samples), np.int16)
         if ret is None:
             ret = np.zeros(self.n, np.int32)
         r = lib().solo_b200_dec_batch_decode_host(self.h, pcm.ctypes.data, bits.ctypes.data, bits.shape[1], nbytes.ctypes.data,

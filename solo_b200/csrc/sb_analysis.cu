@@ -30,14 +30,14 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, int bytes, in
     for (int i = lane; i < bytes / 16; i += 32) d[i] = s[i];
 }
 
-__global__ void __launch_bounds__(SB_ANA_WARPS * 32) sb_enc_analysis_warp_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ pcm, int n) {
+__global__ void __launch_bounds__(SB_ANA_WARPS * 32) sb_enc_analysis_warp_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ pcm, int spp, int n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x * SB_ANA_WARPS + w;
     if (s >= n) return;
     AnaSmem* S = reinterpret_cast<AnaSmem*>(smem_raw) + w;
     copy16(&S->st, static_cast<EncCore*>(&states[s]), (int)sizeof(EncCore), lane);
-    copy16(S->pcm, pcm + (size_t)s * PACKET, PACKET * 2, lane);
+    copy16(S->pcm, pcm + (size_t)s * spp, spp * 2, lane);
     __syncwarp();
     if (lane == 0) S->W.nlsf_fast = nullptr;
     __syncwarp();
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(SB_ANA_WARPS * 32) sb_enc_analysis_warp_kernel
 }  // namespace
 
 // called from the host code in solo_b200.cu; returns a CUDA error code
-extern "C" int sb_launch_enc_analysis_warp(void* states, void* scratch, const void* pcm, int n, void* stream) {
+extern "C" int sb_launch_enc_analysis_warp(void* states, void* scratch, const void* pcm, int spp, int n, void* stream) {
     static bool configured = false;
     const int smem = SB_ANA_WARPS * (int)sizeof(AnaSmem);
     if (!configured) {
@@ -58,6 +58,6 @@ extern "C" int sb_launch_enc_analysis_warp(void* states, void* scratch, const vo
         configured = true;
     }
     sb_enc_analysis_warp_kernel<<<(n + SB_ANA_WARPS - 1) / SB_ANA_WARPS, SB_ANA_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        (EncState*)states, (EncScratch*)scratch, (const i16*)pcm, n);
+        (EncState*)states, (EncScratch*)scratch, (const i16*)pcm, spp, n);
     return (int)cudaGetLastError();
 }

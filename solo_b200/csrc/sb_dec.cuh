@@ -26,6 +26,7 @@ struct DecMd {
 
 struct DecState {
     i32 useMDIndex;
+    i32 frames_per_packet;  // 2: 40 ms packets, 1: 20 ms packets
     i32 seen_good;  // 0 until the first frame has been range-decoded (reference state is still at fs = 24 kHz)
     DecMd md[2];
     i32 prev_inv_gain_Q16;
@@ -63,9 +64,10 @@ struct DecCtrl {
 };
 
 // SKP_Silk_init_decoder + AGR_Sate_Decoder_Init, expressed for the 8 kHz core the first good frame selects.
-SB_FN void dec_state_init(DecState* st, i32 useMDIndex) {
+SB_FN void dec_state_init(DecState* st, i32 useMDIndex, i32 framesize_ms = 40) {
     memset(st, 0, sizeof(DecState));
     st->useMDIndex = useMDIndex;
+    st->frames_per_packet = framesize_ms == 20 ? 1 : 2;
     st->first_frame_after_reset = 1;
     st->prev_inv_gain_Q16 = 65536;
     st->lagPrev = 100;
@@ -81,11 +83,11 @@ SB_FN void dec_state_init(DecState* st, i32 useMDIndex) {
 
 // Length split of AGR_Sate_decode_process (AGR_BWE_decode_frame_FLP.c:171-190): {n0, n1} as passed by the
 // caller -> {len(description in slot 0), len(description in slot 1)}; returns the byte offset of the HB bits.
-SB_HD i32 dec_split_lengths(i16* nb, i32 lostflag) {
+SB_HD i32 dec_split_lengths(i16* nb, i32 lostflag, int hb_bytes) {
     i32 total = nb[0];
-    i32 n0 = lostflag == 2 ? total : total - 8;
+    i32 n0 = lostflag == 2 ? total : total - hb_bytes;
     i32 n1 = nb[1];
-    if (n1) n1 -= 8;
+    if (n1) n1 -= hb_bytes;
     i32 hb_off = n0;
     n0 -= n1;
     nb[0] = (i16)n0;
@@ -607,10 +609,10 @@ SB_FN i32 dec_silk_frame(DecState* st, DecCtrl* c, RangeDec* rc, i32 (*Pulses)[F
     return ret;
 }
 
-// ---- AGR_Sate_qmf_synth, float branch (AGR_BWE_qmf.c:86-182), N = 640, M = 64 --------------------------------------
-SB_FN void qmf_synth_f32(const float* x1, const float* x2, float* y, float* mem1, float* mem2) {
-    enum { N = PACKET, M = 64, M2 = 32, N2 = 320 };
-    float xx1[M2 + N2], xx2[M2 + N2];
+// ---- AGR_Sate_qmf_synth, float branch (AGR_BWE_qmf.c:86-182), N = 2 * N2 = 640 or 320, M = 64 ----------------------
+SB_FN void qmf_synth_f32(const float* x1, const float* x2, float* y, float* mem1, float* mem2, int N2) {
+    enum { M = 64, M2 = 32, N2MAX = PACKET / 2 };
+    float xx1[M2 + N2MAX], xx2[M2 + N2MAX];
     const float* a = SB_T(qmf_flt);
     for (int i = 0; i < N2; i++) xx1[i] = x1[N2 - 1 - i];
     for (int i = 0; i < M2; i++) xx1[N2 + i] = mem1[2 * i + 1];
@@ -711,9 +713,10 @@ SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, 
     if (nb_in[0] <= 0) return -1;
     if (lostflag < 1 || lostflag > 4) return -1;
     i16 nb[2] = {nb_in[0], nb_in[1]};
-    i32 hb_off = dec_split_lengths(nb, lostflag);
+    const int nf = st->frames_per_packet, hb_bytes = 4 * nf, half = nf * FRAME;   // frames, high-band bytes, samples per band
+    i32 hb_off = dec_split_lengths(nb, lostflag, hb_bytes);
     int n0 = nb[0], n1 = nb[1];
-    if (n0 < 0 || n1 < 0 || n0 + n1 > cap || hb_off + 8 > cap + 8) return -1;
+    if (n0 < 0 || n1 < 0 || n0 + n1 > cap || hb_off > cap) return -1;
     // zero-padded private copies of the description payloads (the range decoder may read up to 4 bytes past the end)
     if (lostflag != 1) {
         int c0 = imin(n0, MAX_PAYLOAD), c1 = imin(n1, MAX_PAYLOAD);
@@ -724,10 +727,10 @@ SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, 
             for (int i = c1; i < c1 + 8; i++) W->pay[1][i] = 0;
         }
     }
-    for (int i = 0; i < PACKET / 2; i++) { W->res_Q10[i] = 0; W->lowout[i] = 0; }
+    for (int i = 0; i < half; i++) { W->res_Q10[i] = 0; W->lowout[i] = 0; }
     RangeDec rc[2];
     rc[0].error = 0; rc[1].error = 0; rc[0].bufLen = 0; rc[1].bufLen = 0;
-    for (int f = 0; f < 2; f++) {
+    for (int f = 0; f < nf; f++) {
         i32 ret;
         if (!st->seen_good && lostflag == 1) {
             // Loss before any frame was decoded: the reference conceals at its start-up rate of 24 kHz from an all-zero
@@ -743,17 +746,17 @@ SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, 
         if (ret < 0) return ret;
         for (int i = 0; i < FRAME; i++) W->res_Q10[f * FRAME + i] = st->exc_Q10[i];
     }
-    for (int i = 0; i < PACKET / 2; i++) W->OutLow[i] = (float)W->lowout[i];
+    for (int i = 0; i < half; i++) W->OutLow[i] = (float)W->lowout[i];
     const int hb_lost = (lostflag == 1 || lostflag == 2);
-    for (int f = 0; f < 2; f++) {
+    for (int f = 0; f < nf; f++) {
         for (int i = 0; i < HB_FRAME; i++) W->res_f[i] = (float)(W->res_Q10[f * HB_FRAME + i] >> 10);
-        if (hb_lost) for (int i = 0; i < PACKET / 2; i++) W->res_Q10[i] = 0;  // App. A Q12: the memset wipes the rest of the packet
+        if (hb_lost) for (int i = 0; i < half; i++) W->res_Q10[i] = 0;  // App. A Q12: the memset wipes the rest of the packet
         u8 hb4[4] = {0, 0, 0, 0};
         if (!hb_lost) for (int i = 0; i < 4; i++) hb4[i] = bits[hb_off + 4 * f + i];
         hb_decode_frame(st, hb4, W->OutHigh + f * HB_FRAME, W->res_f, lostflag);
     }
-    qmf_synth_f32(W->OutLow, W->OutHigh, W->out, st->g0_mem, st->g1_mem);
-    for (int i = 0; i < PACKET; i++) {
+    qmf_synth_f32(W->OutLow, W->OutHigh, W->out, st->g0_mem, st->g1_mem, half);
+    for (int i = 0; i < 2 * half; i++) {
         i32 t = (i32)W->out[i];
         if (t > 32767) t = 32767; else if (t < -32768) t = -32768;
         vout[i] = (i16)t;

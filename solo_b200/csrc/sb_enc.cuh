@@ -15,8 +15,9 @@ namespace sb {
 
 // ---- Init: AGR_Sate_Encoder_Init + SKP_Silk_init_encoder_FIX + first SKP_Silk_control_encoder_FIX --------------
 // Returns 0, or -1 for a configuration the reference rejects / this build does not cover.
-SB_FN int enc_state_init(EncState* st, i32 targetRate_bps, i32 dtx_enable, i32 useMDIndex) {
+SB_FN int enc_state_init(EncState* st, i32 targetRate_bps, i32 dtx_enable, i32 useMDIndex, i32 framesize_ms = 40) {
     memset(st, 0, sizeof(EncState));
+    st->frames_per_packet = framesize_ms == 20 ? 1 : 2;
     if (targetRate_bps <= 0) targetRate_bps = 15600;
     i32 silk_rate = targetRate_bps - 1600;  // bwe_framesize 20 ms (AGR_BWE_SDK_API.c:118)
     silk_rate = limit(silk_rate, 5000, 100000);
@@ -56,10 +57,10 @@ SB_FN int enc_state_init(EncState* st, i32 targetRate_bps, i32 dtx_enable, i32 u
     return 0;
 }
 
-// ---- AGR_Sate_qmf_decomp (AGR_BWE_qmf.c:38-80), N = 640, M = 64, fixed point ------------------------------------
-SB_FN void qmf_decomp(const i16* xx, i16* y1, i16* y2, i16* mem) {
-    enum { N = PACKET, M = 64 };
-    i16 x[N + M - 1];
+// ---- AGR_Sate_qmf_decomp (AGR_BWE_qmf.c:38-80), N = 640 or 320, M = 64, fixed point ------------------------------
+SB_FN void qmf_decomp(const i16* xx, i16* y1, i16* y2, i16* mem, int N) {
+    enum { M = 64 };
+    i16 x[PACKET + M - 1];
     const i16* aa = SB_T(qmf_fix);
     for (int i = 0; i < M - 1; i++) x[i] = mem[M - i - 2];
 #ifdef __CUDA_ARCH__
@@ -237,8 +238,9 @@ SB_FN void encode_frame_analysis(EncCore* st, EncAnalysisWork* W, Arena* A, cons
 SB_FN void enc_packet_analysis(EncCore* st, EncAnalysisWork* W, const i16* pcm, EncScratch* scr) {
     Arena A;
     arena_init(&A, W->arena_mem, SB_ANA_ARENA);
-    SB_SERIAL(qmf_decomp(pcm, W->low, W->high, st->qmf_mem));
-    for (int f = 0; f < 2; f++) {
+    const int nf = st->frames_per_packet;
+    SB_SERIAL(qmf_decomp(pcm, W->low, W->high, st->qmf_mem, nf * 2 * FRAME));
+    for (int f = 0; f < nf; f++) {
         encode_frame_analysis(st, W, &A, W->low + f * FRAME, f);
         // hand the frame over to stages B / C (32-bit words; EncCtrl and xfw are both 4-byte multiples)
         {
@@ -253,7 +255,7 @@ SB_FN void enc_packet_analysis(EncCore* st, EncAnalysisWork* W, const i16* pcm, 
         SB_SYNC();
     }
     if (SB_LANE0) scr->dtx_drop = (st->useDTX && st->inDTX) ? 1 : 0;
-    for (int f = 0; f < 2; f++) SB_SERIAL(hb_analyse_frame(st, W->high + f * HB_FRAME, &scr->hb_lsp_idx[f], scr->hb_nrg0[f]));
+    for (int f = 0; f < nf; f++) SB_SERIAL(hb_analyse_frame(st, W->high + f * HB_FRAME, &scr->hb_lsp_idx[f], scr->hb_nrg0[f]));
 }
 
 // stage C: AGR_Sate_Encoder_Encode tail -- returns the byte count; nBytesOut[0] = total, nBytesOut[1] = len(MD2) + 8
@@ -261,13 +263,14 @@ SB_FN i32 enc_packet_finish(EncCore* st, const EncScratch* scr, u8* rcbuf /* MAX
     int nb[2];
     int ok = 1;
     int written = 0;
+    const int nf = st->frames_per_packet, hb_bytes = 4 * nf;
     for (int k = 0; k < 2; k++) {
         RangeEnc rc;
         rc_enc_init(&rc, rcbuf, MAX_PAYLOAD);
-        for (int f = 0; f < 2; f++) {
+        for (int f = 0; f < nf; f++) {
             encode_parameters(&rc, st, &scr->c[f], k, f, scr->vadFlag[f], scr->q_md[f][k]);
-            // frame terminator: MORE_FRAMES (1) after the first frame, LAST_FRAME (0) after the second
-            rc_encode(&rc, f == 0 ? 1 : 0, SB_T(frame_term_cdf));
+            // frame terminator: MORE_FRAMES (1) while frames follow in this packet, LAST_FRAME (0) after the last one
+            rc_encode(&rc, f < nf - 1 ? 1 : 0, SB_T(frame_term_cdf));
         }
         rc_get_length(&rc, &nb[k]);
         if (rc.error) ok = 0;
@@ -281,11 +284,11 @@ SB_FN i32 enc_packet_finish(EncCore* st, const EncScratch* scr, u8* rcbuf /* MAX
     if (!ok) { nb[0] = nb[1] = 0; }
     if (scr->dtx_drop) { nb[0] = nb[1] = 0; }
     u8 hb[8];
-    for (int f = 0; f < 2; f++) hb_pack_frame(scr->hb_lsp_idx[f], scr->hb_nrg0[f], scr->r16[f], hb + 4 * f);
+    for (int f = 0; f < nf; f++) hb_pack_frame(scr->hb_lsp_idx[f], scr->hb_nrg0[f], scr->r16[f], hb + 4 * f);
     int lb = nb[0] + nb[1];
-    int total = lb + 8;
-    for (int i = 0; i < 8; i++) if (lb + i < out_cap) out[lb + i] = hb[i];
-    if (lb) { nBytesOut[0] = (i16)total; nBytesOut[1] = (i16)(nb[1] + 8); }
+    int total = lb + hb_bytes;
+    for (int i = 0; i < hb_bytes; i++) if (lb + i < out_cap) out[lb + i] = hb[i];
+    if (lb) { nBytesOut[0] = (i16)total; nBytesOut[1] = (i16)(nb[1] + hb_bytes); }
     else { nBytesOut[0] = 0; nBytesOut[1] = 0; }
     return imin(out_cap, total);
 }
@@ -300,7 +303,7 @@ struct EncPacketWork {
 };
 // stages B (scalar model of the quantiser) + C on one thread
 SB_FN i32 enc_packet_quantise_and_code(EncState* st, EncPacketWork* W, u8* out, i32 out_cap, i16* nBytesOut) {
-    for (int f = 0; f < 2; f++) {
+    for (int f = 0; f < st->frames_per_packet; f++) {
         nsq_del_dec(st, &W->scr.c[f], &W->nsq, W->scr.xfw[f], (i8*)0, W->scr.q_md[f][0], W->scr.q_md[f][1], W->r);
         for (int i = 0; i < FRAME; i++) W->scr.r16[f][i] = (i16)(W->r[i] >> 10);
     }

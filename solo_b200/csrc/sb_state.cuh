@@ -64,6 +64,7 @@ struct alignas(16) EncCore {
     i32 useMDIndex;
     i32 useDTX;
     i32 targetRate_bps;  // SILK core rate (user rate - 1600)
+    i32 frames_per_packet;  // 2: 40 ms packets (the headline configuration), 1: 20 ms packets (AGR_BWE_SDK_API.c:78-81,106-110)
     // --- QMF analysis memory (AGR_BWE_structs.h:34) ---
     i16 qmf_mem[64];
     // --- SILK encoder ---

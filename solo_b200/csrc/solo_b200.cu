@@ -35,7 +35,7 @@ using namespace sb;
 #ifndef SB_ANALYSIS_WARP
 #define SB_ANALYSIS_WARP 0   // 1: stage A runs as the warp-per-stream kernel of sb_analysis.cu
 #endif
-extern "C" int sb_launch_enc_analysis_warp(void* states, void* scratch, const void* pcm, int n, void* stream);
+extern "C" int sb_launch_enc_analysis_warp(void* states, void* scratch, const void* pcm, int spp, int n, void* stream);
 #ifndef SB_ANALYSIS_MINB
 #define SB_ANALYSIS_MINB 4   // min resident blocks per SM of the analysis kernel (register cap = 65536 / (64 * MINB) = 255)
 #endif
@@ -43,16 +43,16 @@ extern "C" int sb_launch_enc_analysis_warp(void* states, void* scratch, const vo
 #define SB_DECODE_MINB 8
 #endif
 
-__global__ void __launch_bounds__(SB_TPB) sb_enc_init_kernel(EncState* states, int n, int rate, int dtx, int mdi) {
+__global__ void __launch_bounds__(SB_TPB) sb_enc_init_kernel(EncState* states, int n, int rate, int dtx, int mdi, int framesize_ms) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n) enc_state_init(&states[s], rate, dtx, mdi);
+    if (s < n) enc_state_init(&states[s], rate, dtx, mdi, framesize_ms);
 }
 
 // Encoder = three kernels per packet wave (stream s, scratch slot s):
 //   A  sb_enc_analysis_kernel : one thread per stream  -- QMF split, VAD .. gain processing of both frames, high-band analysis
 //   B  sb_enc_nsq_kernel      : one WARP per stream    -- MD delayed-decision noise-shaping quantiser, state in shared memory
 //   C  sb_enc_finish_kernel   : one thread per stream  -- range coding of both descriptions, high-band gains, payload assembly
-__global__ void __launch_bounds__(SB_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ pcm, int n) {
+__global__ void __launch_bounds__(SB_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ pcm, int spp, int n) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ NlsfFastTabs s_nlsf;
     nlsf_fast_tabs_fill(&s_nlsf, threadIdx.x, blockDim.x);
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(SB_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_kern
     if (s >= n) return;
     EncAnalysisWork W;
     W.nlsf_fast = &s_nlsf;
-    const i16* x = pcm + (size_t)s * PACKET;   // read once, with 128-bit loads, by the QMF split
+    const i16* x = pcm + (size_t)s * spp;      // row of spp = 640 (40 ms) or 320 (20 ms) samples, read once, with 128-bit loads, by the QMF split
 #if SB_ANALYSIS_LOCAL_STATE
     // analysis state staged in local memory: same-offset words of the 32 streams of a warp share cache lines there
     EncCore st = static_cast<const EncCore&>(states[s]);
@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(SB_NSQ_WARPS * 32, SB_NSQ_MINB) sb_enc_nsq_ker
     // collectives valid for every warp.
     if (s >= n) s = n - 1;
     EncScratch* scr = &scratch[s];
-    for (int f = 0; f < 2; f++)
+    const int nf = states[s].frames_per_packet;
+    for (int f = 0; f < nf; f++)
         nsq_del_dec_warp(*S, states[s].nsq, &scr->c[f], scr->xfw[f], scr->q_md[f][0], scr->q_md[f][1], scr->r16[f]);
 }
 
@@ -105,14 +106,14 @@ __global__ void __launch_bounds__(SB_TPB) sb_enc_finish_kernel(EncState* states,
     nbytes[2 * s + 1] = nb[1];
 }
 
-__global__ void __launch_bounds__(SB_TPB) sb_dec_init_kernel(DecState* states, int n, int mdi) {
+__global__ void __launch_bounds__(SB_TPB) sb_dec_init_kernel(DecState* states, int n, int mdi, int framesize_ms) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n) dec_state_init(&states[s], mdi);
+    if (s < n) dec_state_init(&states[s], mdi, framesize_ms);
 }
 
 __global__ void __launch_bounds__(SB_TPB, SB_DECODE_MINB) sb_decode_kernel(DecState* states, i16* __restrict__ pcm, const u8* __restrict__ bits, int cap,
                                                            const i16* __restrict__ nbytes, const i32* __restrict__ lostflag,
-                                                           i32* __restrict__ ret, int n) {
+                                                           i32* __restrict__ ret, int spp, int n) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     DecPacketWork W;
@@ -125,10 +126,10 @@ __global__ void __launch_bounds__(SB_TPB, SB_DECODE_MINB) sb_decode_kernel(DecSt
 #else
     i32 r = dec_packet(&states[s], &W, out, bits + (size_t)s * cap, cap, nb, lostflag[s]);
 #endif
-    int4* dst = reinterpret_cast<int4*>(pcm + (size_t)s * PACKET);
+    int4* dst = reinterpret_cast<int4*>(pcm + (size_t)s * spp);
     const int4* src = reinterpret_cast<const int4*>(out);
 #pragma unroll 4
-    for (int i = 0; i < PACKET * 2 / 16; i++) dst[i] = src[i];
+    for (int i = 0; i < spp * 2 / 16; i++) dst[i] = src[i];
     if (ret) ret[s] = r;
 }
 
@@ -237,6 +238,7 @@ static void chunk_bounds(int n, int C, int c, int* lo, int* hi) {
 
 struct solo_b200_enc_batch {
     int n, device;
+    int spp;                    // samples per packet and stream: 640 (40 ms) or 320 (20 ms)
     EncState* d_states;
     EncScratch* d_scratch;
     // staging for the *_host entry points
@@ -246,6 +248,7 @@ struct solo_b200_enc_batch {
 };
 struct solo_b200_dec_batch {
     int n, device;
+    int spp;
     DecState* d_states;
     i16* d_pcm; u8* d_bits; i16* d_nbytes; i32* d_flags; i32* d_ret; int bits_cap;
     cudaStream_t stream;
@@ -254,13 +257,13 @@ struct solo_b200_dec_batch {
 
 static int check_enc_ctrl(const USER_Ctrl_enc* c) {
     if (!c) return -1;
-    if (c->samplerate != 16000 || c->framesize_ms != 40) return -1;
+    if (c->samplerate != 16000 || (c->framesize_ms != 40 && c->framesize_ms != 20)) return -1;
     if (c->joint_enable) return -1;  // joint modes: "Unsupport" / 40 ms HB frame (AGR_BWE_SDK_API.c:56-81), out of scope
     return 0;
 }
 static int check_dec_ctrl(const USER_Ctrl_dec* c) {
     if (!c) return -1;
-    if (c->samplerate != 16000 || c->framesize_ms != 40) return -1;
+    if (c->samplerate != 16000 || (c->framesize_ms != 40 && c->framesize_ms != 20)) return -1;
     if (c->joint_enable) return -1;
     return 0;
 }
@@ -312,7 +315,7 @@ solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_e
     if (require_gpu(device)) return nullptr;
     solo_b200_enc_batch* b = new solo_b200_enc_batch();
     memset(b, 0, sizeof *b);
-    b->n = n_streams; b->device = device;
+    b->n = n_streams; b->device = device; b->spp = 16 * ctrl->framesize_ms;
     if (cudaMalloc(&b->d_states, sizeof(EncState) * (size_t)n_streams) != cudaSuccess ||
         cudaMalloc(&b->d_scratch, sizeof(EncScratch) * (size_t)n_streams) != cudaSuccess ||
         cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || pipe_create(&b->pipe) != 0 ||
@@ -321,7 +324,7 @@ solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_e
         delete b; return nullptr;
     }
     int rate = ctrl->targetRate_bps <= 0 ? 15600 : ctrl->targetRate_bps;
-    sb_enc_init_kernel<<<(n_streams + SB_TPB - 1) / SB_TPB, SB_TPB, 0, b->stream>>>(b->d_states, n_streams, rate, ctrl->dtx_enable, ctrl->useMDIndex);
+    sb_enc_init_kernel<<<(n_streams + SB_TPB - 1) / SB_TPB, SB_TPB, 0, b->stream>>>(b->d_states, n_streams, rate, ctrl->dtx_enable, ctrl->useMDIndex, ctrl->framesize_ms);
     count_launch();
     cudaError_t e = cudaStreamSynchronize(b->stream);
     if (e != cudaSuccess) { fail("enc init kernel", e); cudaFree(b->d_states); delete b; return nullptr; }
@@ -333,13 +336,13 @@ static int enc_launch(solo_b200_enc_batch* b, int lo, int n, const i16* d_pcm, u
     if (n <= 0) return 0;
     EncState* states = b->d_states + lo;
     EncScratch* scratch = b->d_scratch + lo;
-    const i16* pcm = d_pcm + (size_t)lo * PACKET;
+    const i16* pcm = d_pcm + (size_t)lo * b->spp;
     EvPair ev;
     prof_begin(st, 0, &ev);
 #if SB_ANALYSIS_WARP
-    { int e = sb_launch_enc_analysis_warp(states, scratch, pcm, n, st); if (e) return fail("analysis launch", (cudaError_t)e); }
+    { int e = sb_launch_enc_analysis_warp(states, scratch, pcm, b->spp, n, st); if (e) return fail("analysis launch", (cudaError_t)e); }
 #else
-    sb_enc_analysis_kernel<<<(n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(states, scratch, pcm, n);
+    sb_enc_analysis_kernel<<<(n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(states, scratch, pcm, b->spp, n);
 #endif
     prof_end(st, &ev);
     prof_begin(st, 1, &ev);
@@ -376,7 +379,7 @@ int solo_b200_enc_batch_encode_device(solo_b200_enc_batch* b, const int16_t* d_p
 }
 
 static int enc_staging(solo_b200_enc_batch* b, int cap) {
-    if (!b->d_pcm) CK(cudaMalloc(&b->d_pcm, sizeof(i16) * PACKET * (size_t)b->n));
+    if (!b->d_pcm) CK(cudaMalloc(&b->d_pcm, sizeof(i16) * b->spp * (size_t)b->n));
     if (!b->d_nbytes) CK(cudaMalloc(&b->d_nbytes, sizeof(i16) * 2 * (size_t)b->n));
     if (!b->d_bits || b->bits_cap < cap) {
         if (b->d_bits) cudaFree(b->d_bits);
@@ -400,7 +403,7 @@ int solo_b200_enc_batch_encode_host(solo_b200_enc_batch* b, const int16_t* pcm, 
         if (hi <= lo) continue;
         cudaStream_t st = b->pipe.st[c % S];
         const size_t m = (size_t)(hi - lo);
-        CK(cudaMemcpyAsync(b->d_pcm + (size_t)lo * PACKET, pcm + (size_t)lo * PACKET, sizeof(i16) * PACKET * m, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->d_pcm + (size_t)lo * b->spp, pcm + (size_t)lo * b->spp, sizeof(i16) * b->spp * m, cudaMemcpyHostToDevice, st));
         r = enc_launch(b, lo, hi - lo, b->d_pcm, b->d_bits, cap, b->d_nbytes, st);
         if (r) return r;
         CK(cudaMemcpyAsync(bits + (size_t)lo * cap, b->d_bits + (size_t)lo * cap, (size_t)cap * m, cudaMemcpyDeviceToHost, st));
@@ -426,13 +429,13 @@ solo_b200_dec_batch* solo_b200_dec_batch_create(int n_streams, const USER_Ctrl_d
     if (require_gpu(device)) return nullptr;
     solo_b200_dec_batch* b = new solo_b200_dec_batch();
     memset(b, 0, sizeof *b);
-    b->n = n_streams; b->device = device;
+    b->n = n_streams; b->device = device; b->spp = 16 * ctrl->framesize_ms;
     if (cudaMalloc(&b->d_states, sizeof(DecState) * (size_t)n_streams) != cudaSuccess ||
         cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || pipe_create(&b->pipe) != 0) {
         fail("dec_batch_create", cudaGetLastError());
         delete b; return nullptr;
     }
-    sb_dec_init_kernel<<<(n_streams + SB_TPB - 1) / SB_TPB, SB_TPB, 0, b->stream>>>(b->d_states, n_streams, ctrl->useMDIndex);
+    sb_dec_init_kernel<<<(n_streams + SB_TPB - 1) / SB_TPB, SB_TPB, 0, b->stream>>>(b->d_states, n_streams, ctrl->useMDIndex, ctrl->framesize_ms);
     count_launch();
     cudaError_t e = cudaStreamSynchronize(b->stream);
     if (e != cudaSuccess) { fail("dec init kernel", e); cudaFree(b->d_states); delete b; return nullptr; }
@@ -443,8 +446,8 @@ static int dec_launch(solo_b200_dec_batch* b, int lo, int n, i16* d_pcm, const u
                       i32* d_ret, cudaStream_t st) {
     if (n <= 0) return 0;
     EvPair ev; prof_begin(st, 3, &ev);
-    sb_decode_kernel<<<(n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states + lo, d_pcm + (size_t)lo * PACKET, d_bits + (size_t)lo * cap, cap,
-                                                                  d_nbytes + 2 * (size_t)lo, d_lostflag + lo, d_ret ? d_ret + lo : nullptr, n);
+    sb_decode_kernel<<<(n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states + lo, d_pcm + (size_t)lo * b->spp, d_bits + (size_t)lo * cap, cap,
+                                                                  d_nbytes + 2 * (size_t)lo, d_lostflag + lo, d_ret ? d_ret + lo : nullptr, b->spp, n);
     prof_end(st, &ev);
     count_launch();
     CK(cudaGetLastError());
@@ -474,7 +477,7 @@ int solo_b200_dec_batch_decode_device(solo_b200_dec_batch* b, int16_t* d_pcm, co
 }
 
 static int dec_staging(solo_b200_dec_batch* b, int cap) {
-    if (!b->d_pcm) CK(cudaMalloc(&b->d_pcm, sizeof(i16) * PACKET * (size_t)b->n));
+    if (!b->d_pcm) CK(cudaMalloc(&b->d_pcm, sizeof(i16) * b->spp * (size_t)b->n));
     if (!b->d_nbytes) CK(cudaMalloc(&b->d_nbytes, sizeof(i16) * 2 * (size_t)b->n));
     if (!b->d_flags) CK(cudaMalloc(&b->d_flags, sizeof(i32) * (size_t)b->n));
     if (!b->d_ret) CK(cudaMalloc(&b->d_ret, sizeof(i32) * (size_t)b->n));
@@ -506,7 +509,7 @@ int solo_b200_dec_batch_decode_host(solo_b200_dec_batch* b, int16_t* pcm, const 
         CK(cudaMemcpyAsync(b->d_flags + lo, lostflag + lo, sizeof(i32) * m, cudaMemcpyHostToDevice, st));
         r = dec_launch(b, lo, hi - lo, b->d_pcm, b->d_bits, cap, b->d_nbytes, b->d_flags, b->d_ret, st);
         if (r) return r;
-        CK(cudaMemcpyAsync(pcm + (size_t)lo * PACKET, b->d_pcm + (size_t)lo * PACKET, sizeof(i16) * PACKET * m, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(pcm + (size_t)lo * b->spp, b->d_pcm + (size_t)lo * b->spp, sizeof(i16) * b->spp * m, cudaMemcpyDeviceToHost, st));
         if (ret) CK(cudaMemcpyAsync(ret + lo, b->d_ret + lo, sizeof(i32) * m, cudaMemcpyDeviceToHost, st));
     }
     for (int i = 0; i < S; i++) CK(cudaStreamSynchronize(b->pipe.st[i]));
@@ -629,8 +632,8 @@ SKP_int32 AGR_Sate_Encoder_Encode(void* SATEEnc_State, const SKP_int16* AGR_Sate
     int16_t nb[2] = {0, 0};
     int r = solo_b200_enc_batch_encode_host(b, AGR_Sate_PCM, tmp, MAX_PAYLOAD + 8, nb);
     if (r) { fprintf(stderr, "solo_b200: encode failed: %s\n", g_err); return -1; }
-    // DTX packets return the 8 high-band bytes with nBytesOut[0] == 0 (App. A Q16)
-    int total = nb[0] ? nb[0] : 8;
+    // DTX packets return the high-band bytes (4 per 20 ms frame) with nBytesOut[0] == 0 (App. A Q16)
+    int total = nb[0] ? nb[0] : (b->spp / 320) * 4;
     int n = total < AGR_Sate_Buf_Size ? total : AGR_Sate_Buf_Size;
     if (n < 0) n = 0;
     memcpy(AGR_Sate_Bit, tmp, n);
@@ -670,10 +673,10 @@ SKP_int32 AGR_Sate_Decoder_Decode(void* SATEDec_State, SKP_int16* AGR_Sate_PCM, 
     int r = solo_b200_dec_batch_decode_host(b, AGR_Sate_PCM, tmp, MAX_PAYLOAD + 8, nb, &flag, &ret);
     if (r) { fprintf(stderr, "solo_b200: decode failed: %s\n", g_err); return -1; }
     // the reference rewrites the caller's nBytes[] while splitting the payload (AGR_BWE_decode_frame_FLP.c:171-190)
-    dec_split_lengths(nb, lostflag);
+    dec_split_lengths(nb, lostflag, (b->spp / 320) * 4);
     nBytes[0] = nb[0];
     nBytes[1] = nb[1];
-    *nSamplesOut = PACKET;
+    *nSamplesOut = (SKP_int16)((solo_b200_dec_batch*)SATEDec_State)->spp;
     return ret;
 }
 SKP_int32 AGR_Sate_Decoder_Uninit(void* SATEDec_State) {

@@ -18,6 +18,10 @@ def lib(emu=None):
         L = C.CDLL(build_hostsim.build(emu=emu))
         L.hs_enc_create.restype = C.c_void_p
         L.hs_enc_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.hs_enc_create2.restype = C.c_void_p
+        L.hs_enc_create2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+        L.hs_dec_create2.restype = C.c_void_p
+        L.hs_dec_create2.argtypes = [C.c_int, C.c_int]
         L.hs_enc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hs_enc_destroy.argtypes = [C.c_void_p]
         L.hs_dec_create.restype = C.c_void_p
@@ -29,16 +33,17 @@ def lib(emu=None):
 
 
 class SimEncoder:
-    def __init__(self, rate=13600, dtx=0, use_md_index=0, cap=1024, emu=None):
+    def __init__(self, rate=13600, dtx=0, use_md_index=0, cap=1024, emu=None, framesize_ms=40):
         self.L = lib(emu)
-        self.h = self.L.hs_enc_create(rate, dtx, use_md_index)
+        self.h = self.L.hs_enc_create2(rate, dtx, use_md_index, framesize_ms)
+        self.samples = 16 * framesize_ms
         self.cap = cap
         self.out = np.zeros(cap, np.uint8)
         self.nb = np.zeros(6, np.int16)
 
     def encode(self, pcm640):
         x = np.ascontiguousarray(pcm640, np.int16)
-        assert x.size == 640
+        assert x.size == self.samples
         n = self.L.hs_enc_encode(self.h, x.ctypes.data, self.out.ctypes.data, self.cap, self.nb.ctypes.data)
         return bytes(self.out[:max(n, 0)]), (int(self.nb[0]), int(self.nb[1])), n
 
@@ -49,10 +54,10 @@ class SimEncoder:
 
 
 class SimDecoder:
-    def __init__(self, use_md_index=0):
+    def __init__(self, use_md_index=0, framesize_ms=40):
         self.L = lib()
-        self.h = self.L.hs_dec_create(use_md_index)
-        self.pcm = np.zeros(640, np.int16)
+        self.h = self.L.hs_dec_create2(use_md_index, framesize_ms)
+        self.pcm = np.zeros(16 * framesize_ms, np.int16)
 
     def decode(self, payload, nbytes, lostflag):
         buf = np.zeros(max(len(payload), 1), np.uint8)

@@ -205,3 +205,41 @@ def test_single_stream_small_output_buffer(sb):
             n0 = int(g["fix_nbytes"][p, 0])
             assert nb == tuple(g["fix_nbytes"][p]) and n == min(cap, n0) and b == bytes(g["fix_bits"][p, :n])
         e.close()
+
+
+def test_20ms_packets_on_device(sb):
+    """framesize_ms = 20 through the batched ABI and the drop-in ABI against the reference (FIX bytes, FLP PCM)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    N, T, cap = 130, 40, 128
+    clip = load_clip()
+    eb, db = sb.EncoderBatch(N, rate=13600, framesize_ms=20), sb.DecoderBatch(N, framesize_ms=20)
+    sample = [0, 1, 64, 65, 129]
+    renc = {s: ref.RefEncoder("fix", rate=13600, framesize_ms=20) for s in sample}
+    rdec = {s: ref.RefDecoder("flp", framesize_ms=20) for s in sample}
+    off = (np.arange(N) * 7919 * 320) % (len(clip) - 320 * (T + 1))
+    flags = np.array([loss_flags(T, 40, seed=3 + s) for s in range(N)], np.int32)
+    for p in range(T):
+        x = np.stack([clip[o + p * 320:o + (p + 1) * 320] for o in off]).astype(np.int16)
+        bits, nb = eb.encode(x, cap=cap)
+        tb, tnb = np.zeros_like(bits), np.zeros_like(nb)
+        for s in range(N):
+            pb, pnb = trim_payload(bytes(bits[s, :nb[s, 0]]), nb[s], flags[s, p])
+            tb[s, :len(pb)] = np.frombuffer(pb, np.uint8); tnb[s] = pnb
+        pcm, ret = db.decode(tb, tnb, flags[:, p].copy())
+        assert pcm.shape == (N, 320) and (ret == 0).all()
+        for s in sample:
+            b, rnb, n = renc[s].encode(x[s])
+            assert tuple(nb[s]) == rnb and bytes(bits[s, :n]) == b, (p, s)
+            want, r = rdec[s].decode(bytes(tb[s, :tnb[s, 0]]), tuple(tnb[s]), int(flags[s, p]))
+            assert np.array_equal(pcm[s], want), (p, s)
+    eb.close(); db.close()
+    e, d = sb.SoloEncoder(rate=13600, framesize_ms=20), sb.SoloDecoder(framesize_ms=20)
+    r0 = ref.RefEncoder("fix", rate=13600, framesize_ms=20)
+    for p in range(10):
+        b, nb2, n = e.encode(clip[p * 320:(p + 1) * 320])
+        assert (b, nb2, n) == r0.encode(clip[p * 320:(p + 1) * 320])
+        y, r = d.decode(b, nb2, 4)
+        assert r == 0 and y.size == 320 and d.last_nsamples == 320
+    e.close(); d.close()

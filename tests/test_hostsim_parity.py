@@ -160,3 +160,30 @@ def test_small_output_buffer_matches_reference(sim, ref):
             assert n == n2 == min(cap, nb[0]) and (nb[0], nb[1]) == nb2
             assert bytes(bits[:n]) == bytes(s.out[:n]) and bytes(bits[cap:cap + 8]) == b"\xaa" * 8
         e.close(); s.close()
+
+
+def test_20ms_packets_match_reference(sim, ref):
+    """The reference's other packet size (framesize_ms = 20: one SILK frame + one high-band frame per packet, 4 high-band
+    bytes, AGR_BWE_SDK_API.c:78-81,106-110): payloads vs FIX, PCM vs FLP, with loss, DTX and the MD index flag."""
+    clip = load_clip()
+    for rate, dtx, mdi in ((13600, 0, 0), (8000, 0, 1), (24000, 1, 0)):
+        e0 = ref.RefEncoder("fix", rate=rate, dtx=dtx, use_md_index=mdi, framesize_ms=20)
+        e1 = sim.SimEncoder(rate=rate, dtx=dtx, use_md_index=mdi, framesize_ms=20)
+        d0, d1 = ref.RefDecoder("flp", use_md_index=mdi, framesize_ms=20), sim.SimDecoder(use_md_index=mdi, framesize_ms=20)
+        flags = loss_flags(240, 30, seed=5)
+        for p in range(240):
+            x = clip[p * 320:(p + 1) * 320]
+            b0, nb0, n0 = e0.encode(x)
+            b1, nb1, n1 = e1.encode(x)
+            assert (b0[:max(n0, 0)], nb0, n0) == (b1[:max(n1, 0)], nb1, n1), (rate, p)
+            if nb0[0] > 0:
+                assert nb0[1] >= 4 and n0 == nb0[0]
+                pb, pnb, f = trim_payload(b0, nb0, flags[p]) + (flags[p],)
+            else:                                   # DTX: nothing was sent
+                pb, pnb, f = bytes(16), (16, 8), 1
+            y0, r0 = d0.decode(pb, pnb, f)
+            y1, r1 = d1.decode(pb, pnb, f)
+            assert r0 == r1 == 0 and y0.size == y1.size == 320
+            assert np.abs(y0.astype(np.int32) - y1.astype(np.int32)).max() <= PCM_TOL, (rate, p, f)
+        for o in (e0, e1, d0, d1):
+            o.close()
