@@ -243,3 +243,24 @@ def test_20ms_packets_on_device(sb):
         y, r = d.decode(b, nb2, 4)
         assert r == 0 and y.size == 320 and d.last_nsamples == 320
     e.close(); d.close()
+
+
+def test_example_file_codec_reproduces_the_reference_cli_files(sb, tmp_path):
+    """examples/jc1_file_codec.c (plain C on the six-function API + framing helpers) writes the same .bit file and the
+    same decoded PCM files as the reference's enc_main / dec_main: both descriptions, 50 % loss (seed 1), MD1 only, MD2 only."""
+    import hashlib
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "jc1_file_codec"
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "jc1_file_codec.c"),
+                           "-L", os.path.join(root, "solo_b200"), "-lsolo_b200", "-Wl,-rpath," + os.path.join(root, "solo_b200"), "-o", str(exe)])
+    g = load_golden()
+    pcm, bit = tmp_path / "in.pcm", tmp_path / "out.bit"
+    load_clip().tofile(pcm)
+    subprocess.check_call([str(exe), "enc", str(pcm), str(bit), "13600"])
+    assert hashlib.md5(bit.read_bytes()).hexdigest() == str(g["fix_bitfile_md5"])
+    for args, key in ((["0", "0"], "flp_pcm_mode4_md5"), (["50", "0"], "flp_pcm_loss50_md5"), (["0", "1"], "flp_pcm_mode2_md5"), (["0", "2"], "flp_pcm_mode3_md5")):
+        out = tmp_path / ("out_%s_%s.pcm" % tuple(args))
+        subprocess.check_call([str(exe), "dec", str(bit), str(out)] + args)
+        assert hashlib.md5(out.read_bytes()).hexdigest() == str(g[key]), key
