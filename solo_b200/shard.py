@@ -9,6 +9,11 @@ import torch
 import torch.distributed as dist
 
 
+def _bytes(t):
+    """Raw byte view of a contiguous tensor: NCCL has no int16 type, and these transfers are plain byte moves anyway."""
+    return t.view(torch.uint8)
+
+
 def shard_bounds(n_streams, world):
     """[(lo, hi)) per rank: rank r owns streams r*N//W .. (r+1)*N//W (contiguous so every transfer is one message)."""
     return [(r * n_streams // world, (r + 1) * n_streams // world) for r in range(world)]
@@ -32,9 +37,9 @@ def scatter_streams(full, n_streams, row_shape, dtype, device, src=0, group=None
             if r == src:
                 out.copy_(full[a:b])
             elif b > a:
-                ops.append(dist.P2POp(dist.isend, full[a:b].contiguous(), r, group))
+                ops.append(dist.P2POp(dist.isend, _bytes(full[a:b].contiguous()), r, group))
     elif hi > lo:
-        ops.append(dist.P2POp(dist.irecv, out, src, group))
+        ops.append(dist.P2POp(dist.irecv, _bytes(out), src, group))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
@@ -54,9 +59,9 @@ def gather_streams(local, n_streams, dst=0, group=None):
         full[lo:hi].copy_(local)
         for r, (a, b) in enumerate(bounds):
             if r != dst and b > a:
-                ops.append(dist.P2POp(dist.irecv, full[a:b], r, group))
+                ops.append(dist.P2POp(dist.irecv, _bytes(full[a:b]), r, group))
     elif hi > lo:
-        ops.append(dist.P2POp(dist.isend, local.contiguous(), dst, group))
+        ops.append(dist.P2POp(dist.isend, _bytes(local.contiguous()), dst, group))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
