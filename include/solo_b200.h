@@ -12,7 +12,8 @@
  *               (a cudaStream_t passed as void*; NULL = legacy default stream) and does not synchronise.
  *
  * Packet size: ctrl->framesize_ms = 40 (two 20 ms codec frames per packet, 8 high-band bytes, 640 samples per row) or 20
- * (one frame, 4 high-band bytes, 320 samples per row) -- the two packet sizes of the reference (AGR_BWE_SDK_API.c:78-110).
+ * (one frame, 4 high-band bytes, 320 samples per row) -- the two packet sizes of the reference (AGR_BWE_SDK_API.c:78-110);
+ * with joint_enable = 1, joint_mode = 1 (40 ms packets only) the high band is coded as one 40 ms frame (4 bytes, :63-66).
  *
  * Layouts (row = stream):  pcm  int16 [N][16 * framesize_ms]   bits uint8 [N][cap]
  *                          nbytes int16 [N][2]        ({total, len(MD2)+8} as the single-stream API)

@@ -62,10 +62,10 @@ def lib(kind):
 class RefEncoder:
     """One reference encoder handle (kind = 'fix' | 'flp')."""
 
-    def __init__(self, kind="fix", rate=13600, dtx=0, use_md_index=0, framesize_ms=40):
+    def __init__(self, kind="fix", rate=13600, dtx=0, use_md_index=0, framesize_ms=40, joint_hb=0):
         self.L = lib(kind).lib
         self.samples = 16 * framesize_ms
-        self.ctrl = EncCtrl(2, rate, 16000, dtx, framesize_ms, 0, 0, use_md_index)
+        self.ctrl = EncCtrl(2, rate, 16000, dtx, framesize_ms, 1 if joint_hb else 0, 1 if joint_hb else 0, use_md_index)
         self.h = self.L.AGR_Sate_Encoder_Init(C.byref(self.ctrl))
         self._bits = (C.c_uint8 * 1024)()
         self._nb = (C.c_int16 * 6)()
@@ -88,10 +88,10 @@ class RefEncoder:
 class RefDecoder:
     """One reference decoder handle (kind = 'flp' is the PCM parity target)."""
 
-    def __init__(self, kind="flp", use_md_index=0, framesize_ms=40):
+    def __init__(self, kind="flp", use_md_index=0, framesize_ms=40, joint_hb=0):
         self.L = lib(kind).lib
         self.samples = 16 * framesize_ms
-        self.ctrl = DecCtrl(0, 16000, framesize_ms, 0, 0, use_md_index)
+        self.ctrl = DecCtrl(0, 16000, framesize_ms, 1 if joint_hb else 0, 1 if joint_hb else 0, use_md_index)
         self.h = self.L.AGR_Sate_Decoder_Init(C.byref(self.ctrl))
         self._out = np.zeros(960, dtype=np.int16)
         self._ns = C.c_int16(0)

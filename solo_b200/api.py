@@ -166,10 +166,11 @@ class SoloDecoder:
 class EncoderBatch:
     """N encoder streams resident on one GPU; one call = one 40 ms packet for every stream."""
 
-    def __init__(self, n, rate=13600, dtx=0, use_md_index=0, device=0, framesize_ms=40):
+    def __init__(self, n, rate=13600, dtx=0, use_md_index=0, device=0, framesize_ms=40, joint_hb=0):
+        """joint_hb=1: the reference's joint mode 1 (one 40 ms high-band frame per packet)."""
         self.n = int(n)
         self.samples = 16 * framesize_ms          # samples per packet and stream (row length of the PCM matrix)
-        self.ctrl = EncCtrl(2, rate, 16000, dtx, framesize_ms, 0, 0, use_md_index)
+        self.ctrl = EncCtrl(2, rate, 16000, dtx, framesize_ms, 1 if joint_hb else 0, 1 if joint_hb else 0, use_md_index)
         self.h = lib().solo_b200_enc_batch_create(self.n, C.byref(self.ctrl), device)
         if not self.h:
             raise SoloError("solo_b200_enc_batch_create failed: " + _err())
@@ -221,10 +222,10 @@ class EncoderBatch:
 class DecoderBatch:
     """N decoder streams resident on one GPU."""
 
-    def __init__(self, n, use_md_index=0, device=0, framesize_ms=40):
+    def __init__(self, n, use_md_index=0, device=0, framesize_ms=40, joint_hb=0):
         self.n = int(n)
         self.samples = 16 * framesize_ms
-        self.ctrl = DecCtrl(0, 16000, framesize_ms, 0, 0, use_md_index)
+        self.ctrl = DecCtrl(0, 16000, framesize_ms, 1 if joint_hb else 0, 1 if joint_hb else 0, use_md_index)
         self.h = lib().solo_b200_dec_batch_create(self.n, C.byref(self.ctrl), device)
         if not self.h:
             raise SoloError("solo_b200_dec_batch_create failed: " + _err())

@@ -27,6 +27,7 @@ struct DecMd {
 struct DecState {
     i32 useMDIndex;
     i32 frames_per_packet;  // 2: 40 ms packets, 1: 20 ms packets
+    i32 hb_frame;           // 160, or 320 with joint_mode 1
     i32 seen_good;  // 0 until the first frame has been range-decoded (reference state is still at fs = 24 kHz)
     DecMd md[2];
     i32 prev_inv_gain_Q16;
@@ -64,10 +65,11 @@ struct DecCtrl {
 };
 
 // SKP_Silk_init_decoder + AGR_Sate_Decoder_Init, expressed for the 8 kHz core the first good frame selects.
-SB_FN void dec_state_init(DecState* st, i32 useMDIndex, i32 framesize_ms = 40) {
+SB_FN void dec_state_init(DecState* st, i32 useMDIndex, i32 framesize_ms = 40, i32 joint_hb = 0) {
     memset(st, 0, sizeof(DecState));
     st->useMDIndex = useMDIndex;
     st->frames_per_packet = framesize_ms == 20 ? 1 : 2;
+    st->hb_frame = joint_hb ? 320 : HB_FRAME;
     st->first_frame_after_reset = 1;
     st->prev_inv_gain_Q16 = 65536;
     st->lagPrev = 100;
@@ -649,8 +651,9 @@ SB_FN void qmf_synth_f32(const float* x1, const float* x2, float* y, float* mem1
 // ---- AGR_Bwe_decode_frame_FLP (AGR_BWE_decode_frame_FLP.c:41-130): one 20 ms high-band frame ------------------------
 // res_f: float copy of (residue >> 10) for this frame; hb4: the 4 coded bytes (ignored on loss).
 SB_FN void hb_decode_frame(DecState* st, const u8* hb4, float* OutHigh, const float* res_f, int lostflag) {
-    float QHB_LSP[HB_ORDER], QGain[4], HB_PredCoef[HB_ORDER], HB_LPCRes[SUBFR];
-    float sLPC[16 + SUBFR];
+    const int SF = st->hb_frame >> 2;   // sub-frame length: 40, or 80 with joint_mode 1
+    float QHB_LSP[HB_ORDER], QGain[4], HB_PredCoef[HB_ORDER], HB_LPCRes[2 * SUBFR];
+    float sLPC[16 + 2 * SUBFR];
     if (lostflag == 1 || lostflag == 2) {
         for (int i = 0; i < HB_ORDER; i++) QHB_LSP[i] = st->hb_prev_NLSFq[i];
         for (int s = 0; s < 4; s++) QGain[s] = st->hb_prev_Gain;
@@ -678,16 +681,16 @@ SB_FN void hb_decode_frame(DecState* st, const u8* hb4, float* OutHigh, const fl
     for (int i = 0; i < 16; i++) sLPC[i] = st->hb_sLPC[i];
     float* p_out = OutHigh;
     for (int s = 0; s < 4; s++) {
-        for (int i = 0; i < SUBFR; i++) HB_LPCRes[i] = (float)(-0.7 * (double)QGain[s] * (double)res_f[s * SUBFR + i]);
+        for (int i = 0; i < SF; i++) HB_LPCRes[i] = (float)(-0.7 * (double)QGain[s] * (double)res_f[s * SF + i]);
         // AGR_Sate_LPC_synthesizer (AGR_BWE_LPC_synthesizer.c:29-52)
-        for (int i = 0; i < SUBFR; i++) {
+        for (int i = 0; i < SF; i++) {
             float LPC_pred = 0.0f;
             for (int j = 0; j < HB_ORDER; j++) LPC_pred = LPC_pred + sLPC[16 + i - j - 1] * HB_PredCoef[j];
             p_out[i] = HB_LPCRes[i] + LPC_pred;
             sLPC[16 + i] = p_out[i];
         }
-        for (int i = 0; i < 16; i++) sLPC[i] = sLPC[SUBFR + i];
-        p_out += SUBFR;
+        for (int i = 0; i < 16; i++) sLPC[i] = sLPC[SF + i];
+        p_out += SF;
     }
     for (int i = 0; i < 16; i++) st->hb_sLPC[i] = sLPC[i];
     if (lostflag == 0 || lostflag == 4 || lostflag == 3) {
@@ -713,7 +716,7 @@ SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, 
     if (nb_in[0] <= 0) return -1;
     if (lostflag < 1 || lostflag > 4) return -1;
     i16 nb[2] = {nb_in[0], nb_in[1]};
-    const int nf = st->frames_per_packet, hb_bytes = 4 * nf, half = nf * FRAME;   // frames, high-band bytes, samples per band
+    const int nf = st->frames_per_packet, half = nf * FRAME, F = st->hb_frame, nhb = half / F, hb_bytes = 4 * nhb;
     i32 hb_off = dec_split_lengths(nb, lostflag, hb_bytes);
     int n0 = nb[0], n1 = nb[1];
     if (n0 < 0 || n1 < 0 || n0 + n1 > cap || hb_off > cap) return -1;
@@ -748,12 +751,12 @@ SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, 
     }
     for (int i = 0; i < half; i++) W->OutLow[i] = (float)W->lowout[i];
     const int hb_lost = (lostflag == 1 || lostflag == 2);
-    for (int f = 0; f < nf; f++) {
-        for (int i = 0; i < HB_FRAME; i++) W->res_f[i] = (float)(W->res_Q10[f * HB_FRAME + i] >> 10);
+    for (int f = 0; f < nhb; f++) {
+        for (int i = 0; i < F; i++) W->res_f[i] = (float)(W->res_Q10[f * F + i] >> 10);
         if (hb_lost) for (int i = 0; i < half; i++) W->res_Q10[i] = 0;  // App. A Q12: the memset wipes the rest of the packet
         u8 hb4[4] = {0, 0, 0, 0};
         if (!hb_lost) for (int i = 0; i < 4; i++) hb4[i] = bits[hb_off + 4 * f + i];
-        hb_decode_frame(st, hb4, W->OutHigh + f * HB_FRAME, W->res_f, lostflag);
+        hb_decode_frame(st, hb4, W->OutHigh + f * F, W->res_f, lostflag);
     }
     qmf_synth_f32(W->OutLow, W->OutHigh, W->out, st->g0_mem, st->g1_mem, half);
     for (int i = 0; i < 2 * half; i++) {

@@ -15,11 +15,12 @@ namespace sb {
 
 // ---- Init: AGR_Sate_Encoder_Init + SKP_Silk_init_encoder_FIX + first SKP_Silk_control_encoder_FIX --------------
 // Returns 0, or -1 for a configuration the reference rejects / this build does not cover.
-SB_FN int enc_state_init(EncState* st, i32 targetRate_bps, i32 dtx_enable, i32 useMDIndex, i32 framesize_ms = 40) {
+SB_FN int enc_state_init(EncState* st, i32 targetRate_bps, i32 dtx_enable, i32 useMDIndex, i32 framesize_ms = 40, i32 joint_hb = 0) {
     memset(st, 0, sizeof(EncState));
     st->frames_per_packet = framesize_ms == 20 ? 1 : 2;
+    st->hb_frame = joint_hb ? 320 : HB_FRAME;
     if (targetRate_bps <= 0) targetRate_bps = 15600;
-    i32 silk_rate = targetRate_bps - 1600;  // bwe_framesize 20 ms (AGR_BWE_SDK_API.c:118)
+    i32 silk_rate = targetRate_bps - (joint_hb ? 800 : 1600);  // (1600 * 20) / bwe_framesize_ms (AGR_BWE_SDK_API.c:118)
     silk_rate = limit(silk_rate, 5000, 100000);
     st->targetRate_bps = silk_rate;
     st->useDTX = dtx_enable ? 1 : 0;
@@ -122,12 +123,12 @@ SB_FN i32 hb_lsp_quant(i32* lsp) {
 // excitation produced by the noise-shaping quantiser: (1) buffer update, LPC analysis, LSP VQ, per-sub-frame residual
 // energy of the high band; (2) gain = 16*sqrt(E_hb)/sqrt(E_lb_exc), 32-level VQ, bit packing (12 + 4*5 bits, MSB first).
 SB_FN void hb_analyse_frame(EncCore* st, const i16* high, i32* lsp_idx_out, i32* nrg0_out) {
-    const int LPCF = 80;
-    for (int i = 0; i < HB_FRAME; i++) st->x_hb_buf[HB_FRAME + 40 + i] = high[i];
+    const int LPCF = 80, F = st->hb_frame, SF = F >> 2;   // LPC block, frame and sub-frame lengths
+    for (int i = 0; i < F; i++) st->x_hb_buf[F + 40 + i] = high[i];
     // AGR_Sate_find_HB_LPC_FIX: 4 blocks of (80 + 8) samples, hop 80, starting 8 samples before the frame
     i16 LPC_in_pre[4 * (LPCF + HB_ORDER)];
     {
-        const i16* xp = st->x_hb_buf + HB_FRAME - HB_ORDER;
+        const i16* xp = st->x_hb_buf + F - HB_ORDER;
         i16* d = LPC_in_pre;
         for (int k = 0; k < 4; k++) {
             for (int i = 0; i < LPCF + HB_ORDER; i++) d[i] = xp[i];
@@ -139,25 +140,26 @@ SB_FN void hb_analyse_frame(EncCore* st, const i16* high, i32* lsp_idx_out, i32*
     for (int i = 0; i < HB_ORDER; i++) prev_dummy[i] = 0;
     find_lpc(NLSF_Q15, &interp, prev_dummy, 0, HB_ORDER, LPC_in_pre, LPCF + HB_ORDER);
     *lsp_idx_out = hb_lsp_quant(NLSF_Q15);
-    i16 coef[HB_ORDER], exc[SUBFR];
+    i16 coef[HB_ORDER], exc[2 * SUBFR];
     nlsf2a_stable(coef, NLSF_Q15, HB_ORDER);
-    const i16* p_hb = st->x_hb_buf + HB_FRAME;
+    const i16* p_hb = st->x_hb_buf + F;
     for (int sub = 0; sub < 4; sub++) {
-        lpc_analysis_filter_zero_state(p_hb, coef, exc, SUBFR, HB_ORDER);
+        lpc_analysis_filter_zero_state(p_hb, coef, exc, SF, HB_ORDER);
         i32 nrg0 = 0;
-        for (int i = 0; i < SUBFR; i++) nrg0 = addw(nrg0, (i32)exc[i] * (i32)exc[i]);
+        for (int i = 0; i < SF; i++) nrg0 = addw(nrg0, (i32)exc[i] * (i32)exc[i]);
         nrg0_out[sub] = sqrt_approx(nrg0);
-        p_hb += SUBFR;
+        p_hb += SF;
     }
-    for (int i = 0; i < HB_FRAME + 40; i++) st->x_hb_buf[i] = st->x_hb_buf[HB_FRAME + i];
+    for (int i = 0; i < F + 40; i++) st->x_hb_buf[i] = st->x_hb_buf[F + i];
     st->hb_first = 0;
 }
 // r16 = (int16)(low-band excitation Q10 >> 10), the only form in which AGR_BWE_encode_frame_FIX.c:56-58 uses it
-SB_FN void hb_pack_frame(i32 lsp_idx, const i32* nrg0, const i16* r16, u8* out4) {
+// (sf = sub-frame length: 40, or 80 when one high-band frame spans both codec frames of the packet)
+SB_FN void hb_pack_frame(i32 lsp_idx, const i32* nrg0, const i16* r16, u8* out4, int sf = SUBFR) {
     i32 gain_idx[4];
     for (int sub = 0; sub < 4; sub++) {
         i32 nrg1 = 0;
-        for (int i = 0; i < SUBFR; i++) nrg1 = smlabb(nrg1, r16[sub * SUBFR + i], r16[sub * SUBFR + i]);
+        for (int i = 0; i < sf; i++) nrg1 = smlabb(nrg1, r16[sub * sf + i], r16[sub * sf + i]);
         nrg1 = sqrt_approx(nrg1);
         i16 gain = (i16)(shl(nrg0[sub] + 1, 4) / (nrg1 + 1));
         i32 md = SB_I32_MAX; int gi = 0;
@@ -255,7 +257,8 @@ SB_FN void enc_packet_analysis(EncCore* st, EncAnalysisWork* W, const i16* pcm, 
         SB_SYNC();
     }
     if (SB_LANE0) scr->dtx_drop = (st->useDTX && st->inDTX) ? 1 : 0;
-    for (int f = 0; f < nf; f++) SB_SERIAL(hb_analyse_frame(st, W->high + f * HB_FRAME, &scr->hb_lsp_idx[f], scr->hb_nrg0[f]));
+    const int nhb = nf * FRAME / st->hb_frame;    // high-band frames per packet
+    for (int f = 0; f < nhb; f++) SB_SERIAL(hb_analyse_frame(st, W->high + f * st->hb_frame, &scr->hb_lsp_idx[f], scr->hb_nrg0[f]));
 }
 
 // stage C: AGR_Sate_Encoder_Encode tail -- returns the byte count; nBytesOut[0] = total, nBytesOut[1] = len(MD2) + 8
@@ -263,7 +266,7 @@ SB_FN i32 enc_packet_finish(EncCore* st, const EncScratch* scr, u8* rcbuf /* MAX
     int nb[2];
     int ok = 1;
     int written = 0;
-    const int nf = st->frames_per_packet, hb_bytes = 4 * nf;
+    const int nf = st->frames_per_packet, nhb = nf * FRAME / st->hb_frame, hb_bytes = 4 * nhb;
     for (int k = 0; k < 2; k++) {
         RangeEnc rc;
         rc_enc_init(&rc, rcbuf, MAX_PAYLOAD);
@@ -284,7 +287,7 @@ SB_FN i32 enc_packet_finish(EncCore* st, const EncScratch* scr, u8* rcbuf /* MAX
     if (!ok) { nb[0] = nb[1] = 0; }
     if (scr->dtx_drop) { nb[0] = nb[1] = 0; }
     u8 hb[8];
-    for (int f = 0; f < nf; f++) hb_pack_frame(scr->hb_lsp_idx[f], scr->hb_nrg0[f], scr->r16[f], hb + 4 * f);
+    for (int f = 0; f < nhb; f++) hb_pack_frame(scr->hb_lsp_idx[f], scr->hb_nrg0[f], &scr->r16[0][0] + f * st->hb_frame, hb + 4 * f, st->hb_frame >> 2);
     int lb = nb[0] + nb[1];
     int total = lb + hb_bytes;
     for (int i = 0; i < hb_bytes; i++) if (lb + i < out_cap) out[lb + i] = hb[i];

@@ -65,6 +65,7 @@ struct alignas(16) EncCore {
     i32 useDTX;
     i32 targetRate_bps;  // SILK core rate (user rate - 1600)
     i32 frames_per_packet;  // 2: 40 ms packets (the headline configuration), 1: 20 ms packets (AGR_BWE_SDK_API.c:78-81,106-110)
+    i32 hb_frame;           // high-band frame length: 160 (20 ms), or 320 with joint_mode 1 (one 40 ms HB frame per packet, :63-66)
     // --- QMF analysis memory (AGR_BWE_structs.h:34) ---
     i16 qmf_mem[64];
     // --- SILK encoder ---
@@ -83,7 +84,7 @@ struct alignas(16) EncCore {
     i32 prev_sigtype, prevLag, typeOffsetPrev_md[2], frameCounter, first_frame_after_reset;
     i32 noSpeechCounter, inDTX, vadFlag;
     // --- high band (AGR_BWE_structs.h:14-19) ---
-    i16 x_hb_buf[2 * HB_FRAME + 40 + 120];  // tail [360,480) is read by the LPC analysis and stays zero (App. A Q26)
+    i16 x_hb_buf[2 * 320 + 40];  // ring of 2 * hb_frame + 40; with hb_frame = 160 the LPC analysis reads [360,480), which stays zero (App. A Q26)
     i32 hb_first;
 };
 struct EncState : EncCore {

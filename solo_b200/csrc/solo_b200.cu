@@ -43,9 +43,9 @@ extern "C" int sb_launch_enc_analysis_warp(void* states, void* scratch, const vo
 #define SB_DECODE_MINB 8
 #endif
 
-__global__ void __launch_bounds__(SB_TPB) sb_enc_init_kernel(EncState* states, int n, int rate, int dtx, int mdi, int framesize_ms) {
+__global__ void __launch_bounds__(SB_TPB) sb_enc_init_kernel(EncState* states, int n, int rate, int dtx, int mdi, int framesize_ms, int joint_hb) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n) enc_state_init(&states[s], rate, dtx, mdi, framesize_ms);
+    if (s < n) enc_state_init(&states[s], rate, dtx, mdi, framesize_ms, joint_hb);
 }
 
 // Encoder = three kernels per packet wave (stream s, scratch slot s):
@@ -106,9 +106,9 @@ __global__ void __launch_bounds__(SB_TPB) sb_enc_finish_kernel(EncState* states,
     nbytes[2 * s + 1] = nb[1];
 }
 
-__global__ void __launch_bounds__(SB_TPB) sb_dec_init_kernel(DecState* states, int n, int mdi, int framesize_ms) {
+__global__ void __launch_bounds__(SB_TPB) sb_dec_init_kernel(DecState* states, int n, int mdi, int framesize_ms, int joint_hb) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n) dec_state_init(&states[s], mdi, framesize_ms);
+    if (s < n) dec_state_init(&states[s], mdi, framesize_ms, joint_hb);
 }
 
 __global__ void __launch_bounds__(SB_TPB, SB_DECODE_MINB) sb_decode_kernel(DecState* states, i16* __restrict__ pcm, const u8* __restrict__ bits, int cap,
@@ -239,6 +239,7 @@ static void chunk_bounds(int n, int C, int c, int* lo, int* hi) {
 struct solo_b200_enc_batch {
     int n, device;
     int spp;                    // samples per packet and stream: 640 (40 ms) or 320 (20 ms)
+    int hb_bytes;               // high-band bytes per packet: 4 per high-band frame
     EncState* d_states;
     EncScratch* d_scratch;
     // staging for the *_host entry points
@@ -248,25 +249,24 @@ struct solo_b200_enc_batch {
 };
 struct solo_b200_dec_batch {
     int n, device;
-    int spp;
+    int spp, hb_bytes;
     DecState* d_states;
     i16* d_pcm; u8* d_bits; i16* d_nbytes; i32* d_flags; i32* d_ret; int bits_cap;
     cudaStream_t stream;
     Pipe pipe;
 };
 
-static int check_enc_ctrl(const USER_Ctrl_enc* c) {
-    if (!c) return -1;
-    if (c->samplerate != 16000 || (c->framesize_ms != 40 && c->framesize_ms != 20)) return -1;
-    if (c->joint_enable) return -1;  // joint modes: "Unsupport" / 40 ms HB frame (AGR_BWE_SDK_API.c:56-81), out of scope
-    return 0;
+// Supported configurations (AGR_BWE_SDK_API.c:40-81): 16 kHz input; no joint coding with 40 or 20 ms packets ("40ms 2MD",
+// "20ms 2MD"); joint mode 1 (one 40 ms high-band frame per 40 ms packet).  Joint modes 0, 2, 3 are "Unsupport" in the
+// reference as well; 32 kHz input is out of scope here.
+static int check_modes(int samplerate, int framesize_ms, int joint_enable, int joint_mode) {
+    if (samplerate != 16000) return -1;
+    if (!joint_enable) return (framesize_ms == 40 || framesize_ms == 20) ? 0 : -1;
+    return (joint_mode == 1 && framesize_ms == 40) ? 0 : -1;
 }
-static int check_dec_ctrl(const USER_Ctrl_dec* c) {
-    if (!c) return -1;
-    if (c->samplerate != 16000 || (c->framesize_ms != 40 && c->framesize_ms != 20)) return -1;
-    if (c->joint_enable) return -1;
-    return 0;
-}
+static int check_enc_ctrl(const USER_Ctrl_enc* c) { return c ? check_modes(c->samplerate, c->framesize_ms, c->joint_enable, c->joint_mode) : -1; }
+static int check_dec_ctrl(const USER_Ctrl_dec* c) { return c ? check_modes(c->samplerate, c->framesize_ms, c->joint_enable, c->joint_mode) : -1; }
+static int hb_bytes_of(int framesize_ms, int joint_enable) { return joint_enable ? 4 : 4 * (framesize_ms / 20); }
 
 static int require_gpu(int device) {
     int count = 0;
@@ -315,7 +315,7 @@ solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_e
     if (require_gpu(device)) return nullptr;
     solo_b200_enc_batch* b = new solo_b200_enc_batch();
     memset(b, 0, sizeof *b);
-    b->n = n_streams; b->device = device; b->spp = 16 * ctrl->framesize_ms;
+    b->n = n_streams; b->device = device; b->spp = 16 * ctrl->framesize_ms; b->hb_bytes = hb_bytes_of(ctrl->framesize_ms, ctrl->joint_enable);
     if (cudaMalloc(&b->d_states, sizeof(EncState) * (size_t)n_streams) != cudaSuccess ||
         cudaMalloc(&b->d_scratch, sizeof(EncScratch) * (size_t)n_streams) != cudaSuccess ||
         cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || pipe_create(&b->pipe) != 0 ||
@@ -324,7 +324,7 @@ solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_e
         delete b; return nullptr;
     }
     int rate = ctrl->targetRate_bps <= 0 ? 15600 : ctrl->targetRate_bps;
-    sb_enc_init_kernel<<<(n_streams + SB_TPB - 1) / SB_TPB, SB_TPB, 0, b->stream>>>(b->d_states, n_streams, rate, ctrl->dtx_enable, ctrl->useMDIndex, ctrl->framesize_ms);
+    sb_enc_init_kernel<<<(n_streams + SB_TPB - 1) / SB_TPB, SB_TPB, 0, b->stream>>>(b->d_states, n_streams, rate, ctrl->dtx_enable, ctrl->useMDIndex, ctrl->framesize_ms, ctrl->joint_enable ? 1 : 0);
     count_launch();
     cudaError_t e = cudaStreamSynchronize(b->stream);
     if (e != cudaSuccess) { fail("enc init kernel", e); cudaFree(b->d_states); delete b; return nullptr; }
@@ -429,13 +429,13 @@ solo_b200_dec_batch* solo_b200_dec_batch_create(int n_streams, const USER_Ctrl_d
     if (require_gpu(device)) return nullptr;
     solo_b200_dec_batch* b = new solo_b200_dec_batch();
     memset(b, 0, sizeof *b);
-    b->n = n_streams; b->device = device; b->spp = 16 * ctrl->framesize_ms;
+    b->n = n_streams; b->device = device; b->spp = 16 * ctrl->framesize_ms; b->hb_bytes = hb_bytes_of(ctrl->framesize_ms, ctrl->joint_enable);
     if (cudaMalloc(&b->d_states, sizeof(DecState) * (size_t)n_streams) != cudaSuccess ||
         cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || pipe_create(&b->pipe) != 0) {
         fail("dec_batch_create", cudaGetLastError());
         delete b; return nullptr;
     }
-    sb_dec_init_kernel<<<(n_streams + SB_TPB - 1) / SB_TPB, SB_TPB, 0, b->stream>>>(b->d_states, n_streams, ctrl->useMDIndex, ctrl->framesize_ms);
+    sb_dec_init_kernel<<<(n_streams + SB_TPB - 1) / SB_TPB, SB_TPB, 0, b->stream>>>(b->d_states, n_streams, ctrl->useMDIndex, ctrl->framesize_ms, ctrl->joint_enable ? 1 : 0);
     count_launch();
     cudaError_t e = cudaStreamSynchronize(b->stream);
     if (e != cudaSuccess) { fail("dec init kernel", e); cudaFree(b->d_states); delete b; return nullptr; }
@@ -633,7 +633,7 @@ SKP_int32 AGR_Sate_Encoder_Encode(void* SATEEnc_State, const SKP_int16* AGR_Sate
     int r = solo_b200_enc_batch_encode_host(b, AGR_Sate_PCM, tmp, MAX_PAYLOAD + 8, nb);
     if (r) { fprintf(stderr, "solo_b200: encode failed: %s\n", g_err); return -1; }
     // DTX packets return the high-band bytes (4 per 20 ms frame) with nBytesOut[0] == 0 (App. A Q16)
-    int total = nb[0] ? nb[0] : (b->spp / 320) * 4;
+    int total = nb[0] ? nb[0] : b->hb_bytes;
     int n = total < AGR_Sate_Buf_Size ? total : AGR_Sate_Buf_Size;
     if (n < 0) n = 0;
     memcpy(AGR_Sate_Bit, tmp, n);
@@ -673,7 +673,7 @@ SKP_int32 AGR_Sate_Decoder_Decode(void* SATEDec_State, SKP_int16* AGR_Sate_PCM, 
     int r = solo_b200_dec_batch_decode_host(b, AGR_Sate_PCM, tmp, MAX_PAYLOAD + 8, nb, &flag, &ret);
     if (r) { fprintf(stderr, "solo_b200: decode failed: %s\n", g_err); return -1; }
     // the reference rewrites the caller's nBytes[] while splitting the payload (AGR_BWE_decode_frame_FLP.c:171-190)
-    dec_split_lengths(nb, lostflag, (b->spp / 320) * 4);
+    dec_split_lengths(nb, lostflag, b->hb_bytes);
     nBytes[0] = nb[0];
     nBytes[1] = nb[1];
     *nSamplesOut = (SKP_int16)((solo_b200_dec_batch*)SATEDec_State)->spp;

@@ -24,12 +24,13 @@ static void init() { if (!inited) { pthread_barrier_init(&bar, nullptr, 32); ini
 
 extern "C" {
 struct HsEnc { sb::EncState st; sb::EncPacketWork w; };
-void* hs_enc_create2(int rate, int dtx, int mdi, int framesize_ms) {
+void* hs_enc_create3(int rate, int dtx, int mdi, int framesize_ms, int joint_hb) {
     HsEnc* h = (HsEnc*)calloc(1, sizeof(HsEnc));
-    sb::enc_state_init(&h->st, rate, dtx, mdi, framesize_ms);
+    sb::enc_state_init(&h->st, rate, dtx, mdi, framesize_ms, joint_hb);
     h->w.a.nlsf_fast = nullptr;
     return h;
 }
+void* hs_enc_create2(int rate, int dtx, int mdi, int framesize_ms) { return hs_enc_create3(rate, dtx, mdi, framesize_ms, 0); }
 void* hs_enc_create(int rate, int dtx, int mdi) { return hs_enc_create2(rate, dtx, mdi, 40); }
 int hs_enc_encode(void* p, const short* pcm, unsigned char* out, int cap, short* nb) {
     HsEnc* h = (HsEnc*)p;
@@ -59,11 +60,12 @@ void* hs_enc_state(void* p) { return &((HsEnc*)p)->st; }
 void* hs_enc_ctrl(void* p) { return &((HsEnc*)p)->w.scr.c[1]; }
 
 struct HsDec { sb::DecState st; sb::DecPacketWork w; };
-void* hs_dec_create2(int mdi, int framesize_ms) {
+void* hs_dec_create3(int mdi, int framesize_ms, int joint_hb) {
     HsDec* h = (HsDec*)calloc(1, sizeof(HsDec));
-    sb::dec_state_init(&h->st, mdi, framesize_ms);
+    sb::dec_state_init(&h->st, mdi, framesize_ms, joint_hb);
     return h;
 }
+void* hs_dec_create2(int mdi, int framesize_ms) { return hs_dec_create3(mdi, framesize_ms, 0); }
 void* hs_dec_create(int mdi) { return hs_dec_create2(mdi, 40); }
 // same calling convention as AGR_Sate_Decoder_Decode (payload pre-trimmed by the caller); nb is not modified
 int hs_dec_decode(void* p, short* pcm, const unsigned char* bits, int cap, const short* nb, int lostflag) {

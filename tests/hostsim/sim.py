@@ -22,6 +22,10 @@ def lib(emu=None):
         L.hs_enc_create2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
         L.hs_dec_create2.restype = C.c_void_p
         L.hs_dec_create2.argtypes = [C.c_int, C.c_int]
+        L.hs_enc_create3.restype = C.c_void_p
+        L.hs_enc_create3.argtypes = [C.c_int] * 5
+        L.hs_dec_create3.restype = C.c_void_p
+        L.hs_dec_create3.argtypes = [C.c_int] * 3
         L.hs_enc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hs_enc_destroy.argtypes = [C.c_void_p]
         L.hs_dec_create.restype = C.c_void_p
@@ -33,9 +37,9 @@ def lib(emu=None):
 
 
 class SimEncoder:
-    def __init__(self, rate=13600, dtx=0, use_md_index=0, cap=1024, emu=None, framesize_ms=40):
+    def __init__(self, rate=13600, dtx=0, use_md_index=0, cap=1024, emu=None, framesize_ms=40, joint_hb=0):
         self.L = lib(emu)
-        self.h = self.L.hs_enc_create2(rate, dtx, use_md_index, framesize_ms)
+        self.h = self.L.hs_enc_create3(rate, dtx, use_md_index, framesize_ms, joint_hb)
         self.samples = 16 * framesize_ms
         self.cap = cap
         self.out = np.zeros(cap, np.uint8)
@@ -54,9 +58,9 @@ class SimEncoder:
 
 
 class SimDecoder:
-    def __init__(self, use_md_index=0, framesize_ms=40):
+    def __init__(self, use_md_index=0, framesize_ms=40, joint_hb=0):
         self.L = lib()
-        self.h = self.L.hs_dec_create2(use_md_index, framesize_ms)
+        self.h = self.L.hs_dec_create3(use_md_index, framesize_ms, joint_hb)
         self.pcm = np.zeros(16 * framesize_ms, np.int16)
 
     def decode(self, payload, nbytes, lostflag):

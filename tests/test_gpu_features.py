@@ -264,3 +264,38 @@ def test_example_file_codec_reproduces_the_reference_cli_files(sb, tmp_path):
         out = tmp_path / ("out_%s_%s.pcm" % tuple(args))
         subprocess.check_call([str(exe), "dec", str(bit), str(out)] + args)
         assert hashlib.md5(out.read_bytes()).hexdigest() == str(g[key]), key
+
+
+def test_joint_mode1_on_device(sb):
+    """The reference's joint mode 1 through the batched ABI and the drop-in ABI (unsupported modes are refused)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    N, T, cap = 67, 20, 192
+    x = speech_replay(load_clip(), N, T)
+    eb, db = sb.EncoderBatch(N, rate=13600, joint_hb=1), sb.DecoderBatch(N, joint_hb=1)
+    sample = [0, 1, 33, 66]
+    renc = {s: ref.RefEncoder("fix", rate=13600, joint_hb=1) for s in sample}
+    rdec = {s: ref.RefDecoder("flp", joint_hb=1) for s in sample}
+    flags = np.array([loss_flags(T, 40, seed=11 + s) for s in range(N)], np.int32)
+    for p in range(T):
+        bits, nb = eb.encode(x[p], cap=cap)
+        tb, tnb = np.zeros_like(bits), np.zeros_like(nb)
+        for s in range(N):
+            pb, pnb = trim_payload(bytes(bits[s, :nb[s, 0]]), nb[s], flags[s, p])
+            tb[s, :len(pb)] = np.frombuffer(pb, np.uint8); tnb[s] = pnb
+        pcm, ret = db.decode(tb, tnb, flags[:, p].copy())
+        assert (ret == 0).all()
+        for s in sample:
+            b, rnb, n = renc[s].encode(x[p, s])
+            assert tuple(nb[s]) == rnb and bytes(bits[s, :n]) == b, (p, s)
+            want, r = rdec[s].decode(bytes(tb[s, :tnb[s, 0]]), tuple(tnb[s]), int(flags[s, p]))
+            assert np.array_equal(pcm[s], want), (p, s)
+    eb.close(); db.close()
+    e = sb.SoloEncoder(rate=13600, joint_enable=1, joint_mode=1)
+    b, nb2, n = e.encode(x[0, 0])
+    assert (b, nb2, n) == ref.RefEncoder("fix", rate=13600, joint_hb=1).encode(x[0, 0])
+    e.close()
+    for bad in (dict(joint_enable=1, joint_mode=0), dict(joint_enable=1, joint_mode=2), dict(samplerate=32000), dict(framesize_ms=60)):
+        with pytest.raises(sb.SoloError):
+            sb.SoloEncoder(**bad)

@@ -187,3 +187,29 @@ def test_20ms_packets_match_reference(sim, ref):
             assert np.abs(y0.astype(np.int32) - y1.astype(np.int32)).max() <= PCM_TOL, (rate, p, f)
         for o in (e0, e1, d0, d1):
             o.close()
+
+
+def test_joint_mode1_matches_reference(sim, ref):
+    """joint_enable = 1, joint_mode = 1 (AGR_BWE_SDK_API.c:63-66): one 40 ms high-band frame (4 bytes, 80-sample
+    sub-frames) per packet, core rate = target - 800."""
+    clip = load_clip()
+    for rate, dtx, mdi in ((13600, 0, 0), (8000, 0, 1), (24000, 1, 0)):
+        e0 = ref.RefEncoder("fix", rate=rate, dtx=dtx, use_md_index=mdi, joint_hb=1)
+        e1 = sim.SimEncoder(rate=rate, dtx=dtx, use_md_index=mdi, joint_hb=1)
+        d0, d1 = ref.RefDecoder("flp", use_md_index=mdi, joint_hb=1), sim.SimDecoder(use_md_index=mdi, joint_hb=1)
+        flags = loss_flags(120, 30, seed=9)
+        for p in range(120):
+            x = clip[p * 640:(p + 1) * 640]
+            b0, nb0, n0 = e0.encode(x)
+            b1, nb1, n1 = e1.encode(x)
+            assert (b0[:max(n0, 0)], nb0, n0) == (b1[:max(n1, 0)], nb1, n1), (rate, p)
+            if nb0[0] > 0:
+                pb, pnb, f = trim_payload(b0, nb0, flags[p]) + (flags[p],)
+            else:
+                pb, pnb, f = bytes(16), (16, 8), 1
+            y0, r0 = d0.decode(pb, pnb, f)
+            y1, r1 = d1.decode(pb, pnb, f)
+            assert r0 == r1 == 0
+            assert np.abs(y0.astype(np.int32) - y1.astype(np.int32)).max() <= PCM_TOL, (rate, p, f)
+        for o in (e0, e1, d0, d1):
+            o.close()
