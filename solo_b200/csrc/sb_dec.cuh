@@ -650,8 +650,8 @@ SB_FN void qmf_synth_f32(const float* x1, const float* x2, float* y, float* mem1
 
 // ---- AGR_Bwe_decode_frame_FLP (AGR_BWE_decode_frame_FLP.c:41-130): one 20 ms high-band frame ------------------------
 // res_f: float copy of (residue >> 10) for this frame; hb4: the 4 coded bytes (ignored on loss).
-SB_FN void hb_decode_frame(DecState* st, const u8* hb4, float* OutHigh, const float* res_f, int lostflag) {
-    const int SF = st->hb_frame >> 2;   // sub-frame length: 40, or 80 with joint_mode 1
+template <int SF> SB_FN void hb_decode_frame_t(DecState* st, const u8* hb4, float* OutHigh, const float* res_f, int lostflag) {
+    // SF = sub-frame length: 40, or 80 with joint_mode 1
     float QHB_LSP[HB_ORDER], QGain[4], HB_PredCoef[HB_ORDER], HB_LPCRes[2 * SUBFR];
     float sLPC[16 + 2 * SUBFR];
     if (lostflag == 1 || lostflag == 2) {
@@ -698,6 +698,11 @@ SB_FN void hb_decode_frame(DecState* st, const u8* hb4, float* OutHigh, const fl
         for (int i = 0; i < HB_ORDER; i++) st->hb_prev_NLSFq[i] = QHB_LSP[i];
     }
     st->hb_first = 0;
+}
+
+SB_FN void hb_decode_frame(DecState* st, const u8* hb4, float* OutHigh, const float* res_f, int lostflag) {
+    if (st->hb_frame == HB_FRAME) hb_decode_frame_t<SUBFR>(st, hb4, OutHigh, res_f, lostflag);
+    else hb_decode_frame_t<2 * SUBFR>(st, hb4, OutHigh, res_f, lostflag);
 }
 
 // ---- AGR_Sate_Decoder_Decode / AGR_Sate_decode_process (AGR_BWE_decode_frame_FLP.c:134-232) --------------------------

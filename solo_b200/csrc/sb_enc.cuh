@@ -122,8 +122,8 @@ SB_FN i32 hb_lsp_quant(i32* lsp) {
 // ---- AGR_Bwe_encode_frame_FIX (AGR_BWE_encode_frame_FIX.c:8-82), split in two because the gain needs the low-band
 // excitation produced by the noise-shaping quantiser: (1) buffer update, LPC analysis, LSP VQ, per-sub-frame residual
 // energy of the high band; (2) gain = 16*sqrt(E_hb)/sqrt(E_lb_exc), 32-level VQ, bit packing (12 + 4*5 bits, MSB first).
-SB_FN void hb_analyse_frame(EncCore* st, const i16* high, i32* lsp_idx_out, i32* nrg0_out) {
-    const int LPCF = 80, F = st->hb_frame, SF = F >> 2;   // LPC block, frame and sub-frame lengths
+template <int F> SB_FN void hb_analyse_frame_t(EncCore* st, const i16* high, i32* lsp_idx_out, i32* nrg0_out) {
+    const int LPCF = 80, SF = F >> 2;   // LPC block and sub-frame lengths; F = frame length (compile-time: the loops unroll)
     for (int i = 0; i < F; i++) st->x_hb_buf[F + 40 + i] = high[i];
     // AGR_Sate_find_HB_LPC_FIX: 4 blocks of (80 + 8) samples, hop 80, starting 8 samples before the frame
     i16 LPC_in_pre[4 * (LPCF + HB_ORDER)];
@@ -152,6 +152,10 @@ SB_FN void hb_analyse_frame(EncCore* st, const i16* high, i32* lsp_idx_out, i32*
     }
     for (int i = 0; i < F + 40; i++) st->x_hb_buf[i] = st->x_hb_buf[F + i];
     st->hb_first = 0;
+}
+SB_FN void hb_analyse_frame(EncCore* st, const i16* high, i32* lsp_idx_out, i32* nrg0_out) {
+    if (st->hb_frame == HB_FRAME) hb_analyse_frame_t<HB_FRAME>(st, high, lsp_idx_out, nrg0_out);
+    else hb_analyse_frame_t<2 * HB_FRAME>(st, high, lsp_idx_out, nrg0_out);
 }
 // r16 = (int16)(low-band excitation Q10 >> 10), the only form in which AGR_BWE_encode_frame_FIX.c:56-58 uses it
 // (sf = sub-frame length: 40, or 80 when one high-band frame spans both codec frames of the packet)
