@@ -258,6 +258,10 @@ SB_HD i32 cos_approx_q24(i32 x) { return sin_approx_q24(x + 16384); }
 SB_HD i32 lcg_rand(i32 seed) { return mlaw(907633515, seed, 196314165); }
 
 // round-half-away float->int (SigProc_FIX.h:629-632)
-SB_HD i32 float2int(double x) { return (i32)((x > 0) ? x + 0.5 : x - 0.5); }
+// float / double -> int32 by truncation, with the out-of-range behaviour of the reference's build target made explicit:
+// x86 cvttss2si / cvttsd2si return INT_MIN ("integer indefinite") for NaN and for values outside int32, where CUDA's cvt
+// would saturate and ISO C leaves it undefined.  Only reachable with corrupted payloads (a blown-up synthesis filter).
+SB_HD i32 trunc_i32(double x) { return (x > -2147483649.0 && x < 2147483648.0) ? (i32)x : SB_I32_MIN; }
+SB_HD i32 float2int(double x) { return trunc_i32((x > 0) ? x + 0.5 : x - 0.5); }
 
 }  // namespace sb

@@ -37,6 +37,9 @@ struct DecState {
     i16 outBuf[2 * FRAME];
     i32 lagPrev, first_frame_after_reset, moreInternalDecoderFrames, nFramesDecoded, FrameTermination;
     i32 nBytesLeft[2];
+    // range decoder position of a payload that is still being consumed when the packet call returns (see DecStale)
+    u32 rc_base_Q32[2], rc_range_Q16[2];
+    i32 rc_bufferIx[2], rc_error[2], rc_bufLen[2];
     i32 vadFlag, lossCnt, prev_sigtype;
     // PLC (structs.h:268-280)
     i32 plc_pitchL_Q8, plc_last_frame_lost, plc_rand_seed, plc_conc_energy, plc_conc_energy_shift;
@@ -705,6 +708,16 @@ SB_FN void hb_decode_frame(DecState* st, const u8* hb4, float* OutHigh, const fl
     else hb_decode_frame_t<2 * SUBFR>(st, hb4, OutHigh, res_f, lostflag);
 }
 
+// A payload outliving its packet.  The reference keeps the range decoders (with their own copy of the payload) in the
+// persistent state (structs.h:85-92, 295-303) and re-initialises them only when the previous packet is finished.  A
+// corrupted packet whose last frame terminator decodes as "more frames" (with bytes left) therefore makes the following
+// calls continue in the OLD payload, up to 5 frames, ignoring the low-band bytes they are given
+// (SKP_Silk_dec_API.c:104-124, decode_frame.c:88-97).  Valid streams never get there; to behave identically on corrupted
+// ones the payload copies are kept here, in storage that is only touched in that case.
+struct DecStale {
+    u8 pay[2][MAX_PAYLOAD + 8];
+};
+
 // ---- AGR_Sate_Decoder_Decode / AGR_Sate_decode_process (AGR_BWE_decode_frame_FLP.c:134-232) --------------------------
 struct DecPacketWork {
     DecCtrl c;
@@ -717,16 +730,33 @@ struct DecPacketWork {
 };
 
 // bits/cap: payload row as handed in by the caller; nb: {n0, n1} (not modified); returns the reference's return code.
-SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, int cap, const i16* nb_in, i32 lostflag) {
+SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, int cap, const i16* nb_in, i32 lostflag, DecStale* stale = nullptr) {
     if (nb_in[0] <= 0) return -1;
     if (lostflag < 1 || lostflag > 4) return -1;
+    // frame control starts from zeros: after a rejected (corrupted) frame a few of its fields are read before anything
+    // has written them (the reference reads uninitialised stack there); zeros keep host and device builds deterministic
+    memset(&W->c, 0, sizeof(DecCtrl));
     i16 nb[2] = {nb_in[0], nb_in[1]};
     const int nf = st->frames_per_packet, half = nf * FRAME, F = st->hb_frame, nhb = half / F, hb_bytes = 4 * nhb;
     i32 hb_off = dec_split_lengths(nb, lostflag, hb_bytes);
     int n0 = nb[0], n1 = nb[1];
     if (n0 < 0 || n1 < 0 || n0 + n1 > cap || hb_off > cap) return -1;
+    RangeDec rc[2];
+    for (int k = 0; k < 2; k++) {   // fully defined even for a description this packet does not carry
+        rc[k].base_Q32 = 0; rc[k].range_Q16 = 0; rc[k].bufferIx = 0; rc[k].error = 0; rc[k].bufLen = 0; rc[k].buf = W->pay[k];
+    }
+    bool cont = st->moreInternalDecoderFrames != 0;   // only after a corrupted packet, see DecStale
+    if (cont && !stale) { st->moreInternalDecoderFrames = 0; cont = false; }   // no storage given: resynchronise on this packet
+    if (cont) {
+        for (int k = 0; k < 2; k++) {
+            for (int i = 0; i < MAX_PAYLOAD + 8; i++) W->pay[k][i] = stale->pay[k][i];
+            rc[k].base_Q32 = st->rc_base_Q32[k]; rc[k].range_Q16 = st->rc_range_Q16[k];
+            rc[k].bufferIx = st->rc_bufferIx[k]; rc[k].error = st->rc_error[k]; rc[k].bufLen = st->rc_bufLen[k];
+            rc[k].buf = W->pay[k];
+        }
+    }
     // zero-padded private copies of the description payloads (the range decoder may read up to 4 bytes past the end)
-    if (lostflag != 1) {
+    if (lostflag != 1 && !cont) {
         int c0 = imin(n0, MAX_PAYLOAD), c1 = imin(n1, MAX_PAYLOAD);
         for (int i = 0; i < c0; i++) W->pay[0][i] = bits[i];
         for (int i = c0; i < c0 + 8; i++) W->pay[0][i] = 0;
@@ -736,8 +766,6 @@ SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, 
         }
     }
     for (int i = 0; i < half; i++) { W->res_Q10[i] = 0; W->lowout[i] = 0; }
-    RangeDec rc[2];
-    rc[0].error = 0; rc[1].error = 0; rc[0].bufLen = 0; rc[1].bufLen = 0;
     for (int f = 0; f < nf; f++) {
         i32 ret;
         if (!st->seen_good && lostflag == 1) {
@@ -754,6 +782,13 @@ SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, 
         if (ret < 0) return ret;
         for (int i = 0; i < FRAME; i++) W->res_Q10[f * FRAME + i] = st->exc_Q10[i];
     }
+    if (st->moreInternalDecoderFrames && stale) {     // the payload outlives this call
+        for (int k = 0; k < 2; k++) {
+            for (int i = 0; i < MAX_PAYLOAD + 8; i++) stale->pay[k][i] = W->pay[k][i];
+            st->rc_base_Q32[k] = rc[k].base_Q32; st->rc_range_Q16[k] = rc[k].range_Q16;
+            st->rc_bufferIx[k] = rc[k].bufferIx; st->rc_error[k] = rc[k].error; st->rc_bufLen[k] = rc[k].bufLen;
+        }
+    }
     for (int i = 0; i < half; i++) W->OutLow[i] = (float)W->lowout[i];
     const int hb_lost = (lostflag == 1 || lostflag == 2);
     for (int f = 0; f < nhb; f++) {
@@ -765,7 +800,7 @@ SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, 
     }
     qmf_synth_f32(W->OutLow, W->OutHigh, W->out, st->g0_mem, st->g1_mem, half);
     for (int i = 0; i < 2 * half; i++) {
-        i32 t = (i32)W->out[i];
+        i32 t = trunc_i32((double)W->out[i]);
         if (t > 32767) t = 32767; else if (t < -32768) t = -32768;
         vout[i] = (i16)t;
     }

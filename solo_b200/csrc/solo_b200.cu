@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(SB_TPB) sb_dec_init_kernel(DecState* states, i
 
 __global__ void __launch_bounds__(SB_TPB, SB_DECODE_MINB) sb_decode_kernel(DecState* states, i16* __restrict__ pcm, const u8* __restrict__ bits, int cap,
                                                            const i16* __restrict__ nbytes, const i32* __restrict__ lostflag,
-                                                           i32* __restrict__ ret, int spp, int n) {
+                                                           i32* __restrict__ ret, DecStale* stale, int spp, int n) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     DecPacketWork W;
@@ -121,10 +121,10 @@ __global__ void __launch_bounds__(SB_TPB, SB_DECODE_MINB) sb_decode_kernel(DecSt
     i16 out[PACKET];
 #if SB_DECODE_LOCAL_STATE
     DecState st = states[s];
-    i32 r = dec_packet(&st, &W, out, bits + (size_t)s * cap, cap, nb, lostflag[s]);
+    i32 r = dec_packet(&st, &W, out, bits + (size_t)s * cap, cap, nb, lostflag[s], &stale[s]);
     states[s] = st;
 #else
-    i32 r = dec_packet(&states[s], &W, out, bits + (size_t)s * cap, cap, nb, lostflag[s]);
+    i32 r = dec_packet(&states[s], &W, out, bits + (size_t)s * cap, cap, nb, lostflag[s], &stale[s]);
 #endif
     int4* dst = reinterpret_cast<int4*>(pcm + (size_t)s * spp);
     const int4* src = reinterpret_cast<const int4*>(out);
@@ -251,6 +251,7 @@ struct solo_b200_dec_batch {
     int n, device;
     int spp, hb_bytes;
     DecState* d_states;
+    DecStale* d_stale;          // payload copies that outlive a packet call (only touched after a corrupted packet, see sb_dec.cuh)
     i16* d_pcm; u8* d_bits; i16* d_nbytes; i32* d_flags; i32* d_ret; int bits_cap;
     cudaStream_t stream;
     Pipe pipe;
@@ -431,6 +432,7 @@ solo_b200_dec_batch* solo_b200_dec_batch_create(int n_streams, const USER_Ctrl_d
     memset(b, 0, sizeof *b);
     b->n = n_streams; b->device = device; b->spp = 16 * ctrl->framesize_ms; b->hb_bytes = hb_bytes_of(ctrl->framesize_ms, ctrl->joint_enable);
     if (cudaMalloc(&b->d_states, sizeof(DecState) * (size_t)n_streams) != cudaSuccess ||
+        cudaMalloc(&b->d_stale, sizeof(DecStale) * (size_t)n_streams) != cudaSuccess ||
         cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || pipe_create(&b->pipe) != 0) {
         fail("dec_batch_create", cudaGetLastError());
         delete b; return nullptr;
@@ -447,7 +449,7 @@ static int dec_launch(solo_b200_dec_batch* b, int lo, int n, i16* d_pcm, const u
     if (n <= 0) return 0;
     EvPair ev; prof_begin(st, 3, &ev);
     sb_decode_kernel<<<(n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states + lo, d_pcm + (size_t)lo * b->spp, d_bits + (size_t)lo * cap, cap,
-                                                                  d_nbytes + 2 * (size_t)lo, d_lostflag + lo, d_ret ? d_ret + lo : nullptr, b->spp, n);
+                                                                  d_nbytes + 2 * (size_t)lo, d_lostflag + lo, d_ret ? d_ret + lo : nullptr, b->d_stale + lo, b->spp, n);
     prof_end(st, &ev);
     count_launch();
     CK(cudaGetLastError());
@@ -521,7 +523,7 @@ void solo_b200_dec_batch_destroy(solo_b200_dec_batch* b) {
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     pipe_destroy(&b->pipe);
-    cudaFree(b->d_states); cudaFree(b->d_pcm); cudaFree(b->d_bits); cudaFree(b->d_nbytes); cudaFree(b->d_flags); cudaFree(b->d_ret);
+    cudaFree(b->d_states); cudaFree(b->d_stale); cudaFree(b->d_pcm); cudaFree(b->d_bits); cudaFree(b->d_nbytes); cudaFree(b->d_flags); cudaFree(b->d_ret);
     cudaStreamDestroy(b->stream);
     delete b;
 }

@@ -59,7 +59,7 @@ int hs_enc_work_size() { return (int)sizeof(sb::EncPacketWork); }
 void* hs_enc_state(void* p) { return &((HsEnc*)p)->st; }
 void* hs_enc_ctrl(void* p) { return &((HsEnc*)p)->w.scr.c[1]; }
 
-struct HsDec { sb::DecState st; sb::DecPacketWork w; };
+struct HsDec { sb::DecState st; sb::DecPacketWork w; sb::DecStale stale; };
 void* hs_dec_create3(int mdi, int framesize_ms, int joint_hb) {
     HsDec* h = (HsDec*)calloc(1, sizeof(HsDec));
     sb::dec_state_init(&h->st, mdi, framesize_ms, joint_hb);
@@ -70,7 +70,7 @@ void* hs_dec_create(int mdi) { return hs_dec_create2(mdi, 40); }
 // same calling convention as AGR_Sate_Decoder_Decode (payload pre-trimmed by the caller); nb is not modified
 int hs_dec_decode(void* p, short* pcm, const unsigned char* bits, int cap, const short* nb, int lostflag) {
     HsDec* h = (HsDec*)p;
-    return sb::dec_packet(&h->st, &h->w, pcm, bits, cap, nb, lostflag);
+    return sb::dec_packet(&h->st, &h->w, pcm, bits, cap, nb, lostflag, &h->stale);
 }
 void hs_dec_destroy(void* p) { free(p); }
 int hs_dec_state_size() { return (int)sizeof(sb::DecState); }

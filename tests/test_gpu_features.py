@@ -299,3 +299,39 @@ def test_joint_mode1_on_device(sb):
     for bad in (dict(joint_enable=1, joint_mode=0), dict(joint_enable=1, joint_mode=2), dict(samplerate=32000), dict(framesize_ms=60)):
         with pytest.raises(sb.SoloError):
             sb.SoloEncoder(**bad)
+
+
+def test_malformed_payloads_do_not_fault_and_match_the_host_build(sb):
+    """Bit-flipped / random / mislabelled payloads on the device: the kernel must survive (a fault would kill the whole
+    batch) and, the arithmetic being deterministic, produce exactly what the host build of the same source produces --
+    including the reference's 'stale payload' continuation after a corrupted frame terminator."""
+    from tests.hostsim import sim
+    N, T, cap = 96, 24, 128
+    rng = np.random.Generator(np.random.PCG64(21))
+    x = speech_replay(load_clip(), N, T)
+    eb, db = sb.EncoderBatch(N), sb.DecoderBatch(N)
+    hdec = [sim.SimDecoder() for _ in range(N)]
+    for p in range(T):
+        bits, nb = eb.encode(x[p], cap=cap)
+        bits, nb = bits.copy(), nb.copy()
+        flags = rng.integers(1, 5, size=N).astype(np.int32)
+        for s in range(N):
+            kind = int(rng.integers(0, 6))
+            n0 = int(nb[s, 0])
+            if kind == 1:
+                for _ in range(int(rng.integers(1, 4))):
+                    bits[s, int(rng.integers(0, n0))] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            elif kind == 2:
+                bits[s] = rng.integers(0, 256, size=cap).astype(np.uint8)
+            elif kind == 3:
+                nb[s] = (int(rng.integers(1, cap + 1)), 0)
+                nb[s, 1] = int(rng.integers(0, int(nb[s, 0]) + 1))
+            elif kind == 4:
+                flags[s] = int(rng.integers(-2, 8))
+        pcm, ret = db.decode(bits, nb, flags)
+        for s in range(N):
+            want, r = hdec[s].decode(bytes(bits[s]), (int(nb[s, 0]), int(nb[s, 1])), int(flags[s]))
+            assert r == ret[s], (p, s, r, ret[s])
+            if r == 0:
+                assert np.array_equal(want, pcm[s]), (p, s)
+    eb.close(); db.close()
