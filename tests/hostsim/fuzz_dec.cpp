@@ -1,5 +1,5 @@
-// Robustness fuzzer for the decoder arithmetic (host build of solo_b200/csrc, test infrastructure only).
-// Encodes a synthetic signal, then feeds the decoder corrupted / truncated / random payloads with random lost flags.
+// Robustness fuzzer for the codec arithmetic, decoder first (host build of solo_b200/csrc, test infrastructure only).
+// Encodes synthetic signals (incl. full-scale noise, rail-to-rail, impulses), then feeds the decoder corrupted / truncated / random payloads with random lost flags.
 // Build with -fsanitize=address,undefined: any out-of-bounds table or buffer access on malformed input shows up here
 // instead of as a faulting CUDA kernel that takes the whole batch down.
 //   g++ -O1 -g -std=c++17 -fsanitize=address,undefined -fno-sanitize-recover=all -w tests/hostsim/fuzz_dec.cpp -o fuzz_dec && ./fuzz_dec [iterations] [seed]
@@ -32,7 +32,16 @@ int main(int argc, char** argv) {
         double ph = 0;
         for (int it = 0; it < iters; it++) {
             short pcm[640], nb[2] = {0, 0}, out[640];
-            for (int i = 0; i < spp; i++) { ph += 0.05 + 0.04 * sin(it * 0.01); pcm[i] = (short)(6000 * sin(ph) + (int)(rnd() % 2000) - 1000); }
+            const int sig = (it / 50) % 6;     // encoder input classes: tonal + noise, full-scale noise, rails, silence, impulses, DC steps
+            for (int i = 0; i < spp; i++) {
+                ph += 0.05 + 0.04 * sin(it * 0.01);
+                if (sig == 0) pcm[i] = (short)(6000 * sin(ph) + (int)(rnd() % 2000) - 1000);
+                else if (sig == 1) pcm[i] = (short)rnd();
+                else if (sig == 2) pcm[i] = (rnd() & 64) ? 32767 : -32768;
+                else if (sig == 3) pcm[i] = 0;
+                else if (sig == 4) pcm[i] = (rnd() % 97 == 0) ? (short)((rnd() & 1) ? 32767 : -32768) : 0;
+                else pcm[i] = (short)(((it >> 2) & 1) ? 30000 : -30000);
+            }
             std::vector<unsigned char> row(1100, 0);        // exact-size heap buffers so that ASan sees overruns
             sb::enc_packet(est, ew, pcm, row.data(), 1024, nb);
             int kind = rnd() % 8, flag = 1 + rnd() % 4;
