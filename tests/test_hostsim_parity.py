@@ -213,3 +213,39 @@ def test_joint_mode1_matches_reference(sim, ref):
             assert np.abs(y0.astype(np.int32) - y1.astype(np.int32)).max() <= PCM_TOL, (rate, p, f)
         for o in (e0, e1, d0, d1):
             o.close()
+
+
+def test_long_run_with_level_changes_dtx_and_loss_bursts(sim, ref):
+    """Soak: 1 000 packets per configuration (40 ms, 20 ms, joint mode 1) of programme material that changes level, goes
+    silent (DTX on) and suffers loss bursts -- counters, hysteresis, CNG and concealment state must track the reference
+    packet after packet."""
+    clip = load_clip()
+    rng = np.random.Generator(np.random.PCG64(5))
+    for rate, dtx, mdi, fs, j in ((13600, 1, 0, 40, 0), (9000, 0, 1, 20, 0), (20000, 1, 0, 40, 1)):
+        spp = 16 * fs
+        kw = dict(rate=rate, dtx=dtx, use_md_index=mdi, framesize_ms=fs, joint_hb=j)
+        e0, e1 = ref.RefEncoder("fix", **kw), sim.SimEncoder(**kw)
+        d0 = ref.RefDecoder("flp", use_md_index=mdi, framesize_ms=fs, joint_hb=j)
+        d1 = sim.SimDecoder(use_md_index=mdi, framesize_ms=fs, joint_hb=j)
+        P = 1000
+        flags = loss_flags(P, 25, seed=77)
+        pos, gain = 0, 1.0
+        for p in range(P):
+            if p % 97 == 0:
+                gain = [1.0, 0.5, 0.1, 2.5, 0.0][int(rng.integers(0, 5))]
+            seg = clip[pos:pos + spp]
+            pos = (pos + spp) % (len(clip) - spp)
+            x = np.clip(seg.astype(np.float64) * gain, -32768, 32767).astype(np.int16)
+            b0, nb0, n0 = e0.encode(x)
+            b1, nb1, n1 = e1.encode(x)
+            assert (b0[:max(n0, 0)], nb0, n0) == (b1[:max(n1, 0)], nb1, n1), (rate, p)
+            f = flags[p] if (p // 200) % 2 == 0 else (1 if rng.random() < 0.6 else 4)
+            if nb0[0] <= 0:
+                pb, pnb, f = bytes(16), (16, 8), 1
+            else:
+                pb, pnb = trim_payload(b0, nb0, f)
+            y0, r0 = d0.decode(pb, pnb, f)
+            y1, r1 = d1.decode(pb, pnb, f)
+            assert r0 == r1 == 0 and np.abs(y0.astype(np.int32) - y1.astype(np.int32)).max() <= PCM_TOL, (rate, p, f)
+        for o in (e0, e1, d0, d1):
+            o.close()
