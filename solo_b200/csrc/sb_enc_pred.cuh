@@ -70,7 +70,7 @@ SB_FN void corr_matrix(const i16* x, int L, int order, int head_room, i32* XX, i
 }
 
 // ---- SKP_Silk_solve_LS_FIX.c:41-241 (M = 5) -----------------------------------------------------------------
-SB_FN void solve_ldl5(i32* A, const i32* b, i32* x_Q16) {
+SB_FN_BIG void solve_ldl5(i32* A, const i32* b, i32* x_Q16) {
     const int M = 5;
     i32 L_Q16[M * M], Y[M], invD_Q36[M], invD_Q48[M], v_Q0[M], D_Q0[M];
     i32 diag_min_value = imax(smmul(add_sat32(A[0], A[M * M - 1]), SB_FIXC(1e-5f, 31)), 1 << 9);
@@ -337,7 +337,7 @@ SB_FN void ltp_scale_ctrl(EncCore* st, EncCtrl* c, int frame_in_packet) {
 }
 
 // ---- SKP_Silk_LTP_analysis_filter_FIX.c:30-80 --------------------------------------------------------------
-SB_FN void ltp_analysis_filter(i16* LTP_res, const i16* x, const i16* LTPCoef_Q14, const i32* pitchL, const i32* invGains_Q16) {
+SB_FN_BIG void ltp_analysis_filter(i16* LTP_res, const i16* x, const i16* LTPCoef_Q14, const i32* pitchL, const i32* invGains_Q16) {
     const int pre = LPC_ORDER;
     const i16* x_ptr = x;
     i16* out = LTP_res;
@@ -359,7 +359,7 @@ SB_FN void ltp_analysis_filter(i16* LTP_res, const i16* x, const i16* LTPCoef_Q1
 
 // ---- SKP_Silk_find_LPC_FIX.c:32-148 --------------------------------------------------------------------
 // x: nb_subfr blocks of subfr_length samples (each with `order` preceding samples); x is 4-byte aligned.
-SB_FN void find_lpc(i32* NLSF_Q15, i32* interpIndex, const i32* prev_NLSFq_Q15, int useInterp, int order, const i16* x,
+SB_FN_BIG void find_lpc(i32* NLSF_Q15, i32* interpIndex, const i32* prev_NLSFq_Q15, int useInterp, int order, const i16* x,
                     int subfr_length) {
     i32 a_Q16[16], a_tmp_Q16[16], NLSF0_Q15[16];
     i16 a_tmp_Q12[16];

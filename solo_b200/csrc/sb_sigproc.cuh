@@ -23,7 +23,7 @@ SB_HD i64 inner_prod16_64(const i16* a, const i16* b, int len) {
 // The reference takes a different accumulation path when the input pointer is only 2-byte aligned
 // (SURVEY.md App. A Q21).  All its buffers are 4-byte aligned arrays, so the path is decided by the
 // parity of the element offset, which every call site passes as `odd_start`.
-SB_FN void sum_sqr_shift(i32* energy, i32* shift, const i16* x, int len, int odd_start) {
+SB_FN_BIG void sum_sqr_shift(i32* energy, i32* shift, const i16* x, int len, int odd_start) {
     i32 nrg; int i, shft = 0;
     if (odd_start) { nrg = (i32)x[0] * (i32)x[0]; i = 1; } else { nrg = 0; i = 0; }
     len--;
@@ -141,7 +141,7 @@ SB_FN void bwexpander_32(i32* ar, int d, i32 chirp_Q16) {
 }
 
 // ---- SKP_Silk_LPC_inv_pred_gain.c:42-153 --------------------------------------------------------------
-SB_FN int lpc_inv_pred_gain_qa(i32* invGain_Q30, i32 A_QA[2][16], int order) {
+SB_FN_BIG int lpc_inv_pred_gain_qa(i32* invGain_Q30, i32 A_QA[2][16], int order) {
     const i32 A_LIMIT = SB_FIXC(0.99975, 16);
     i32* Anew = A_QA[order & 1];
     *invGain_Q30 = 1 << 30;
@@ -312,7 +312,7 @@ SB_FN void insertion_sort_increasing(i32* a, i32* index, int L, int K) {
         }
     }
 }
-SB_FN void insertion_sort_decreasing_i16(i16* a, i32* index, int L, int K) {
+SB_FN_BIG void insertion_sort_decreasing_i16(i16* a, i32* index, int L, int K) {
     for (int i = 0; i < K; i++) index[i] = i;
     for (int i = 1; i < K; i++) {
         i32 value = a[i]; int j;
@@ -330,7 +330,7 @@ SB_FN void insertion_sort_decreasing_i16(i16* a, i32* index, int L, int K) {
 }
 
 // ---- SKP_Silk_burg_modified.c:49-228 (QA = 25) --------------------------------------------------------
-SB_FN void burg_modified(i32* res_nrg, i32* res_nrg_Q, i32* A_Q16, const i16* x, int subfr_length, int nb_subfr,
+SB_FN_BIG void burg_modified(i32* res_nrg, i32* res_nrg_Q, i32* A_Q16, const i16* x, int subfr_length, int nb_subfr,
                          i32 WhiteNoiseFrac_Q32, int D) {
     const int QA = 25, MAX_RSHIFTS = 32 - QA, MIN_RSHIFTS = -16, HEAD = 2;
     i32 C0, rshifts;
@@ -482,7 +482,7 @@ SB_FN void a2nlsf_init(const i32* a_Q16, i32* P, i32* Q, int dd) {
     a2nlsf_trans_poly(P, dd);
     a2nlsf_trans_poly(Q, dd);
 }
-SB_FN void a2nlsf(i32* NLSF, i32* a_Q16, int d) {
+SB_FN_BIG void a2nlsf(i32* NLSF, i32* a_Q16, int d) {
     const int BIN = 3, TABSZ = 128, MAX_ITER = 30;
     i32 P[9], Q[9];
     int dd = d >> 1;
@@ -554,7 +554,7 @@ SB_HD void nlsf2a_find_poly(i32* out, const i32* cLSF, int dd) {
         out[1] = subw(out[1], ftmp);
     }
 }
-SB_FN void nlsf2a(i16* a, const i32* NLSF, int d) {
+SB_FN_BIG void nlsf2a(i16* a, const i32* NLSF, int d) {
     i32 cos_LSF_Q20[16], P[9], Q[9], a_int32[16];
     for (int k = 0; k < d; k++) {
         i32 f_int = NLSF[k] >> 8;
@@ -605,7 +605,7 @@ SB_HD void interpolate(i32* xi, const i32* x0, const i32* x1, int ifact_Q2, int 
 }
 
 // ---- SKP_Silk_NLSF_stabilize.c:42-138 -----------------------------------------------------------------
-SB_FN void nlsf_stabilize(i32* NLSF_Q15, const i32* NDeltaMin_Q15, int L) {
+SB_FN_BIG void nlsf_stabilize(i32* NLSF_Q15, const i32* NDeltaMin_Q15, int L) {
     int loops;
     for (loops = 0; loops < 20; loops++) {
         i32 min_diff = NLSF_Q15[0] - NDeltaMin_Q15[0];
