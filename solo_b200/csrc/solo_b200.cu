@@ -26,6 +26,12 @@ using namespace sb;
 // kernels
 // ---------------------------------------------------------------------------------------------------
 #define SB_TPB 64
+#ifndef SB_ANA_TPB
+#define SB_ANA_TPB 64        // threads per block of the analysis kernel
+#endif
+#ifndef SB_DEC_TPB
+#define SB_DEC_TPB 64
+#endif
 #ifndef SB_ANALYSIS_LOCAL_STATE
 #define SB_ANALYSIS_LOCAL_STATE 1   // stage the per-stream state in local memory for the duration of a packet (thread-per-stream kernels)
 #endif
@@ -52,7 +58,7 @@ __global__ void __launch_bounds__(SB_TPB) sb_enc_init_kernel(EncState* states, i
 //   A  sb_enc_analysis_kernel : one thread per stream  -- QMF split, VAD .. gain processing of both frames, high-band analysis
 //   B  sb_enc_nsq_kernel      : one WARP per stream    -- MD delayed-decision noise-shaping quantiser, state in shared memory
 //   C  sb_enc_finish_kernel   : one thread per stream  -- range coding of both descriptions, high-band gains, payload assembly
-__global__ void __launch_bounds__(SB_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ pcm, int spp, int n) {
+__global__ void __launch_bounds__(SB_ANA_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ pcm, int spp, int n) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ NlsfFastTabs s_nlsf;
     nlsf_fast_tabs_fill(&s_nlsf, threadIdx.x, blockDim.x);
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(SB_TPB) sb_dec_init_kernel(DecState* states, i
     if (s < n) dec_state_init(&states[s], mdi, framesize_ms, joint_hb);
 }
 
-__global__ void __launch_bounds__(SB_TPB, SB_DECODE_MINB) sb_decode_kernel(DecState* states, i16* __restrict__ pcm, const u8* __restrict__ bits, int cap,
+__global__ void __launch_bounds__(SB_DEC_TPB, SB_DECODE_MINB) sb_decode_kernel(DecState* states, i16* __restrict__ pcm, const u8* __restrict__ bits, int cap,
                                                            const i16* __restrict__ nbytes, const i32* __restrict__ lostflag,
                                                            i32* __restrict__ ret, DecStale* stale, int spp, int n) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -343,7 +349,7 @@ static int enc_launch(solo_b200_enc_batch* b, int lo, int n, const i16* d_pcm, u
 #if SB_ANALYSIS_WARP
     { int e = sb_launch_enc_analysis_warp(states, scratch, pcm, b->spp, n, st); if (e) return fail("analysis launch", (cudaError_t)e); }
 #else
-    sb_enc_analysis_kernel<<<(n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(states, scratch, pcm, b->spp, n);
+    sb_enc_analysis_kernel<<<(n + SB_ANA_TPB - 1) / SB_ANA_TPB, SB_ANA_TPB, 0, st>>>(states, scratch, pcm, b->spp, n);
 #endif
     prof_end(st, &ev);
     prof_begin(st, 1, &ev);
@@ -448,7 +454,7 @@ static int dec_launch(solo_b200_dec_batch* b, int lo, int n, i16* d_pcm, const u
                       i32* d_ret, cudaStream_t st) {
     if (n <= 0) return 0;
     EvPair ev; prof_begin(st, 3, &ev);
-    sb_decode_kernel<<<(n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(b->d_states + lo, d_pcm + (size_t)lo * b->spp, d_bits + (size_t)lo * cap, cap,
+    sb_decode_kernel<<<(n + SB_DEC_TPB - 1) / SB_DEC_TPB, SB_DEC_TPB, 0, st>>>(b->d_states + lo, d_pcm + (size_t)lo * b->spp, d_bits + (size_t)lo * cap, cap,
                                                                   d_nbytes + 2 * (size_t)lo, d_lostflag + lo, d_ret ? d_ret + lo : nullptr, b->d_stale + lo, b->spp, n);
     prof_end(st, &ev);
     count_launch();
