@@ -58,6 +58,28 @@ SB_FN int enc_state_init(EncState* st, i32 targetRate_bps, i32 dtx_enable, i32 u
     return 0;
 }
 
+// One low-band / high-band output pair of the 64-tap QMF analysis (AGR_BWE_qmf.c:66-79): x = [63 history | N new]
+// samples (already >> 1), aa = the 64 coefficients.  Products are summed mod 2^32, so any order gives the same bits.
+SB_HD void qmf_output_pair(const i16* x, const i16* aa, int k, i16* lo, i16* hi) {
+    enum { M = 64 };
+    const int i = 2 * k;
+    const i16* x2 = x + M - 1;
+    i32 y1k = 0, y2k = 0;
+#pragma unroll 4
+    for (int j = 0; j < M / 2; j += 2) {
+        i32 a0 = aa[M - j - 1], a1 = aa[M - j - 2];
+        i32 s0 = (i16)(x[i + j] + x2[i - j]), d0 = (i16)(x[i + j] - x2[i - j]);
+        i32 s1 = (i16)(x[i + j + 1] + x2[i - j - 1]), d1 = (i16)(x[i + j + 1] - x2[i - j - 1]);
+        y1k = addw(y1k, a0 * s0);
+        y2k = subw(y2k, a0 * d0);
+        y1k = addw(y1k, a1 * s1);
+        y2k = addw(y2k, a1 * d1);
+    }
+    i32 v1 = addw(y1k, 16384) >> 15, v2 = addw(y2k, 16384) >> 15;
+    *lo = (i16)(v1 > 32767 ? 32767 : (v1 < -32767 ? -32767 : v1));
+    *hi = (i16)(v2 > 32767 ? 32767 : (v2 < -32767 ? -32767 : v2));
+}
+
 // ---- AGR_Sate_qmf_decomp (AGR_BWE_qmf.c:38-80), N = 640 or 320, M = 64, fixed point ------------------------------
 SB_FN void qmf_decomp(const i16* xx, i16* y1, i16* y2, i16* mem, int N) {
     enum { M = 64 };
@@ -78,22 +100,7 @@ SB_FN void qmf_decomp(const i16* xx, i16* y1, i16* y2, i16* mem, int N) {
 #endif
     for (int i = 0; i < N; i++) x[i + M - 1] = (i16)(xx[i] >> 1);
     for (int i = 0; i < M - 1; i++) mem[i] = x[N + M - 2 - i];   // == xx[N - i - 1] >> 1
-    const i16* x2 = x + M - 1;
-    for (int i = 0, k = 0; i < N; i += 2, k++) {
-        i32 y1k = 0, y2k = 0;
-        for (int j = 0; j < M / 2; j += 2) {
-            i32 a0 = aa[M - j - 1], a1 = aa[M - j - 2];
-            i32 s0 = (i16)(x[i + j] + x2[i - j]), d0 = (i16)(x[i + j] - x2[i - j]);
-            i32 s1 = (i16)(x[i + j + 1] + x2[i - j - 1]), d1 = (i16)(x[i + j + 1] - x2[i - j - 1]);
-            y1k = addw(y1k, a0 * s0);
-            y2k = subw(y2k, a0 * d0);
-            y1k = addw(y1k, a1 * s1);
-            y2k = addw(y2k, a1 * d1);
-        }
-        i32 v1 = addw(y1k, 16384) >> 15, v2 = addw(y2k, 16384) >> 15;
-        y1[k] = (i16)(v1 > 32767 ? 32767 : (v1 < -32767 ? -32767 : v1));
-        y2[k] = (i16)(v2 > 32767 ? 32767 : (v2 < -32767 ? -32767 : v2));
-    }
+    for (int k = 0; k < N / 2; k++) qmf_output_pair(x, aa, k, &y1[k], &y2[k]);
 }
 
 // ---- AGR_Sate_lsp_quant_highband (AGR_BWE_quant_highband.c:23-104) ----------------------------------------------
@@ -241,11 +248,24 @@ SB_FN void encode_frame_analysis(EncCore* st, EncAnalysisWork* W, Arena* A, cons
 }
 
 // stage A (cooperative).  st and W: shared memory in the warp-per-stream kernel; pcm and scr: global memory.
-SB_FN void enc_packet_analysis(EncCore* st, EncAnalysisWork* W, const i16* pcm, EncScratch* scr) {
+// bands: the packet already split into [low | high] by the QMF kernel (device pipeline), or null: split it here.
+SB_FN void enc_packet_analysis(EncCore* st, EncAnalysisWork* W, const i16* pcm, EncScratch* scr, const i16* bands = nullptr) {
     Arena A;
     arena_init(&A, W->arena_mem, SB_ANA_ARENA);
     const int nf = st->frames_per_packet;
-    SB_SERIAL(qmf_decomp(pcm, W->low, W->high, st->qmf_mem, nf * 2 * FRAME));
+    if (bands) {
+        const int half = nf * FRAME;
+#ifdef __CUDA_ARCH__
+        const int4* src = reinterpret_cast<const int4*>(bands);          // rows are 16-byte aligned (spp * 2 = 1280 or 640 bytes)
+        int4* dl = reinterpret_cast<int4*>(W->low);
+        int4* dh = reinterpret_cast<int4*>(W->high);
+        for (int i = 0; i < half / 8; i++) { dl[i] = src[i]; dh[i] = src[half / 8 + i]; }
+#else
+        for (int i = 0; i < half; i++) { W->low[i] = bands[i]; W->high[i] = bands[half + i]; }
+#endif
+    } else {
+        SB_SERIAL(qmf_decomp(pcm, W->low, W->high, st->qmf_mem, nf * 2 * FRAME));
+    }
     for (int f = 0; f < nf; f++) {
         encode_frame_analysis(st, W, &A, W->low + f * FRAME, f);
         // hand the frame over to stages B / C (32-bit words; EncCtrl and xfw are both 4-byte multiples)

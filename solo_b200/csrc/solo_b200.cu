@@ -38,6 +38,12 @@ using namespace sb;
 #ifndef SB_DECODE_LOCAL_STATE
 #define SB_DECODE_LOCAL_STATE 0
 #endif
+#ifndef SB_ANA_SMEM_TABS
+#define SB_ANA_SMEM_TABS 1    // NLSF codebooks of kernel A in shared memory (5.2 KB per block)
+#endif
+#ifndef SB_QMF_KERNEL
+#define SB_QMF_KERNEL 1       // band split as its own warp-per-stream kernel with a TMA-fetched PCM tile (0: inside kernel A)
+#endif
 #ifndef SB_ANALYSIS_WARP
 #define SB_ANALYSIS_WARP 0   // 1: stage A runs as the warp-per-stream kernel of sb_analysis.cu
 #endif
@@ -54,26 +60,94 @@ __global__ void __launch_bounds__(SB_TPB) sb_enc_init_kernel(EncState* states, i
     if (s < n) enc_state_init(&states[s], rate, dtx, mdi, framesize_ms, joint_hb);
 }
 
+// ---- stage A0: QMF band split, one warp per stream, PCM tile fetched by the TMA engine ----------------------------------
+// The split is the one part of the analysis without a recurrence: 320 (160) output pairs of a 64-tap symmetric FIR per
+// packet.  A block takes SB_QMF_SPB consecutive streams; their PCM rows are contiguous in HBM, so ONE bulk asynchronous copy
+// (cp.async.bulk -> UBLKCP, completion on an mbarrier) brings the whole tile into shared memory while the warps load their
+// filter memories; each lane then produces output pairs k = lane, lane + 32, ... (products summed mod 2^32: order-free).
+// Measured (65 536 streams, 2 chunks): +3.3 % end-to-end throughput, -0.4 % device-resident, versus the split inside kernel A;
+// larger blocks (8 streams) cost 2 % device-resident because they cannot start while kernel B holds the shared memory.
+#ifndef SB_QMF_SPB
+#define SB_QMF_SPB 1        // one-warp blocks of 2.8 KB: they fit in the shared memory the quantiser kernel leaves free on an SM
+#endif
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(SB_QMF_SPB * 32) sb_enc_qmf_kernel(EncState* states, const i16* __restrict__ pcm, i16* __restrict__ bands, int spp, int n) {
+    __shared__ __align__(16) i16 tile[SB_QMF_SPB][PACKET];
+    __shared__ __align__(16) i16 xs[SB_QMF_SPB][PACKET + 64];
+    __shared__ i16 coef[64];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s0 = blockIdx.x * SB_QMF_SPB;
+    const int rows = min(SB_QMF_SPB, n - s0);
+    const i16* src = pcm + (size_t)s0 * spp;
+    const unsigned bytes = (unsigned)(rows * spp * 2);
+    const bool bulk = (((size_t)src) & 15) == 0;            // 16-byte aligned source: use the copy engine
+    const unsigned mb = smem_u32(&mbar);
+    if (threadIdx.x == 0 && bulk) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (threadIdx.x < 64) coef[threadIdx.x] = SB_T(qmf_fix)[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0 && bulk) {
+        // rows of `spp` samples land back to back: tile is addressed as a flat [rows * spp] array below
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&tile[0][0])), "l"(src),
+                     "r"(bytes), "r"(mb)
+                     : "memory");
+    }
+    const int s = s0 + w;
+    const bool live = w < rows;
+    EncState* st = live ? &states[s] : nullptr;
+    i16* x = xs[w];
+    if (live) for (int i = lane; i < 63; i += 32) x[i] = st->qmf_mem[62 - i];      // x[i] = mem[M - i - 2]
+    const i16* flat = &tile[0][0];
+    if (bulk) {
+        asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(mb), "r"(0u)
+                     : "memory");
+    } else {
+        for (int i = threadIdx.x; i < rows * spp; i += blockDim.x) tile[0][i] = src[i];
+        __syncthreads();
+    }
+    if (!live) return;
+    for (int i = lane; i < spp; i += 32) x[63 + i] = (i16)(flat[w * spp + i] >> 1);
+    __syncwarp();
+    i16* out = bands + (size_t)s * spp;
+    const int half = spp >> 1;
+    for (int k = lane; k < half; k += 32) {
+        i16 lo, hi;
+        qmf_output_pair(x, coef, k, &lo, &hi);
+        out[k] = lo; out[half + k] = hi;
+    }
+    for (int i = lane; i < 63; i += 32) st->qmf_mem[i] = x[spp + 62 - i];          // mem[i] = x[N + M - 2 - i]
+}
+
 // Encoder = three kernels per packet wave (stream s, scratch slot s):
 //   A  sb_enc_analysis_kernel : one thread per stream  -- QMF split, VAD .. gain processing of both frames, high-band analysis
 //   B  sb_enc_nsq_kernel      : one WARP per stream    -- MD delayed-decision noise-shaping quantiser, state in shared memory
 //   C  sb_enc_finish_kernel   : one thread per stream  -- range coding of both descriptions, high-band gains, payload assembly
-__global__ void __launch_bounds__(SB_ANA_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ pcm, int spp, int n) {
+__global__ void __launch_bounds__(SB_ANA_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ pcm, const i16* __restrict__ bands, int spp, int n) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
+#if SB_ANA_SMEM_TABS
     __shared__ NlsfFastTabs s_nlsf;
     nlsf_fast_tabs_fill(&s_nlsf, threadIdx.x, blockDim.x);
     __syncthreads();
+#endif
     if (s >= n) return;
     EncAnalysisWork W;
+#if SB_ANA_SMEM_TABS
     W.nlsf_fast = &s_nlsf;
+#else
+    W.nlsf_fast = nullptr;
+#endif
     const i16* x = pcm + (size_t)s * spp;      // row of spp = 640 (40 ms) or 320 (20 ms) samples, read once, with 128-bit loads, by the QMF split
 #if SB_ANALYSIS_LOCAL_STATE
     // analysis state staged in local memory: same-offset words of the 32 streams of a warp share cache lines there
     EncCore st = static_cast<const EncCore&>(states[s]);
-    enc_packet_analysis(&st, &W, x, &scratch[s]);
+    enc_packet_analysis(&st, &W, x, &scratch[s], bands ? bands + (size_t)s * spp : nullptr);
     static_cast<EncCore&>(states[s]) = st;
 #else
-    enc_packet_analysis(&states[s], &W, x, &scratch[s]);
+    enc_packet_analysis(&states[s], &W, x, &scratch[s], bands ? bands + (size_t)s * spp : nullptr);
 #endif
 }
 
@@ -248,6 +322,7 @@ struct solo_b200_enc_batch {
     int hb_bytes;               // high-band bytes per packet: 4 per high-band frame
     EncState* d_states;
     EncScratch* d_scratch;
+    i16* d_bands;               // [n][spp]: low band | high band of the packet, written by the QMF kernel
     // staging for the *_host entry points
     i16* d_pcm; u8* d_bits; i16* d_nbytes; int bits_cap;
     cudaStream_t stream;
@@ -325,6 +400,7 @@ solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_e
     b->n = n_streams; b->device = device; b->spp = 16 * ctrl->framesize_ms; b->hb_bytes = hb_bytes_of(ctrl->framesize_ms, ctrl->joint_enable);
     if (cudaMalloc(&b->d_states, sizeof(EncState) * (size_t)n_streams) != cudaSuccess ||
         cudaMalloc(&b->d_scratch, sizeof(EncScratch) * (size_t)n_streams) != cudaSuccess ||
+        cudaMalloc(&b->d_bands, sizeof(i16) * (size_t)b->spp * (size_t)n_streams) != cudaSuccess ||
         cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || pipe_create(&b->pipe) != 0 ||
         cudaFuncSetAttribute(sb_enc_nsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SB_NSQ_SPB * sizeof(NsqSmem))) != cudaSuccess) {
         fail("enc_batch_create", cudaGetLastError());
@@ -349,7 +425,14 @@ static int enc_launch(solo_b200_enc_batch* b, int lo, int n, const i16* d_pcm, u
 #if SB_ANALYSIS_WARP
     { int e = sb_launch_enc_analysis_warp(states, scratch, pcm, b->spp, n, st); if (e) return fail("analysis launch", (cudaError_t)e); }
 #else
-    sb_enc_analysis_kernel<<<(n + SB_ANA_TPB - 1) / SB_ANA_TPB, SB_ANA_TPB, 0, st>>>(states, scratch, pcm, b->spp, n);
+#if SB_QMF_KERNEL
+    i16* bands = b->d_bands + (size_t)lo * b->spp;
+    sb_enc_qmf_kernel<<<(n + SB_QMF_SPB - 1) / SB_QMF_SPB, SB_QMF_SPB * 32, 0, st>>>(states, pcm, bands, b->spp, n);
+    count_launch();
+#else
+    const i16* bands = nullptr;
+#endif
+    sb_enc_analysis_kernel<<<(n + SB_ANA_TPB - 1) / SB_ANA_TPB, SB_ANA_TPB, 0, st>>>(states, scratch, pcm, bands, b->spp, n);
 #endif
     prof_end(st, &ev);
     prof_begin(st, 1, &ev);
@@ -425,7 +508,7 @@ void solo_b200_enc_batch_destroy(solo_b200_enc_batch* b) {
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     pipe_destroy(&b->pipe);
-    cudaFree(b->d_states); cudaFree(b->d_scratch); cudaFree(b->d_pcm); cudaFree(b->d_bits); cudaFree(b->d_nbytes);
+    cudaFree(b->d_states); cudaFree(b->d_scratch); cudaFree(b->d_bands); cudaFree(b->d_pcm); cudaFree(b->d_bits); cudaFree(b->d_nbytes);
     cudaStreamDestroy(b->stream);
     delete b;
 }
