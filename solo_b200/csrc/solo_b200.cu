@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(SB_QMF_SPB * 32) sb_enc_qmf_kernel(EncState* s
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (threadIdx.x < 64) coef[threadIdx.x] = SB_T(qmf_fix)[threadIdx.x];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) coef[i] = SB_T(qmf_fix)[i];
     __syncthreads();
     if (threadIdx.x == 0 && bulk) {
         // rows of `spp` samples land back to back: tile is addressed as a flat [rows * spp] array below
