@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(SB_TPB) sb_enc_init_kernel(EncState* states, i
 // packet.  A block takes SB_QMF_SPB consecutive streams; their PCM rows are contiguous in HBM, so ONE bulk asynchronous copy
 // (cp.async.bulk -> UBLKCP, completion on an mbarrier) brings the whole tile into shared memory while the warps load their
 // filter memories; each lane then produces output pairs k = lane, lane + 32, ... (products summed mod 2^32: order-free).
-// Measured (65 536 streams, 2 chunks): +3.3 % end-to-end throughput, -0.4 % device-resident, versus the split inside kernel A;
+// Measured (65 536 streams, 2 chunks): +3.3 % end-to-end throughput, device-resident unchanged, versus the split inside kernel A;
 // larger blocks (8 streams) cost 2 % device-resident because they cannot start while kernel B holds the shared memory.
 #ifndef SB_QMF_SPB
 #define SB_QMF_SPB 1        // one-warp blocks of 2.8 KB: they fit in the shared memory the quantiser kernel leaves free on an SM
