@@ -185,8 +185,8 @@ SB_FN void hb_pack_frame(i32 lsp_idx, const i32* nrg0, const i16* r16, u8* out4,
     out4[0] = (u8)(w >> 24); out4[1] = (u8)(w >> 16); out4[2] = (u8)(w >> 8); out4[3] = (u8)w;
 }
 
-// ---- per-packet hand-over between the three encoder stages (device: global scratch, one slot per stream) ----------
-//   stage A (analysis, one thread per stream)   : QMF split, VAD .. process_gains for both frames, high-band analysis
+// ---- per-packet hand-over between the encoder stages (device: global scratch, one slot per stream) -------------------
+//   stage A (analysis, one thread per stream)   : [QMF split, its own kernel on the device,] VAD .. process_gains per frame, high-band analysis
 //   stage B (MD noise-shaping quantiser)         : consumes c[f], xfw[f]; produces q_md[f], r16[f], c[f].Seed
 //   stage C (entropy coding + packing)           : range-codes both descriptions, high-band gains, payload assembly
 struct EncScratch {

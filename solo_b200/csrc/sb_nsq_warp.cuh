@@ -1,14 +1,17 @@
-// solo_b200 -- MD delayed-decision noise-shaping quantiser, one stream per warp (sm_100a device code).
+// solo_b200 -- MD delayed-decision noise-shaping quantiser, one stream per lane group of a warp (sm_100a device code).
 //
 // Same arithmetic as the scalar model in sb_nsq.cuh (which cites the reference line by line); this file only changes
 // WHERE things live and WHO computes them:
-//   * lane L < 12 owns one (quantiser qz = L >> 2, delayed-decision state s = L & 3) recurrence: its 16-stage warped
-//     all-pass chain, its 10 newest short-term-prediction taps and its scalars sit in registers;
-//   * the decision history (5 x 32 x 4 words per quantiser) and the long-term buffers sit in shared memory; a survivor
-//     replacing another state is 40 warp shuffles (registers + 64-bit path word) instead of a 1.5 KB memcpy;
-//   * the joint rate-distortion argmin / worst-best replacement run on shuffles, the flush after a rewhitening reset and
-//     all per-sub-frame rescaling loops are spread over the 32 lanes.
-// Lanes 12..31 execute the same instruction stream on clamped indices and never store.
+//   * a warp serves two streams, one per 16-lane group (SB_NSQ_GW); lane L < 12 of a group owns one (quantiser qz = L >> 2,
+//     delayed-decision state s = L & 3) recurrence: its 16-stage warped all-pass chain, its 10 newest short-term-prediction
+//     taps and its scalars sit in registers;
+//   * the decision history (4 x 32 x 4 words per quantiser + excitation + pulses) and the three long buffers (160-entry
+//     rings) sit in shared memory, 12.2 KB per stream; a survivor replacing another state is ~40 warp shuffles (registers +
+//     a 64-bit path word) instead of the reference's 1.5 KB memcpy;
+//   * the joint rate-distortion argmin, worst/best replacement and winner emission run on shuffles; the sample loop is
+//     executed by both groups in lock step with full-warp collectives and warp-uniform trip counts, everything around it
+//     (rewhitening, flushes, rescaling) names its own group so the two streams may diverge there.
+// Lanes 12..15 of a group execute the same instruction stream on clamped indices and never store.
 #pragma once
 #ifdef __CUDACC__
 #include "sb_nsq.cuh"

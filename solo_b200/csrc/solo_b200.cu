@@ -1,7 +1,8 @@
 // solo_b200 -- sm_100a kernels and the C ABI of libsolo_b200.so.
 //
-// One packet wave = four kernels:
-//   A  sb_enc_analysis_kernel  thread per stream   QMF split, VAD .. gain processing of both 20 ms frames, high-band analysis
+// One packet wave = five kernels:
+//   A0 sb_enc_qmf_kernel       warp per stream     QMF band split, PCM row fetched by TMA (cp.async.bulk)
+//   A  sb_enc_analysis_kernel  thread per stream   VAD .. gain processing of both 20 ms frames, high-band analysis
 //   B  sb_enc_nsq_kernel       two streams / warp  MD delayed-decision noise-shaping quantiser, history in shared memory
 //   C  sb_enc_finish_kernel    thread per stream   range coding of both descriptions, high-band gains, payload assembly
 //   D  sb_decode_kernel        thread per stream   the whole decoder incl. concealment, high band and QMF synthesis
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(SB_QMF_SPB * 32) sb_enc_qmf_kernel(EncState* s
     for (int i = lane; i < 63; i += 32) st->qmf_mem[i] = x[spp + 62 - i];          // mem[i] = x[N + M - 2 - i]
 }
 
-// Encoder = three kernels per packet wave (stream s, scratch slot s):
+// Encoder after the band split = three kernels per packet wave (stream s, scratch slot s):
 //   A  sb_enc_analysis_kernel : one thread per stream  -- QMF split, VAD .. gain processing of both frames, high-band analysis
 //   B  sb_enc_nsq_kernel      : one WARP per stream    -- MD delayed-decision noise-shaping quantiser, state in shared memory
 //   C  sb_enc_finish_kernel   : one thread per stream  -- range coding of both descriptions, high-band gains, payload assembly
@@ -414,7 +415,7 @@ solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_e
     return b;
 }
 
-// the three encoder kernels for streams [lo, lo + n) on one CUDA stream
+// the encoder kernels (A0, A, B, C) for streams [lo, lo + n) on one CUDA stream
 static int enc_launch(solo_b200_enc_batch* b, int lo, int n, const i16* d_pcm, u8* d_bits, int cap, i16* d_nbytes, cudaStream_t st) {
     if (n <= 0) return 0;
     EncState* states = b->d_states + lo;
@@ -487,7 +488,7 @@ int solo_b200_enc_batch_encode_host(solo_b200_enc_batch* b, const int16_t* pcm, 
     if (r) return r;
     const int C = pipe_chunks(b->n);
     const int S = C < SB_PIPE_STREAMS ? C : SB_PIPE_STREAMS;
-    for (int c = 0; c < C; c++) {   // per chunk: H2D, three kernels, D2H -- chunks alternate over the internal streams
+    for (int c = 0; c < C; c++) {   // per chunk: H2D, encoder kernels, D2H -- chunks alternate over the internal streams
         int lo, hi;
         chunk_bounds(b->n, C, c, &lo, &hi);
         if (hi <= lo) continue;
