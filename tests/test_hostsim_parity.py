@@ -249,3 +249,17 @@ def test_long_run_with_level_changes_dtx_and_loss_bursts(sim, ref):
             assert r0 == r1 == 0 and np.abs(y0.astype(np.int32) - y1.astype(np.int32)).max() <= PCM_TOL, (rate, p, f)
         for o in (e0, e1, d0, d1):
             o.close()
+
+
+def test_cooperative_form_under_32_thread_emulation(sim):
+    """The analysis stage in its cooperative form (sb_par.cuh: SB_PARFOR / SB_SERIAL / barriers), executed by 32 OS threads
+    per stream, still reproduces the golden bitstream -- the CPU-side check of the warp-per-stream kernel's scaffolding
+    (sb_analysis.cu; every routine that has not been made cooperative yet runs on lane 0 behind a barrier)."""
+    g = load_golden()
+    clip = load_clip()
+    e = sim.SimEncoder(rate=13600, emu=True)
+    assert e.L.hs_is_emu() == 1
+    for p in range(16):
+        b, nb, n = e.encode(clip[p * 640:(p + 1) * 640])
+        assert nb == tuple(g["fix_nbytes"][p]) and b[:n] == bytes(g["fix_bits"][p, :n]), p
+    e.close()
