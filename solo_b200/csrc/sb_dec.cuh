@@ -741,6 +741,8 @@ SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, 
     i32 hb_off = dec_split_lengths(nb, lostflag, hb_bytes);
     int n0 = nb[0], n1 = nb[1];
     if (n0 < 0 || n1 < 0 || n0 + n1 > cap || hb_off > cap) return -1;
+    // the high-band bytes are read from the row (lostflag 3 / 4): a declared total beyond the row is rejected, never followed
+    if ((lostflag == 3 || lostflag == 4) && (hb_off < 0 || hb_off + hb_bytes > cap)) return -1;
     RangeDec rc[2];
     for (int k = 0; k < 2; k++) {   // fully defined even for a description this packet does not carry
         rc[k].base_Q32 = 0; rc[k].range_Q16 = 0; rc[k].bufferIx = 0; rc[k].error = 0; rc[k].bufLen = 0; rc[k].buf = W->pay[k];

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(SB_DEC_TPB, SB_DECODE_MINB) sb_decode_kernel(D
     if (s >= n) return;
     DecPacketWork W;
     i16 nb[2] = {nbytes[2 * s], nbytes[2 * s + 1]};
-    i16 out[PACKET];
+    __align__(16) i16 out[PACKET];   // moved to the PCM row (cudaMalloc / 16-byte aligned, see solo_b200.h) with 128-bit stores
 #if SB_DECODE_LOCAL_STATE
     DecState st = states[s];
     i32 r = dec_packet(&st, &W, out, bits + (size_t)s * cap, cap, nb, lostflag[s], &stale[s]);
@@ -236,7 +236,10 @@ __global__ void __launch_bounds__(256) sb_apply_loss_kernel(const u8* __restrict
     int off = 0, len = n0, o0 = n0, o1 = n1;
     if (f == 2) { len = n0 - n1; o0 = len; o1 = 0; }
     else if (f == 3) { off = n0 - n1; len = n1; o0 = n1; o1 = 0; }
+    // wire-supplied lengths: anything outside 0 <= n1 <= n0, off + len <= cap yields an empty row (the decoder rejects it)
+    if (n0 < 0 || n1 < 0 || n1 > n0 || off < 0 || off > cap) { off = 0; len = 0; o0 = 0; o1 = 0; }
     if (len < 0) len = 0;
+    if (len > cap) len = cap;
     if (len > cap - off) len = cap - off;
     const u8* src = bits_in + (size_t)row * cap + off;
     u8* dst = bits_out + (size_t)row * cap;
@@ -306,10 +309,13 @@ static int pipe_create(Pipe* p) {
     p->ok = true;
     return 0;
 }
-static void pipe_destroy(Pipe* p) {
-    if (!p->ok) return;
-    for (int i = 0; i < SB_PIPE_STREAMS; i++) { cudaStreamSynchronize(p->st[i]); cudaStreamDestroy(p->st[i]); cudaEventDestroy(p->join[i]); }
-    cudaEventDestroy(p->fork);
+static void pipe_destroy(Pipe* p) {   // also after a partial pipe_create: members are zero until created
+    for (int i = 0; i < SB_PIPE_STREAMS; i++) {
+        if (p->st[i]) { cudaStreamSynchronize(p->st[i]); cudaStreamDestroy(p->st[i]); p->st[i] = nullptr; }
+        if (p->join[i]) { cudaEventDestroy(p->join[i]); p->join[i] = nullptr; }
+    }
+    if (p->fork) { cudaEventDestroy(p->fork); p->fork = nullptr; }
+    p->ok = false;
 }
 // chunk c of C over n streams, boundaries on multiples of 64 streams (block size of the thread-per-stream kernels)
 static void chunk_bounds(int n, int C, int c, int* lo, int* hi) {
@@ -408,13 +414,13 @@ solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_e
         cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || pipe_create(&b->pipe) != 0 ||
         cudaFuncSetAttribute(sb_enc_nsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SB_NSQ_SPB * sizeof(NsqSmem))) != cudaSuccess) {
         fail("enc_batch_create", cudaGetLastError());
-        delete b; return nullptr;
+        solo_b200_enc_batch_destroy(b); return nullptr;
     }
     int rate = ctrl->targetRate_bps <= 0 ? 15600 : ctrl->targetRate_bps;
     sb_enc_init_kernel<<<(n_streams + SB_TPB - 1) / SB_TPB, SB_TPB, 0, b->stream>>>(b->d_states, n_streams, rate, ctrl->dtx_enable, ctrl->useMDIndex, ctrl->framesize_ms, ctrl->joint_enable ? 1 : 0);
     count_launch();
     cudaError_t e = cudaStreamSynchronize(b->stream);
-    if (e != cudaSuccess) { fail("enc init kernel", e); cudaFree(b->d_states); delete b; return nullptr; }
+    if (e != cudaSuccess) { fail("enc init kernel", e); solo_b200_enc_batch_destroy(b); return nullptr; }
     return b;
 }
 
@@ -452,6 +458,7 @@ static int enc_launch(solo_b200_enc_batch* b, int lo, int n, const i16* d_pcm, u
 
 int solo_b200_enc_batch_encode_device(solo_b200_enc_batch* b, const int16_t* d_pcm, uint8_t* d_bits, int cap, int16_t* d_nbytes, void* cuda_stream) {
     if (!b || !d_pcm || !d_bits || !d_nbytes || cap < 16) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
+    CK(cudaSetDevice(b->device));
     cudaStream_t user = (cudaStream_t)cuda_stream;
     const int C = pipe_chunks(b->n);
     if (C == 1) return enc_launch(b, 0, b->n, d_pcm, d_bits, cap, d_nbytes, user);
@@ -510,7 +517,7 @@ int solo_b200_enc_batch_encode_host(solo_b200_enc_batch* b, const int16_t* pcm, 
 void solo_b200_enc_batch_destroy(solo_b200_enc_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
-    cudaStreamSynchronize(b->stream);
+    if (b->stream) cudaStreamSynchronize(b->stream);
     pipe_destroy(&b->pipe);
     cudaFree(b->d_states); cudaFree(b->d_scratch); cudaFree(b->d_bands); cudaFree(b->d_pcm); cudaFree(b->d_bits); cudaFree(b->d_nbytes);
     cudaStreamDestroy(b->stream);
@@ -528,12 +535,12 @@ solo_b200_dec_batch* solo_b200_dec_batch_create(int n_streams, const USER_Ctrl_d
         cudaMalloc(&b->d_stale, sizeof(DecStale) * (size_t)n_streams) != cudaSuccess ||
         cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || pipe_create(&b->pipe) != 0) {
         fail("dec_batch_create", cudaGetLastError());
-        delete b; return nullptr;
+        solo_b200_dec_batch_destroy(b); return nullptr;
     }
     sb_dec_init_kernel<<<(n_streams + SB_TPB - 1) / SB_TPB, SB_TPB, 0, b->stream>>>(b->d_states, n_streams, ctrl->useMDIndex, ctrl->framesize_ms, ctrl->joint_enable ? 1 : 0);
     count_launch();
     cudaError_t e = cudaStreamSynchronize(b->stream);
-    if (e != cudaSuccess) { fail("dec init kernel", e); cudaFree(b->d_states); delete b; return nullptr; }
+    if (e != cudaSuccess) { fail("dec init kernel", e); solo_b200_dec_batch_destroy(b); return nullptr; }
     return b;
 }
 
@@ -552,6 +559,7 @@ static int dec_launch(solo_b200_dec_batch* b, int lo, int n, i16* d_pcm, const u
 int solo_b200_dec_batch_decode_device(solo_b200_dec_batch* b, int16_t* d_pcm, const uint8_t* d_bits, int cap, const int16_t* d_nbytes,
                                       const int32_t* d_lostflag, int32_t* d_ret, void* cuda_stream) {
     if (!b || !d_pcm || !d_bits || !d_nbytes || !d_lostflag || cap < 16) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
+    CK(cudaSetDevice(b->device));
     cudaStream_t user = (cudaStream_t)cuda_stream;
     const int C = pipe_chunks(b->n);
     if (C == 1) return dec_launch(b, 0, b->n, d_pcm, d_bits, cap, d_nbytes, d_lostflag, d_ret, user);
@@ -614,10 +622,10 @@ int solo_b200_dec_batch_decode_host(solo_b200_dec_batch* b, int16_t* pcm, const 
 void solo_b200_dec_batch_destroy(solo_b200_dec_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
-    cudaStreamSynchronize(b->stream);
+    if (b->stream) cudaStreamSynchronize(b->stream);
     pipe_destroy(&b->pipe);
     cudaFree(b->d_states); cudaFree(b->d_stale); cudaFree(b->d_pcm); cudaFree(b->d_bits); cudaFree(b->d_nbytes); cudaFree(b->d_flags); cudaFree(b->d_ret);
-    cudaStreamDestroy(b->stream);
+    if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
 
@@ -625,7 +633,8 @@ void solo_b200_dec_batch_destroy(solo_b200_dec_batch* b) {
 static int state_copy(void* dev_base, size_t stride, int n, int idx, void* host, int to_host, int device, cudaStream_t st) {
     if (!dev_base || !host || idx < 0 || idx >= n) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
     CK(cudaSetDevice(device));
-    CK(cudaStreamSynchronize(st));
+    (void)st;
+    CK(cudaDeviceSynchronize());    // packet waves run on the internal pipeline streams and on caller streams: wait for all of them
     char* p = (char*)dev_base + stride * (size_t)idx;
     if (to_host) CK(cudaMemcpy(host, p, stride, cudaMemcpyDeviceToHost));
     else CK(cudaMemcpy(p, host, stride, cudaMemcpyHostToDevice));
@@ -653,7 +662,7 @@ int solo_b200_split_packet(const uint8_t* bits, const int16_t* nbytes, const uin
     if (!bits || !nbytes || !p1 || !n1 || !p2 || !n2) return -1;
     const int t = nbytes[0], m2 = nbytes[1];
     if (t <= 0) { *p1 = *p2 = bits; *n1 = *n2 = 0; return 0; }    // DTX: nothing to send (enc_API.c:260-265)
-    if (m2 < 8 || m2 > t) return -1;
+    if (m2 < 4 || m2 > t) return -1;   // description 2 carries the high-band bytes: 8 (40 ms packets) or 4 (20 ms, joint mode 1)
     *p1 = bits; *n1 = t - m2;          // description 1: low band only
     *p2 = bits + (t - m2); *n2 = m2;   // description 2: low band + the 8 high-band bytes
     return 0;

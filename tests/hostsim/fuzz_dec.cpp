@@ -52,11 +52,13 @@ int main(int argc, char** argv) {
             if (kind == 3) { n0 = 1 + rnd() % 1024; n1 = rnd() % (n0 + 1); }                                                  // lying lengths
             if (kind == 4) { n0 = 1 + rnd() % 12; n1 = rnd() % 16; }                                                         // tiny / inconsistent
             if (kind == 5) flag = (int)(rnd() % 9) - 2;                                                                       // invalid flags
+            int capx = 1024;
+            if (kind == 6) { capx = 64 + rnd() % 64; n0 = capx + 1 + rnd() % 8; n1 = rnd() % (n0 + 1); }                      // declared total just beyond a short row
             short nbb[2] = {(short)n0, (short)n1};
             if (flag == 2 && kind < 3) { nbb[0] = (short)(n0 - n1); nbb[1] = 0; }
             if (flag == 3 && kind < 3) { for (int i = 0; i < n1; i++) row[i] = row[n0 - n1 + i]; nbb[0] = (short)n1; nbb[1] = 0; }
-            std::vector<unsigned char> arg(row.begin(), row.begin() + 1024);
-            int r = sb::dec_packet(dst, dw, out, arg.data(), 1024, nbb, flag, (rnd() & 1) ? stale : nullptr);
+            std::vector<unsigned char> arg(row.begin(), row.begin() + capx);
+            int r = sb::dec_packet(dst, dw, out, arg.data(), capx, nbb, flag, (rnd() & 1) ? stale : nullptr);
             (r < 0 ? errs : oks)++;
         }
     }
