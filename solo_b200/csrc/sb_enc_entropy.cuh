@@ -108,7 +108,7 @@ SB_FN void encode_pulses(RangeEnc* rc, int sigtype, int QuantOffsetType, const i
 }
 
 // SKP_Silk_encode_parameters (encode_parameters.c:33-182) for description `md` (0 or 1), 8 kHz.
-SB_FN void encode_parameters(RangeEnc* rc, EncCore* st, const EncCtrl* c, int md, int frame_in_packet, int vadFlag, const i8* q) {
+SB_FN void encode_parameters(RangeEnc* rc, EncSilk* st, const EncCtrl* c, int md, int frame_in_packet, int vadFlag, const i8* q) {
     if (frame_in_packet == 0) {
         if (st->useMDIndex == 1) rc_encode(rc, md, SB_T(md_index_cdf));
         int i;

@@ -110,7 +110,7 @@ SB_FN void vad_get_sa_q8(VadState* v, i32* pSA_Q8, i32* pQuality_Q15, i32* pTilt
 }
 
 // ---- SKP_Silk_HP_variable_cutoff_FIX.c:37-118 ---------------------------------------------------------
-SB_FN void hp_variable_cutoff(EncCore* st, EncCtrl* c, i16* out, const i16* in) {
+SB_FN void hp_variable_cutoff(EncSilk* st, EncCtrl* c, i16* out, const i16* in) {
     if (st->prev_sigtype == 0) {
         i32 pitch_freq_Hz_Q16 = shl(8 * 1000, 16) / st->prevLag;
         i32 pitch_freq_log_Q7 = lin2log(pitch_freq_Hz_Q16) - (16 << 7);
@@ -299,7 +299,7 @@ SB_FN int pitch_analysis_core(const i16* signal, i32* pitch_out, i32* lagIndex, 
 
 // ---- SKP_Silk_find_pitch_lags_FIX.c:32-125 -----------------------------------------------------------
 // x points at x_buf + FRAME (start of the frame to encode); res receives 336 samples of LPC residual.
-SB_FN void find_pitch_lags(EncCore* st, EncCtrl* c, i16* res, const i16* x) {
+SB_FN void find_pitch_lags(EncSilk* st, EncCtrl* c, i16* res, const i16* x) {
     enum { BUF_LEN = LA_PITCH + 2 * FRAME, ORD = 10 };
     i16 Wsig[PITCH_LPC_WIN];
     i32 auto_corr[ORD + 1];

@@ -320,7 +320,7 @@ SB_FN void quant_ltp_gains(i16* B_Q14, i32* cbk_index, i32* periodicity_index, c
 }
 
 // ---- SKP_Silk_LTP_scale_ctrl_FIX.c:39-81 (PacketLoss_perc == 0) ---------------------------------------------------
-SB_FN void ltp_scale_ctrl(EncCore* st, EncCtrl* c, int frame_in_packet) {
+SB_FN void ltp_scale_ctrl(EncSilk* st, EncCtrl* c, int frame_in_packet) {
     st->HPLTPredCodGain_Q7 = imax(c->LTPredCodGain_Q7 - st->prevLTPredCodGain_Q7, 0) + rshift_round(st->HPLTPredCodGain_Q7, 1);
     st->prevLTPredCodGain_Q7 = c->LTPredCodGain_Q7;
     i32 g_out_Q5 = rshift_round((c->LTPredCodGain_Q7 >> 1) + (st->HPLTPredCodGain_Q7 >> 1), 3);
@@ -553,7 +553,7 @@ SB_FN void nlsf_fast_tabs_fill(NlsfFastTabs* T, int tid, int nthreads) {
     for (int i = tid; i < 720; i += nthreads) T->cb1[i] = SB_T(nlsf_cb1_q15)[i];
     for (int i = tid; i < 72; i += nthreads) T->rates1[i] = SB_T(nlsf_cb1_rates_q5)[i];
 }
-SB_FN void process_nlsfs(EncCore* st, EncCtrl* c, i32* pNLSF_Q15, const NlsfFastTabs* fast = nullptr) {
+SB_FN void process_nlsfs(EncSilk* st, EncCtrl* c, i32* pNLSF_Q15, const NlsfFastTabs* fast = nullptr) {
     i32 pNLSFW_Q6[LPC_ORDER], pNLSF0_temp_Q15[LPC_ORDER], pNLSFW0_temp_Q6[LPC_ORDER];
     i32 NLSF_mu_Q15, NLSF_mu_fluc_red_Q16;
     if (c->sigtype == 0) {
@@ -615,7 +615,7 @@ SB_FN void residual_energy(i32* nrgs, i32* nrgsQ, const i16* x, const i16 a_Q12[
 }
 
 // ---- SKP_Silk_find_pred_coefs_FIX.c:31-131 -----------------------------------------------------------------
-SB_FN void find_pred_coefs(EncCore* st, EncCtrl* c, const i16* res_pitch, int frame_in_packet, const NlsfFastTabs* fast = nullptr) {
+SB_FN void find_pred_coefs(EncSilk* st, EncCtrl* c, const i16* res_pitch, int frame_in_packet, const NlsfFastTabs* fast = nullptr) {
     i32 WLTP[NB_SUBFR * LTP_ORDER * LTP_ORDER];
     i32 invGains_Q16[NB_SUBFR], local_gains[NB_SUBFR], Wght_Q15[NB_SUBFR], LTP_corrs_rshift[NB_SUBFR];
     i32 NLSF_Q15[LPC_ORDER];
@@ -686,7 +686,7 @@ SB_FN void gains_quant(i32* ind, i32* gain_Q16, i32* prev_ind, int conditional, 
 }
 
 // ---- SKP_Silk_process_gains_FIX.c:32-150 -------------------------------------------------------------------
-SB_FN void process_gains(EncCore* st, EncCtrl* c, int frame_in_packet) {
+SB_FN void process_gains(EncSilk* st, EncCtrl* c, int frame_in_packet) {
     if (c->sigtype == 0) {
         i32 s_Q16 = -sigm_q15(rshift_round(c->LTPredCodGain_Q7 - SB_FIXC(12.0, 7), 4));
         for (int k = 0; k < NB_SUBFR; k++) c->Gains_Q16[k] = smlawb(c->Gains_Q16[k], c->Gains_Q16[k], s_Q16);

@@ -106,7 +106,7 @@ SB_FN void limit_warped_coefs(i32* syn_Q24, i32* ana_Q24, i32 lambda_Q16, i32 li
 
 // ---- SKP_Silk_noise_shape_analysis_FIX.c:137-531 ---------------------------------------------------------
 // pitch_res points at res_pitch + FRAME, x at x_buf + FRAME.
-SB_FN void noise_shape_analysis(EncCore* st, EncCtrl* c, const i16* pitch_res, const i16* x) {
+SB_FN void noise_shape_analysis(EncSilk* st, EncCtrl* c, const i16* pitch_res, const i16* x) {
     i32 auto_corr[SHAPE_ORDER + 1], refl_coef_Q16[SHAPE_ORDER], AR1_Q24[SHAPE_ORDER], AR2_Q24[SHAPE_ORDER];
     i16 x_windowed[SHAPE_WIN];
     i32 scale = 0, nrg;
@@ -287,7 +287,7 @@ SB_FN void warped_lpc_analysis_filter(i32* state, i16* res, const i16* coef_Q13,
 }
 
 // ---- SKP_Silk_prefilter_FIX.c:85-224 -------------------------------------------------------------------
-SB_FN void prefilter(EncCore* st, const EncCtrl* c, i16* xw, const i16* x) {
+SB_FN void prefilter(EncSilk* st, const EncCtrl* c, i16* xw, const i16* x) {
     i32 x_filt_Q12[SUBFR];
     i16 st_res[SUBFR];
     const i16* px = x;

@@ -29,7 +29,7 @@
 #define SB_COOP_ACTIVE 1
 #define SB_NLANES 32
 namespace sb { namespace emu {
-extern thread_local int lane;
+extern int lane;
 void barrier();
 long long* scratch();   // 32 x 8-byte slots shared by the lanes of the current stream
 } }
@@ -76,6 +76,43 @@ __device__ __forceinline__ i32 wmin(i32 v) {
     return v;
 }
 __device__ __forceinline__ i32 wbcast(i32 v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+// general exchanges: value of lane `src` (per-lane source), of the lane d below / above, of lane ^ m; ballot
+__device__ __forceinline__ i32 wshfl(i32 v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ i32 wshfl_up(i32 v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }      // lanes < d keep their own value
+__device__ __forceinline__ i32 wshfl_down(i32 v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }  // lanes >= 32 - d keep their own value
+__device__ __forceinline__ i32 wshfl_xor(i32 v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ i64 wshfl64(i64 v, int src) {
+    u32 lo = __shfl_sync(0xffffffffu, (u32)v, src), hi = __shfl_sync(0xffffffffu, (u32)((u64)v >> 32), src);
+    return (i64)(((u64)hi << 32) | lo);
+}
+__device__ __forceinline__ u32 wballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+// sums / extrema inside aligned groups of G lanes (G = 2, 4, 8, 16)
+template <int G> __device__ __forceinline__ i32 gsum(i32 v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = (i32)((u32)v + (u32)__shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int G> __device__ __forceinline__ i64 gsum64(i64 v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        u32 lo = __shfl_xor_sync(0xffffffffu, (u32)v, o), hi = __shfl_xor_sync(0xffffffffu, (u32)((u64)v >> 32), o);
+        v = (i64)((u64)v + (((u64)hi << 32) | lo));
+    }
+    return v;
+}
+template <int G> __device__ __forceinline__ i32 gmax(i32 v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) { i32 t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    return v;
+}
+// minimum and, among equals, the smallest index, inside aligned groups of G lanes
+template <int G> __device__ __forceinline__ void gargmin(i32& v, i32& idx) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        i32 tv = __shfl_xor_sync(0xffffffffu, v, o), ti = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (tv < v || (tv == v && ti < idx)) { v = tv; idx = ti; }
+    }
+}
 // minimum value and, among equal values, the smallest index (what a first-minimum-wins scan returns)
 __device__ __forceinline__ void wargmin(i32& v, i32& idx) {
 #pragma unroll
@@ -113,6 +150,57 @@ inline i32 wbcast(i32 v, int src) {
     emu::barrier();
     return r;
 }
+inline i32 wshfl(i32 v, int src) {
+    long long* s = emu::scratch();
+    s[emu::lane] = v;
+    emu::barrier();
+    i32 r = (i32)s[src & 31];
+    emu::barrier();
+    return r;
+}
+inline i32 wshfl_up(i32 v, int d) { return wshfl(v, emu::lane >= d ? emu::lane - d : emu::lane); }
+inline i32 wshfl_down(i32 v, int d) { return wshfl(v, emu::lane + d < 32 ? emu::lane + d : emu::lane); }
+inline i32 wshfl_xor(i32 v, int m) { return wshfl(v, emu::lane ^ m); }
+inline i64 wshfl64(i64 v, int src) {
+    long long* s = emu::scratch();
+    s[emu::lane] = v;
+    emu::barrier();
+    i64 r = s[src & 31];
+    emu::barrier();
+    return r;
+}
+inline u32 wballot(bool p) {
+    long long* s = emu::scratch();
+    s[emu::lane] = p ? 1 : 0;
+    emu::barrier();
+    u32 r = 0;
+    for (int i = 0; i < 32; i++) r |= (u32)s[i] << i;
+    emu::barrier();
+    return r;
+}
+template <class T, int G, class F> inline T emu_greduce(T v, F f) {
+    long long* s = emu::scratch();
+    s[emu::lane] = (long long)v;
+    emu::barrier();
+    const int b = emu::lane & ~(G - 1);
+    T r = (T)s[b];
+    for (int i = 1; i < G; i++) r = f(r, (T)s[b + i]);
+    emu::barrier();
+    return r;
+}
+template <int G> inline i32 gsum(i32 v) { return emu_greduce<i32, G>(v, [](i32 a, i32 b) { return (i32)((u32)a + (u32)b); }); }
+template <int G> inline i64 gsum64(i64 v) { return emu_greduce<i64, G>(v, [](i64 a, i64 b) { return (i64)((u64)a + (u64)b); }); }
+template <int G> inline i32 gmax(i32 v) { return emu_greduce<i32, G>(v, [](i32 a, i32 b) { return a > b ? a : b; }); }
+template <int G> inline void gargmin(i32& v, i32& idx) {
+    long long* s = emu::scratch();
+    s[emu::lane] = ((long long)v << 32) | (u32)idx;
+    emu::barrier();
+    const int b = emu::lane & ~(G - 1);
+    i32 bv = (i32)(s[b] >> 32), bi = (i32)(u32)s[b];
+    for (int i = 1; i < G; i++) { i32 tv = (i32)(s[b + i] >> 32), ti = (i32)(u32)s[b + i]; if (tv < bv || (tv == bv && ti < bi)) { bv = tv; bi = ti; } }
+    emu::barrier();
+    v = bv; idx = bi;
+}
 inline void wargmin(i32& v, i32& idx) {
     long long* s = emu::scratch();
     s[emu::lane] = ((long long)v << 32) | (u32)idx;
@@ -139,6 +227,9 @@ SB_HD i32 wmin(i32 v) { return v; }
 SB_HD i32 wbcast(i32 v, int) { return v; }
 SB_HD void wargmin(i32&, i32&) {}
 SB_HD void wargmax(i32&, i32&) {}
+SB_HD i32 wshfl(i32 v, int) { return v; }
+SB_HD i64 wshfl64(i64 v, int) { return v; }
+SB_HD u32 wballot(bool p) { return p ? 1u : 0u; }
 #endif
 
 // ---- Arena: LIFO scratch shared by the lanes of a stream (shared memory on the device) ------------------------------

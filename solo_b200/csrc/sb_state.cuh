@@ -55,9 +55,10 @@ struct VadState {
     i16 HPstate;
 };
 
-// EncCore: everything the analysis (stage A) and entropy-coding (stage C) kernels keep between packets; the warp-per-stream
-// analysis kernel stages exactly this struct in shared memory.  EncState adds the three quantiser states of stage B.
-struct alignas(16) EncCore {
+// Persistent encoder state, split by consumer: EncSilk is what the warp-per-stream analysis kernel stages in shared memory
+// (and what the entropy-coding stage reads), EncBands belongs to the band-split and high-band kernels, NsqState x 3 to the
+// quantiser kernel.  EncCore = EncSilk + EncBands is the part the scalar model (tests/hostsim) passes around as one object.
+struct alignas(16) EncSilk {
     // --- per-stream constants fixed at Init (control_codec_FIX.c:319-389) ---
     i32 SNR_dB_Q7;
     i32 SNRPerMD_dB_Q7;
@@ -66,8 +67,6 @@ struct alignas(16) EncCore {
     i32 targetRate_bps;  // SILK core rate (user rate - 1600)
     i32 frames_per_packet;  // 2: 40 ms packets (the headline configuration), 1: 20 ms packets (AGR_BWE_SDK_API.c:78-81,106-110)
     i32 hb_frame;           // high-band frame length: 160 (20 ms), or 320 with joint_mode 1 (one 40 ms HB frame per packet, :63-66)
-    // --- QMF analysis memory (AGR_BWE_structs.h:34) ---
-    i16 qmf_mem[64];
     // --- SILK encoder ---
     VadState vad;
     i32 In_HP_State[2];
@@ -83,10 +82,14 @@ struct alignas(16) EncCore {
     i32 LTPCorr_Q15, avgGain_Q16, speech_activity_Q8, prevLTPredCodGain_Q7, HPLTPredCodGain_Q7;
     i32 prev_sigtype, prevLag, typeOffsetPrev_md[2], frameCounter, first_frame_after_reset;
     i32 noSpeechCounter, inDTX, vadFlag;
+};
+struct alignas(16) EncBands {
+    i16 qmf_mem[64];             // QMF analysis memory (AGR_BWE_structs.h:34)
     // --- high band (AGR_BWE_structs.h:14-19) ---
     i16 x_hb_buf[2 * 320 + 40];  // ring of 2 * hb_frame + 40; with hb_frame = 160 the LPC analysis reads [360,480), which stays zero (App. A Q26)
     i32 hb_first;
 };
+struct EncCore : EncSilk, EncBands {};
 struct EncState : EncCore {
     NsqState nsq[3];  // 0 = centre, 1 = description 1, 2 = description 2
 };

@@ -12,7 +12,7 @@ SRC = os.path.join(HERE, "hostsim.cpp")
 def build(force=False, emu=False):
     """emu=True: the cooperative (32 threads per stream) build of the analysis stage, libsb_hostsim_emu.so."""
     if emu:
-        return _build(os.path.join(OUT_DIR, "libsb_hostsim_emu.so"), ["-DSB_EMU", "-pthread"], force)
+        return _build(os.path.join(OUT_DIR, "libsb_hostsim_emu.so"), ["-DSB_EMU"], force)
     return _build(OUT, [], force)
 
 

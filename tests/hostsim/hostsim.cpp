@@ -4,22 +4,56 @@
 // With -DSB_EMU the analysis stage runs in its cooperative form on 32 OS threads per stream (sb_par.cuh), so that
 // races / missing barriers of the warp-per-stream kernel can be caught without a GPU.
 #ifdef SB_EMU
-#include <pthread.h>
-#include <thread>
-#include <vector>
+// 32 lanes of one stream as 32 fibers on one OS thread, run round-robin between barriers: lane 0 runs to its next barrier,
+// then lane 1, ... so a lane that reads what another lane has not written yet (missing SB_SYNC) or that takes a different
+// number of barriers (divergent collective) shows up deterministically.
+#include <ucontext.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <functional>
 #include "../../solo_b200/csrc/sb_common.cuh"
 namespace sb { namespace emu {
-thread_local int lane = 0;
-static pthread_barrier_t bar;
+int lane = 0;
+static ucontext_t ctx[32], main_ctx;
+static char* stacks[32];
 static long long scr[32];
-static bool inited = false;
-void barrier() { pthread_barrier_wait(&bar); }
+static long nbar[32];
+static std::function<void()> body;
+void barrier() {
+    const int me = lane;
+    nbar[me]++;
+    lane = (me + 1) & 31;
+    swapcontext(&ctx[me], &ctx[lane]);
+    lane = me;
+}
 long long* scratch() { return scr; }
-static void init() { if (!inited) { pthread_barrier_init(&bar, nullptr, 32); inited = true; } }
+static void entry() { body(); }
+// run f on 32 lanes (f reads sb::emu::lane)
+static void run32(const std::function<void()>& f) {
+    body = f;
+    for (int i = 0; i < 32; i++) {
+        if (!stacks[i]) stacks[i] = (char*)malloc(1 << 20);
+        getcontext(&ctx[i]);
+        ctx[i].uc_stack.ss_sp = stacks[i];
+        ctx[i].uc_stack.ss_size = 1 << 20;
+        ctx[i].uc_link = i < 31 ? &ctx[i + 1] : &main_ctx;
+        makecontext(&ctx[i], (void (*)())entry, 0);
+        nbar[i] = 0;
+    }
+    // a lane that returns falls through (uc_link) into the next lane's saved context; `lane` is restored inside barrier()
+    lane = 0;
+    swapcontext(&main_ctx, &ctx[0]);
+    for (int i = 1; i < 32; i++)
+        if (nbar[i] != nbar[0]) { fprintf(stderr, "emu: lane %d took %ld barriers, lane 0 took %ld (divergent collective)\n", i, nbar[i], nbar[0]); abort(); }
+    lane = 0;
+}
 } }
 #endif
 #include "../../solo_b200/csrc/sb_enc.cuh"
 #include "../../solo_b200/csrc/sb_dec.cuh"
+#ifdef SB_EMU
+#include "../../solo_b200/csrc/sb_coop.cuh"
+#endif
 #include <stdlib.h>
 
 extern "C" {
@@ -35,12 +69,14 @@ void* hs_enc_create(int rate, int dtx, int mdi) { return hs_enc_create2(rate, dt
 int hs_enc_encode(void* p, const short* pcm, unsigned char* out, int cap, short* nb) {
     HsEnc* h = (HsEnc*)p;
 #ifdef SB_EMU
-    sb::emu::init();
-    std::vector<std::thread> th;
-    for (int l = 0; l < 32; l++)
-        th.emplace_back([=]() { sb::emu::lane = l; sb::enc_packet_analysis(&h->st, &h->w.a, pcm, &h->w.scr); });
-    for (auto& t : th) t.join();
-    sb::emu::lane = 0;
+    // device pipeline: band split (kernel A0), core analysis (kernel A, cooperative), high-band analysis
+    static sb::CoopWork cw;
+    const int nf = h->st.frames_per_packet;
+    sb::qmf_decomp(pcm, h->w.a.low, h->w.a.high, h->st.qmf_mem, nf * 2 * sb::FRAME);
+    for (int i = 0; i < nf * sb::FRAME; i++) cw.low[i] = h->w.a.low[i];
+    sb::emu::run32([=]() { sb::c_enc_packet_analysis(&h->st, &cw, &h->w.scr); });
+    for (int f = 0; f < nf * sb::FRAME / h->st.hb_frame; f++)
+        sb::hb_analyse_frame(&h->st, h->w.a.high + f * h->st.hb_frame, &h->w.scr.hb_lsp_idx[f], h->w.scr.hb_nrg0[f]);
     return sb::enc_packet_quantise_and_code(&h->st, &h->w, out, cap, nb);
 #else
     return sb::enc_packet(&h->st, &h->w, pcm, out, cap, nb);
