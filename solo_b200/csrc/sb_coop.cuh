@@ -457,6 +457,1025 @@ SB_FN void c_find_pitch_lags(EncSilk* st, EncCtrl* c, PitchScr* P, i16* res, con
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// noise-shape analysis (SKP_Silk_noise_shape_analysis_FIX.c:137-531)
+// ---------------------------------------------------------------------------------------------------------------------
+struct ShapeScr {
+    i16 xw[NB_SUBFR][SHAPE_WIN];
+    i32 acorr[NB_SUBFR][SHAPE_ORDER + 1];
+    i32 scale[NB_SUBFR];
+};
+
+// Warped autocorrelation of the four shaping windows at once (SKP_Silk_warped_autocorrelation_FIX.c:36-85): the 16
+// all-pass sections run as a wavefront, lane g of an 8-lane group owns sections 2g and 2g+1 of its window and works on
+// sample t - g at step t; a section's right-hand state is its own previous output, so one shuffle per step suffices.
+SB_FN void c_warped_autocorr4(ShapeScr* S, i32 warping_Q16) {
+    const int QC = 10, QS = 14;
+    const int lane = SB_LANE, g = lane & 7, win = lane >> 3;
+    const i16* input = S->xw[win];
+    const i32 w = (i16)warping_Q16;
+    i32 p0 = 0, p1 = 0, p2 = 0, out = 0;
+    i64 c0 = 0, c1 = 0, c2 = 0;
+    for (int t = 0; t < SHAPE_WIN + 7; t++) {
+        const int n = t - g;
+        const i32 from_prev = wshfl_up(out, 1);
+        if (n >= 0 && n < SHAPE_WIN) {
+            const i32 s0 = shl((i32)input[n], QS);
+            const i32 in = g == 0 ? s0 : from_prev;
+            const i32 tmp2 = smlawb(p0, subw(p1, in), w);
+            const i32 tmp1 = smlawb(p1, subw(p2, tmp2), w);
+            c0 += smull(in, s0) >> (2 * QS - QC);
+            c1 += smull(tmp2, s0) >> (2 * QS - QC);
+            if (g == 7) c2 += smull(tmp1, s0) >> (2 * QS - QC);
+            p0 = in; p1 = tmp2; p2 = tmp1; out = tmp1;
+        }
+    }
+    const i64 corr0 = wshfl64(c0, win * 8);
+    int lsh = clz64(corr0) - 35;
+    lsh = limit(lsh, -12 - QC, 30 - QC);
+    i32* corr = S->acorr[win];
+    if (lsh >= 0) {
+        corr[2 * g] = (i32)shl64(c0, lsh); corr[2 * g + 1] = (i32)shl64(c1, lsh);
+        if (g == 7) corr[16] = (i32)shl64(c2, lsh);
+    } else {
+        corr[2 * g] = (i32)(c0 >> (-lsh)); corr[2 * g + 1] = (i32)(c1 >> (-lsh));
+        if (g == 7) corr[16] = (i32)(c2 >> (-lsh));
+    }
+    if (g == 0) S->scale[win] = -(QC + lsh);
+}
+
+// pitch_res points at res_pitch + FRAME, x at x_buf + FRAME.
+SB_FN void c_noise_shape_analysis(EncSilk* st, EncCtrl* c, ShapeScr* S, const i16* pitch_res, const i16* x) {
+    const int lane = SB_LANE;
+    // ---- scalars, computed by every lane from shared data; lane 0 stores ----
+    const i32 sigtype = c->sigtype;
+    const i32 speech_activity_Q8 = st->speech_activity_Q8, LTPCorr_Q15 = st->LTPCorr_Q15;
+    const i32 current_SNR_dB_Q7 = st->SNR_dB_Q7, current_SNRPerMD_dB_Q7 = st->SNRPerMD_dB_Q7;
+    const i32 input_quality_Q14 = (c->input_quality_bands_Q15[0] + c->input_quality_bands_Q15[1]) >> 2;
+    const i32 coding_quality_Q14 = sigm_q15(rshift_round(current_SNR_dB_Q7 - SB_FIXC(18.0, 7), 4)) >> 1;
+    i32 b_Q8 = SB_FIXC(1.0, 8) - speech_activity_Q8;
+    b_Q8 = smulwb(shl(b_Q8, 8), b_Q8);
+    i32 SNR_adj_dB_Q7 = smlawb(current_SNR_dB_Q7, smulbb(SB_FIXC(-4.0f, 7) >> (4 + 1), b_Q8),
+                               smulwb(SB_FIXC(1.0, 14) + input_quality_Q14, coding_quality_Q14));
+    if (sigtype == 0) SNR_adj_dB_Q7 = smlawb(SNR_adj_dB_Q7, SB_FIXC(2.0f, 8), LTPCorr_Q15);
+    else SNR_adj_dB_Q7 = smlawb(SNR_adj_dB_Q7, smlawb(SB_FIXC(6.0, 9), -SB_FIXC(0.4, 18), current_SNR_dB_Q7), SB_FIXC(1.0, 14) - input_quality_Q14);
+    const i32 md_input_quality_Q14 = sigm_q15(rshift_round(current_SNRPerMD_dB_Q7 - SB_FIXC(18.0, 7), 4)) >> 1;
+    i32 md_SNR_adj_dB_Q7 = smlawb(current_SNRPerMD_dB_Q7, smulbb(SB_FIXC(-4.0f, 7) >> (4 + 1), b_Q8),
+                                  smulwb(SB_FIXC(1.0, 14) + md_input_quality_Q14, coding_quality_Q14));
+    if (sigtype == 0) md_SNR_adj_dB_Q7 = smlawb(md_SNR_adj_dB_Q7, SB_FIXC(2.0f, 8), LTPCorr_Q15);
+    else md_SNR_adj_dB_Q7 = smlawb(md_SNR_adj_dB_Q7, smlawb(SB_FIXC(6.0, 9), -SB_FIXC(0.4, 18), current_SNRPerMD_dB_Q7), SB_FIXC(1.0, 14) - input_quality_Q14);
+
+    // sparseness of the residual (unvoiced): ten 2 ms energies, one per lane
+    i32 sparseness_Q8 = 0, QuantOffsetType = 0;
+    if (sigtype != 0) {      // uniform
+        i32 log_energy_Q7 = 0;
+        if (lane < 10) {
+            i32 nrg, scale;
+            sum_sqr_shift(&nrg, &scale, pitch_res + 16 * lane, 16, 0);
+            nrg += 16 >> scale;
+            log_energy_Q7 = lin2log(nrg);
+        }
+        const i32 prev = wshfl_up(log_energy_Q7, 1);
+        const i32 energy_variation_Q7 = wsum((lane >= 1 && lane < 10) ? iabs(log_energy_Q7 - prev) : 0);
+        sparseness_Q8 = sigm_q15(smulwb(energy_variation_Q7 - SB_FIXC(5.0, 7), SB_FIXC(0.1, 16))) >> 7;
+        QuantOffsetType = sparseness_Q8 > SB_FIXC(0.75f, 8) ? 0 : 1;
+        SNR_adj_dB_Q7 = smlawb(SNR_adj_dB_Q7, SB_FIXC(2.0f, 15), sparseness_Q8 - SB_FIXC(0.5, 8));
+        md_SNR_adj_dB_Q7 = smlawb(md_SNR_adj_dB_Q7, SB_FIXC(2.0f, 15), sparseness_Q8 - SB_FIXC(0.5, 8));
+    }
+    // bandwidth expansion control
+    const i32 predGain_Q16 = c->predGain_Q16;
+    i32 strength_Q16 = smulwb(predGain_Q16, SB_FIXC(1e-3f, 16));
+    i32 BWExp1_Q16, BWExp2_Q16;
+    BWExp1_Q16 = BWExp2_Q16 = div32_varq(SB_FIXC(0.95f, 16), smlaww(SB_FIXC(1.0, 16), strength_Q16, strength_Q16), 16);
+    const i32 delta_Q16 = smulwb(SB_FIXC(1.0, 16) - smulbb(3, coding_quality_Q14), SB_FIXC(0.01f, 16));
+    BWExp1_Q16 = subw(BWExp1_Q16, delta_Q16);
+    BWExp2_Q16 = addw(BWExp2_Q16, delta_Q16);
+    BWExp1_Q16 = shl(BWExp1_Q16, 14) / (BWExp2_Q16 >> 2);
+    const i32 warping_Q16 = smlawb(WARPING_Q16, coding_quality_Q14, SB_FIXC(0.01, 18));
+
+    // ---- the four 15 ms windows: slopes on eight lanes, flat parts copied by all ----
+    {
+        const int slope = (SHAPE_WIN - 40) >> 1;   // 40
+        if (lane < 8) {
+            const int k = lane >> 1, h = lane & 1;
+            const i16* xp = x - LA_SHAPE + k * SUBFR + h * (slope + 40);
+            apply_sine_window(S->xw[k] + h * (slope + 40), xp, h + 1, slope);
+        }
+        SB_PARFOR(i, 0, NB_SUBFR * 40) {
+            const int k = i / 40, j = i - 40 * k;
+            S->xw[k][slope + j] = (x - LA_SHAPE + k * SUBFR)[slope + j];
+        }
+    }
+    SB_SYNC();
+    c_warped_autocorr4(S, warping_Q16);
+    SB_SYNC();
+    // ---- per window: reflection coefficients, shaping filters, gains -- one window per lane (lanes 0..3) ----
+    i32 gain_k = 0, gains_pre_k = 0;
+    if (lane < NB_SUBFR) {
+        const int k = lane;
+        i32 auto_corr[SHAPE_ORDER + 1], refl_coef_Q16[SHAPE_ORDER], AR1_Q24[SHAPE_ORDER], AR2_Q24[SHAPE_ORDER];
+        for (int i = 0; i <= SHAPE_ORDER; i++) auto_corr[i] = S->acorr[k][i];
+        auto_corr[0] = addw(auto_corr[0], imax(smulwb(auto_corr[0] >> 4, SB_FIXC(1e-5f, 20)), 1));
+        i32 nrg = schur64(refl_coef_Q16, auto_corr, SHAPE_ORDER);
+        k2a_q16(AR2_Q24, refl_coef_Q16, SHAPE_ORDER);
+        int Qnrg = -S->scale[k];
+        if (Qnrg & 1) { Qnrg -= 1; nrg >>= 1; }
+        const i32 tmp32 = sqrt_approx(nrg);
+        Qnrg >>= 1;
+        gain_k = lshift_sat32(tmp32, 16 - Qnrg);
+        const i32 gain_mult_Q16 = warped_gain(AR2_Q24, warping_Q16, SHAPE_ORDER);
+        gain_k = smulww(gain_k, gain_mult_Q16);
+        if (gain_k < 0) gain_k = SB_I32_MAX;
+        bwexpander_32(AR2_Q24, SHAPE_ORDER, BWExp2_Q16);
+        for (int i = 0; i < SHAPE_ORDER; i++) AR1_Q24[i] = AR2_Q24[i];
+        bwexpander_32(AR1_Q24, SHAPE_ORDER, BWExp1_Q16);
+        i32 pre_nrg_Q30;
+        lpc_inv_pred_gain_q24(&pre_nrg_Q30, AR2_Q24, SHAPE_ORDER);
+        lpc_inv_pred_gain_q24(&nrg, AR1_Q24, SHAPE_ORDER);
+        pre_nrg_Q30 = shl(smulwb(pre_nrg_Q30, SB_FIXC(0.7, 15)), 1);
+        gains_pre_k = SB_FIXC(0.3, 14) + div32_varq(pre_nrg_Q30, nrg, 14);
+        limit_warped_coefs(AR2_Q24, AR1_Q24, warping_Q16, SB_FIXC(3.999, 24), SHAPE_ORDER);
+        for (int i = 0; i < SHAPE_ORDER; i++) {
+            c->AR1_Q13[k * SHAPE_ORDER + i] = (i16)sat16(rshift_round(AR1_Q24[i], 11));
+            c->AR2_Q13[k * SHAPE_ORDER + i] = (i16)sat16(rshift_round(AR2_Q24[i], 11));
+        }
+    }
+    // ---- gain tweaking ----
+    const i32 md_gain_mult_Q16 = log2lin(negw(smlawb(-SB_FIXC(16.0, 7), md_SNR_adj_dB_Q7, SB_FIXC(0.16, 16))));
+    i32 gain_mult_Q16 = log2lin(negw(smlawb(-SB_FIXC(16.0, 7), SNR_adj_dB_Q7, SB_FIXC(0.16, 16))));
+    const float md_delta_gain_par = (float)gain_mult_Q16 / (float)md_gain_mult_Q16;
+    i32 gain_add_Q16 = log2lin(smlawb(SB_FIXC(16.0, 7), SB_FIXC(4.0f, 7), SB_FIXC(0.16, 16)));
+    i32 avgGain_Q16 = st->avgGain_Q16;
+    {
+        i32 t32 = log2lin(smlawb(SB_FIXC(16.0, 7), SB_FIXC(-50.0f, 7), SB_FIXC(0.16, 16)));
+        t32 = smulww(avgGain_Q16, t32);
+        gain_add_Q16 = add_sat32(gain_add_Q16, t32);
+    }
+    gain_k = smulww(gain_k, gain_mult_Q16);
+    if (gain_k < 0) gain_k = SB_I32_MAX;
+    gain_k = add_pos_sat32(gain_k, gain_add_Q16);
+    {   // the running average chains through the four sub-frames
+        const i32 coef = rshift_round(smulbb(speech_activity_Q8, SB_FIXC(1e-3f, 10)), 2);
+        for (int k = 0; k < NB_SUBFR; k++) {
+            const i32 gk = wshfl(gain_k, k);
+            avgGain_Q16 = add_sat32(avgGain_Q16, smulwb(gk - avgGain_Q16, coef));
+        }
+    }
+    gain_mult_Q16 = SB_FIXC(1.0, 16) + rshift_round(mlaw(SB_FIXC(0.05f, 26), coding_quality_Q14, SB_FIXC(0.1f, 12)), 10);
+    gains_pre_k = smulwb(gain_mult_Q16, gains_pre_k);
+    // ---- low-frequency shaping, tilt, harmonic shaping ----
+    strength_Q16 = mulw(SB_FIXC(3.0f, 0), SB_FIXC(1.0, 16) + smulbb(SB_FIXC(0.5f, 1), c->input_quality_bands_Q15[0] - SB_FIXC(1.0, 15)));
+    i32 Tilt_Q16, LF_shp_k;
+    if (sigtype == 0) {
+        const i32 fs_kHz_inv = SB_FIXC(0.2, 14) / 8;
+        const i32 b_Q14 = fs_kHz_inv + SB_FIXC(3.0, 14) / imax(c->pitchL[lane & 3], 1);
+        LF_shp_k = shl(SB_FIXC(1.0, 14) - b_Q14 - smulwb(strength_Q16, b_Q14), 16);
+        LF_shp_k |= (u16)(b_Q14 - SB_FIXC(1.0, 14));
+        Tilt_Q16 = -SB_FIXC(0.3f, 16) - smulwb(SB_FIXC(1.0, 16) - SB_FIXC(0.3f, 16), smulwb(SB_FIXC(0.35f, 24), speech_activity_Q8));
+    } else {
+        const i32 b_Q14 = 21299 / 8;
+        LF_shp_k = shl(SB_FIXC(1.0, 14) - b_Q14 - smulwb(strength_Q16, smulwb(SB_FIXC(0.6, 16), b_Q14)), 16);
+        LF_shp_k |= (u16)(b_Q14 - SB_FIXC(1.0, 14));
+        Tilt_Q16 = -SB_FIXC(0.3f, 16);
+    }
+    i32 HarmBoost_Q16 = smulwb(smulwb(SB_FIXC(1.0, 17) - shl(coding_quality_Q14, 3), LTPCorr_Q15), SB_FIXC(0.1f, 16));
+    HarmBoost_Q16 = smlawb(HarmBoost_Q16, SB_FIXC(1.0, 16) - shl(input_quality_Q14, 2), SB_FIXC(0.1f, 16));
+    i32 HarmShapeGain_Q16 = 0;
+    if (sigtype == 0) {
+        HarmShapeGain_Q16 = smlawb(SB_FIXC(0.3f, 16),
+            SB_FIXC(1.0, 16) - smulwb(SB_FIXC(1.0, 18) - shl(coding_quality_Q14, 4), input_quality_Q14), SB_FIXC(0.2f, 16));
+        HarmShapeGain_Q16 = smulwb(shl(HarmShapeGain_Q16, 1), sqrt_approx(shl(LTPCorr_Q15, 15)));
+    }
+    i32 hb = st->HarmBoost_smth_Q16, hs = st->HarmShapeGain_smth_Q16, ti = st->Tilt_smth_Q16;
+    i32 hb_k = 0, hs_k = 0, ti_k = 0;
+    for (int k = 0; k < NB_SUBFR; k++) {
+        hb = smlawb(hb, HarmBoost_Q16 - hb, SB_FIXC(0.4f, 16));
+        hs = smlawb(hs, HarmShapeGain_Q16 - hs, SB_FIXC(0.4f, 16));
+        ti = smlawb(ti, Tilt_Q16 - ti, SB_FIXC(0.4f, 16));
+        if (lane == k) { hb_k = rshift_round(hb, 2); hs_k = rshift_round(hs, 2); ti_k = rshift_round(ti, 2); }
+    }
+    SB_SYNC();     // every lane has read what it needs from c / st
+    if (lane < NB_SUBFR) {
+        c->Gains_Q16[lane] = gain_k;
+        c->GainsPre_Q14[lane] = gains_pre_k;
+        c->LF_shp_Q14[lane] = LF_shp_k;
+        c->HarmBoost_Q14[lane] = hb_k;
+        c->HarmShapeGain_Q14[lane] = hs_k;
+        c->Tilt_Q14[lane] = ti_k;
+    }
+    if (lane == 0) {
+        c->current_SNR_dB_Q7 = current_SNR_dB_Q7;
+        c->current_SNRPerMD_dB_Q7 = current_SNRPerMD_dB_Q7;
+        c->input_quality_Q14 = input_quality_Q14;
+        c->coding_quality_Q14 = coding_quality_Q14;
+        c->sparseness_Q8 = sparseness_Q8;
+        c->QuantOffsetType = QuantOffsetType;
+        c->md_delta_gain_par = md_delta_gain_par;
+        st->avgGain_Q16 = avgGain_Q16;
+        st->HarmBoost_smth_Q16 = hb; st->HarmShapeGain_smth_Q16 = hs; st->Tilt_smth_Q16 = ti;
+    }
+    SB_SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// prefilter (SKP_Silk_prefilter_FIX.c:43-224)
+// ---------------------------------------------------------------------------------------------------------------------
+struct PrefScr {
+    i16 st_res[FRAME];
+    i32 sLF_MA[FRAME];         // x_filt_Q12 on the way in, sLF_MA_shp_Q12 on the way out of the lane-0 recursion
+    i32 par[NB_SUBFR][6];      // per sub-frame: B0, B1, Tilt_Q14, LF_shp_Q14, HarmShapeFIRPacked_Q12, lag
+};
+
+SB_FN void c_prefilter(EncSilk* st, const EncCtrl* c, PrefScr* S, i16* xw, const i16* x) {
+    const int lane = SB_LANE;
+    // ---- warped LPC analysis filter over the whole frame: wavefront, lane j = all-pass section j (16 lanes) ----
+    {
+        const int j = lane;
+        const i32 lambda = WARPING_Q16;
+        i32 p0 = 0, p1 = 0, out = 0, acc_out = 0;
+        if (j < SHAPE_ORDER) { p0 = st->pf_sAR_shp[j]; p1 = st->pf_sAR_shp[j + 1]; }
+        for (int t = 0; t < FRAME + SHAPE_ORDER - 1; t++) {
+            const int n = t - j;
+            const i32 in_prev = wshfl_up(out, 1), acc_prev = wshfl_up(acc_out, 1);
+            if (j < SHAPE_ORDER && n >= 0 && n < FRAME) {
+                const i32 xin = x[n];
+                const i32 in = j == 0 ? shl(xin, 14) : in_prev;
+                const i32 o = j == 0 ? smlawb(p0, p1, lambda) : smlawb(p0, subw(p1, in), lambda);
+                const i32 coef = c->AR1_Q13[(n / SUBFR) * SHAPE_ORDER + j];
+                const i32 a = j == 0 ? smulwb(o, coef) : smlawb(acc_prev, o, coef);
+                p0 = in; p1 = o; out = o; acc_out = a;
+                if (j == SHAPE_ORDER - 1) S->st_res[n] = (i16)sat16(xin - rshift_round(a, 11));
+            }
+        }
+        SB_SYNC();      // state is read above by every lane before anyone writes it
+        if (j < SHAPE_ORDER) st->pf_sAR_shp[j] = p0;
+        if (j == SHAPE_ORDER - 1) st->pf_sAR_shp[SHAPE_ORDER] = p1;
+    }
+    // ---- per sub-frame constants (lanes 0..3) ----
+    const i32 lagPrev = st->pf_lagPrev, idx_start = st->pf_sLTP_shp_buf_idx;   // read before lane 0 advances them below
+    if (lane < NB_SUBFR) {
+        const int k = lane;
+        const i32 HarmShapeGain_Q12 = smulwb(c->HarmShapeGain_Q14[k], 16384 - c->HarmBoost_Q14[k]);
+        i32 packed = HarmShapeGain_Q12 >> 2;
+        packed |= shl(HarmShapeGain_Q12 >> 1, 16);
+        i32 t32 = smlabb(SB_FIXC(0.05f, 26), c->HarmBoost_Q14[k], HarmShapeGain_Q12);
+        t32 = smlabb(t32, c->coding_quality_Q14, SB_FIXC(0.1f, 12));
+        t32 = smulwb(t32, -c->GainsPre_Q14[k]);
+        t32 = rshift_round(t32, 12);
+        S->par[k][0] = rshift_round(c->GainsPre_Q14[k], 2);
+        S->par[k][1] = sat16(t32);
+        S->par[k][2] = c->Tilt_Q14[k];
+        S->par[k][3] = c->LF_shp_Q14[k];
+        S->par[k][4] = packed;
+        S->par[k][5] = c->sigtype == 0 ? c->pitchL[k] : lagPrev;
+    }
+    const i32 sHarmHP = st->pf_sHarmHP;
+    SB_SYNC();
+    SB_PARFOR(i, 0, FRAME) {
+        const int k = i / SUBFR;
+        const i32 prev = i > 0 ? (i32)S->st_res[i - 1] : sHarmHP;
+        S->sLF_MA[i] = smlabb(smulbb(S->st_res[i], S->par[k][0]), prev, S->par[k][1]);
+    }
+    SB_SYNC();
+    // ---- low-frequency shaping recursion (SKP_Silk_prefilt_FIX :174-224): one chain per frame, lane 0 ----
+    if (lane == 0) {
+        i32 sLF_AR = st->pf_sLF_AR_shp_Q12, sLF_MA = st->pf_sLF_MA_shp_Q12;
+        for (int k = 0; k < NB_SUBFR; k++) {
+            const i32 Tilt_Q14 = S->par[k][2], LF_shp_Q14 = S->par[k][3];
+            for (int i = k * SUBFR; i < (k + 1) * SUBFR; i++) {
+                const i32 n_Tilt_Q10 = smulwb(sLF_AR, Tilt_Q14);
+                const i32 n_LF_Q10 = smlawb(smulwt(sLF_AR, LF_shp_Q14), sLF_MA, LF_shp_Q14);
+                sLF_AR = subw(S->sLF_MA[i], shl(n_Tilt_Q10, 2));
+                sLF_MA = subw(sLF_AR, shl(n_LF_Q10, 2));
+                S->sLF_MA[i] = sLF_MA;
+            }
+        }
+        st->pf_sLF_AR_shp_Q12 = sLF_AR;
+        st->pf_sLF_MA_shp_Q12 = sLF_MA;
+        st->pf_sHarmHP = S->st_res[FRAME - 1];
+        st->pf_sLTP_shp_buf_idx = (idx_start - FRAME) & LTP_MASK;
+        st->pf_lagPrev = c->pitchL[NB_SUBFR - 1];
+    }
+    SB_SYNC();
+    // shaping-buffer writes of the whole frame first, harmonic taps afterwards: a tap of sample i reaches lag - 2 .. lag
+    // samples back (lag >= 16), i.e. only positions written before sample i
+    SB_PARFOR(i, 0, FRAME) st->pf_sLTP_shp[(idx_start - 1 - i) & LTP_MASK] = (i16)sat16(rshift_round(S->sLF_MA[i], 12));
+    SB_SYNC();
+    SB_PARFOR(i, 0, FRAME) {
+        const int k = i / SUBFR;
+        const i32 lag = S->par[k][5], packed = S->par[k][4];
+        i32 n_LTP_Q12 = 0;
+        if (lag > 0) {
+            const i32 idx = lag + idx_start - i;
+            n_LTP_Q12 = smulbb(st->pf_sLTP_shp[(idx - 2) & LTP_MASK], packed);
+            n_LTP_Q12 = smlabt(n_LTP_Q12, st->pf_sLTP_shp[(idx - 1) & LTP_MASK], packed);
+            n_LTP_Q12 = smlabb(n_LTP_Q12, st->pf_sLTP_shp[idx & LTP_MASK], packed);
+        }
+        xw[i] = (i16)sat16(rshift_round(subw(S->sLF_MA[i], n_LTP_Q12), 12));
+    }
+    SB_SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// prediction analysis (SKP_Silk_find_pred_coefs_FIX.c:31-131 and what it calls)
+// ---------------------------------------------------------------------------------------------------------------------
+// Two Burg analyses side by side (SKP_Silk_burg_modified.c:49-228, QA = 25): lanes 0..15 analyse nb0 blocks starting at x0,
+// lanes 16..31 nb1 blocks starting at x1 (find_LPC runs the whole frame and its second half; a caller with one analysis
+// passes the same arguments twice).  Lane k of a half keeps row k of C_first_row / C_last_row / Af / CAf / CAb in registers;
+// sums over the prediction order are 16-lane reductions (addition mod 2^32 is order-free), index reversals are shuffles.
+// All lanes of a half return that half's results; A_Q16 (shared memory, [2][16], not inside B) receives the coefficients.
+struct BurgScr {
+    i32 cfr[2][NB_SUBFR][16];    // per block: first-row correlations before they are summed over the blocks
+};
+template <int D> SB_FN void c_burg2(i32* res_nrg, i32* res_nrg_Q, i32 (*A_Q16)[16], BurgScr* B, const i16* x0, int nb0, const i16* x1, int nb1, int L,
+                                    i32 WhiteNoiseFrac_Q32) {
+    const int QA = 25, MAX_RSHIFTS = 32 - QA, MIN_RSHIFTS = -16, HEAD = 2;
+    const int lane = SB_LANE, h = lane >> 4, k = lane & 15, base = h << 4;
+    const i16* x = h ? x1 : x0;
+    const int nb = h ? nb1 : nb0;
+    // ---- C0 = energy with the reference's shift logic ----
+    i32 C0, rshifts;
+    {
+        i64 part = 0;
+        for (int i = k; i < nb * L; i += 16) part += (i64)((i32)x[i] * (i32)x[i]);
+        const i64 total = gsum64<16>(part);
+        i32 e = 0, sft = 0;
+        if (total < ((i64)1 << 31)) {
+            e = (i32)total;
+            if (e & 0xC0000000) { e = (i32)((u32)e >> 2); sft = 2; }
+        } else if (k == 0) {
+            sum_sqr_shift(&e, &sft, x, nb * L, 0);
+        }
+        C0 = wshfl(e, base); rshifts = wshfl(sft, base);
+    }
+    if (rshifts > MAX_RSHIFTS) {
+        C0 = shl(C0, rshifts - MAX_RSHIFTS);
+        rshifts = MAX_RSHIFTS;
+    } else {
+        const int lz = clz32(C0) - 1;
+        int extra = HEAD - lz;
+        if (extra > 0) { extra = imin(extra, MAX_RSHIFTS - rshifts); C0 = C0 >> extra; }
+        else { extra = imax(extra, MIN_RSHIFTS - rshifts); C0 = shl(C0, -extra); }
+        rshifts += extra;
+    }
+    // ---- first-row correlations: tasks (block, lag) over the 16 lanes of the half ----
+    for (int t = k; t < nb * D; t += 16) {
+        const int s = t / D, n = t - s * D + 1;
+        const i16* xp = x + s * L;
+        i64 acc = 0;
+        for (int i = 0; i < L - n; i++) acc += (i64)((i32)xp[i] * (i32)xp[i + n]);
+        B->cfr[h][s][n - 1] = rshifts > 0 ? (i32)(acc >> rshifts) : shl((i32)acc, -rshifts);
+    }
+    SB_SYNC();
+    i32 Cf = 0, Cl, Af = 0, CAf = 0, CAb = 0;
+    if (k < D) for (int s = 0; s < nb; s++) Cf = addw(Cf, B->cfr[h][s][k]);
+    Cl = Cf;
+    if (k == 0) CAb = CAf = addw(addw(C0, smmul(WhiteNoiseFrac_Q32, C0)), 1);
+    bool done = false;
+    for (int n = 0; n < D; n++) {
+        // (a) per block: prediction errors at both ends (4 lanes per block, 16-lane halves hold up to 4 blocks)
+        const int sblk = k >> 2, j = k & 3;
+        i32 t1 = 0, t2 = 0;
+        for (int r = 0; 4 * r < n; r++) {           // n is uniform: every lane takes part in every exchange
+            const int kk = j + 4 * r;
+            const i32 At = wshfl(Af, base + (kk & 15));
+            if (kk < n && sblk < nb) {
+                const i16* xp = x + sblk * L;
+                if (rshifts > -2) {
+                    t1 = smlawb(t1, At, xp[n - kk - 1]);
+                    t2 = smlawb(t2, At, xp[L - n + kk]);
+                } else {
+                    const i32 At1 = rshift_round(At, QA - 17);
+                    t1 = mlaw(t1, xp[n - kk - 1], At1);
+                    t2 = mlaw(t2, xp[L - n + kk], At1);
+                }
+            }
+        }
+        t1 = gsum<4>(t1); t2 = gsum<4>(t2);
+        if (sblk < nb) {
+            const i16* xp = x + sblk * L;
+            if (rshifts > -2) {
+                t1 = addw(t1, shl((i32)xp[n], QA - 16)); t2 = addw(t2, shl((i32)xp[L - n - 1], QA - 16));
+                t1 = shl(negw(t1), 32 - QA - rshifts); t2 = shl(negw(t2), 32 - QA - rshifts);
+            } else {
+                t1 = addw(t1, shl((i32)xp[n], 17)); t2 = addw(t2, shl((i32)xp[L - n - 1], 17));
+                t1 = negw(t1); t2 = negw(t2);
+            }
+        }
+        // (b) rank-one updates of the four rows, lane k = column k, blocks in turn
+        for (int s = 0; s < NB_SUBFR; s++) {
+            const i32 e1 = wshfl(t1, base + 4 * s), e2 = wshfl(t2, base + 4 * s);
+            if (s < nb && !done) {
+                const i16* xp = x + s * L;
+                if (rshifts > -2) {
+                    const i32 x1 = negw(shl((i32)xp[n], 16 - rshifts)), x2 = negw(shl((i32)xp[L - n - 1], 16 - rshifts));
+                    if (k < n) { Cf = smlawb(Cf, x1, xp[n - k - 1]); Cl = smlawb(Cl, x2, xp[L - n + k]); }
+                    if (k <= n) { CAf = smlawb(CAf, e1, xp[n - k]); CAb = smlawb(CAb, e2, xp[L - n + k - 1]); }
+                } else {
+                    const i32 x1 = negw(shl((i32)xp[n], -rshifts)), x2 = negw(shl((i32)xp[L - n - 1], -rshifts));
+                    if (k < n) { Cf = mlaw(Cf, x1, xp[n - k - 1]); Cl = mlaw(Cl, x2, xp[L - n + k]); }
+                    if (k <= n) { CAf = smlaww(CAf, e1, shl((i32)xp[n - k], -rshifts - 1)); CAb = smlaww(CAb, e2, shl((i32)xp[L - n + k - 1], -rshifts - 1)); }
+                }
+            }
+        }
+        // (c) reflection coefficient
+        i32 tmp1 = wshfl(Cf, base + n), tmp2 = wshfl(Cl, base + n);
+        {
+            const i32 a = wshfl(Cl, base + ((n - k - 1) & 15)), b = wshfl(Cf, base + ((n - k - 1) & 15));
+            const i32 cb = wshfl(CAb, base + ((n - k) & 15)), s1 = wshfl(CAb, base + ((k + 1) & 15)), s2 = wshfl(CAf, base + ((k + 1) & 15));
+            i32 T1 = 0, T2 = 0, T3 = 0, T4 = 0;
+            if (k < n) {
+                int lz = clz32(iabs(Af)) - 1;
+                lz = imin(32 - QA, lz);
+                const i32 At1 = shl(Af, lz);
+                const int sh = 32 - QA - lz;
+                T1 = shl(smmul(a, At1), sh); T2 = shl(smmul(b, At1), sh);
+                T3 = shl(smmul(cb, At1), sh); T4 = shl(smmul(addw(s1, s2), At1), sh);
+            }
+            tmp1 = addw(tmp1, gsum<16>(T1)); tmp2 = addw(tmp2, gsum<16>(T2));
+            const i32 num0 = gsum<16>(T3);
+            const i32 nrg = addw(addw(wshfl(CAb, base), wshfl(CAf, base)), gsum<16>(T4));
+            i32 num = shl(negw(addw(num0, tmp2)), 1);
+            const bool ok = iabs(num) < nrg;
+            const i32 rc_Q31 = (ok && !done) ? div32_varq(num, nrg, 31) : 0;
+            if (!done) {
+                if (k == n + 1) { CAf = tmp1; CAb = tmp2; }
+                if (!ok) { if (k >= n) Af = 0; done = true; }
+            }
+            // (d), (e): order update of the predictor and of the two correlation rows (old values on the right-hand side)
+            const i32 tA = wshfl(Af, base + ((n - k - 1) & 15));
+            const i32 ob = wshfl(CAb, base + ((n + 1 - k) & 15)), of = wshfl(CAf, base + ((n + 1 - k) & 15));
+            if (!done) {
+                if (k < n) Af = addw(Af, shl(smmul(tA, rc_Q31), 1));
+                if (k == n) Af = rc_Q31 >> (31 - QA);
+                if (k <= n + 1) {
+                    const i32 cf_old = CAf, cb_old = CAb;
+                    CAf = addw(cf_old, shl(smmul(ob, rc_Q31), 1));
+                    CAb = addw(cb_old, shl(smmul(of, rc_Q31), 1));
+                }
+            }
+        }
+    }
+    // ---- result ----
+    const i32 At1 = k < D ? rshift_round(Af, QA - 16) : 0;
+    const i32 caf_next = wshfl(CAf, base + ((k + 1) & 15));
+    const i32 nrg = addw(wshfl(CAf, base), gsum<16>(k < D ? smulww(caf_next, At1) : 0));
+    const i32 tt = addw(1 << 16, gsum<16>(k < D ? smulww(At1, At1) : 0));
+    if (k < D) A_Q16[h][k] = negw(At1);
+    *res_nrg = smlaww(nrg, smmul(WhiteNoiseFrac_Q32, C0), negw(tt));
+    *res_nrg_Q = -rshifts;
+}
+
+// SKP_Silk_A2NLSF (A2NLSF.c:46-287).  The reference walks a 128-interval cosine grid and alternates between the two
+// symmetric polynomials; here both polynomials are evaluated on the whole grid (lanes over grid points), sign changes are
+// collected as bit masks, the walk becomes a scan for the next set bit, and the d bisections run on d lanes.
+// a_Q16: shared memory (modified when the root search has to widen the bandwidth); NLSF: shared memory.
+struct A2nlsfScr { i32 y[2][132]; i32 k_of[16]; i32 ylo_of[16]; };
+template <int D> SB_FN void c_a2nlsf(i32* NLSF, i32* a_Q16, A2nlsfScr* Z) {
+    enum { DD = D / 2, BIN = 3, TABSZ = 128, MAX_ITER = 30 };
+    const int lane = SB_LANE;
+    const i32* cosv = SB_T(lsf_cos_q12);
+    for (int iter = 0;; iter++) {
+        i32 PQ[2][DD + 1];
+        {
+            i32 a[D];
+#pragma unroll
+            for (int i = 0; i < D; i++) a[i] = a_Q16[i];
+            PQ[0][DD] = 1 << 16; PQ[1][DD] = 1 << 16;
+#pragma unroll
+            for (int k = 0; k < DD; k++) {
+                PQ[0][k] = subw(negw(a[DD - k - 1]), a[DD + k]);
+                PQ[1][k] = addw(negw(a[DD - k - 1]), a[DD + k]);
+            }
+#pragma unroll
+            for (int k = DD; k > 0; k--) { PQ[0][k - 1] = subw(PQ[0][k - 1], PQ[0][k]); PQ[1][k - 1] = addw(PQ[1][k - 1], PQ[1][k]); }
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+#pragma unroll
+                for (int k = 2; k <= DD; k++) {
+#pragma unroll
+                    for (int n = DD; n > k; n--) PQ[q][n - 2] = subw(PQ[q][n - 2], PQ[q][n]);
+                    PQ[q][k - 2] = subw(PQ[q][k - 2], shl(PQ[q][k], 1));
+                }
+            }
+        }
+        SB_SYNC();
+        // both polynomials on the grid
+        for (int g = lane; g <= TABSZ; g += 32) {
+            const i32 x_Q16 = shl(cosv[g], 4);
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                i32 y32 = PQ[q][DD];
+#pragma unroll
+                for (int n = DD - 1; n >= 0; n--) y32 = smlaww(PQ[q][n], y32, x_Q16);
+                Z->y[q][g] = y32;
+            }
+        }
+        SB_SYNC();
+        // sign changes between neighbouring grid points: bit g of word w <-> interval ending at grid point 32 w + g
+        u32 sc[2][5];
+#pragma unroll
+        for (int w = 0; w < 5; w++) {
+            const int g = 32 * w + lane;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                bool on = false;
+                if (g >= 1 && g <= TABSZ) { const i32 lo = Z->y[q][g - 1], hi = Z->y[q][g]; on = (lo <= 0 && hi >= 0) || (lo >= 0 && hi <= 0); }
+                sc[q][w] = wballot(on);
+            }
+        }
+        // the walk (every lane, identical)
+        int root_ix = 0, q = 0, k = 1;
+        bool forced = false; i32 fy = 0;
+        if (Z->y[0][0] < 0) { root_ix = 1; q = 1; }
+        bool fail = false;
+        while (root_ix < D) {
+            int kk = -1;
+            if (forced) {
+                const i32 hi = Z->y[q][k];
+                if ((fy <= 0 && hi >= 0) || (fy >= 0 && hi <= 0)) kk = k;
+            }
+            int from = forced ? k + 1 : k;
+            bool was_forced = forced && kk == k;
+            if (kk < 0) {
+                for (int w = from >> 5; w < 5 && kk < 0; w++) {
+                    u32 m = sc[q][w];
+                    if (w == (from >> 5)) m &= ~0u << (from & 31);
+                    if (m) kk = 32 * w + ctz32(m);
+                }
+            }
+            if (kk < 0 || kk > TABSZ) { fail = true; break; }
+            if (lane == root_ix) { Z->k_of[root_ix] = kk; Z->ylo_of[root_ix] = was_forced ? fy : Z->y[q][kk - 1]; }
+            root_ix++;
+            q = root_ix & 1;
+            k = kk;
+            forced = true;
+            fy = shl(1 - (root_ix & 2), 12);
+        }
+        if (!fail) {
+            SB_SYNC();
+            const int first = Z->y[0][0] < 0 ? 1 : 0;
+            if (lane == 0 && first) NLSF[0] = 0;
+            if (lane >= first && lane < D) {
+                const int r = lane, qq = r & 1, kk = Z->k_of[r];
+                i32 xlo = cosv[kk - 1], xhi = cosv[kk], ylo = Z->ylo_of[r], yhi = Z->y[qq][kk];
+                i32 ffrac = -256;
+                for (int m = 0; m < BIN; m++) {
+                    const i32 xmid = rshift_round(xlo + xhi, 1);
+                    const i32 x_Q16 = shl(xmid, 4);
+                    i32 ymid = qq ? PQ[1][DD] : PQ[0][DD];
+#pragma unroll
+                    for (int n = DD - 1; n >= 0; n--) ymid = smlaww(qq ? PQ[1][n] : PQ[0][n], ymid, x_Q16);
+                    if ((ylo <= 0 && ymid >= 0) || (ylo >= 0 && ymid <= 0)) { xhi = xmid; yhi = ymid; }
+                    else { xlo = xmid; ylo = ymid; ffrac = ffrac + (128 >> m); }
+                }
+                if (iabs(ylo) < 65536) {
+                    const i32 den = subw(ylo, yhi);
+                    const i32 nom = addw(shl(ylo, 8 - BIN), den >> 1);
+                    if (den != 0) ffrac += nom / den;
+                } else {
+                    ffrac += ylo / (subw(ylo, yhi) >> (8 - BIN));
+                }
+                NLSF[r] = imin(shl(kk, 8) + ffrac, 32767);
+            }
+            SB_SYNC();
+            return;
+        }
+        // no root left on the grid: widen the bandwidth and start over (A2NLSF.c:251-283)
+        const int i = iter + 1;
+        if (i > MAX_ITER) {
+            SB_SYNC();
+            const i32 n0 = (1 << 15) / (D + 1);
+            if (lane < D) NLSF[lane] = lane == 0 ? n0 : smulbb(lane + 1, n0);
+            SB_SYNC();
+            return;
+        }
+        const i32 f = c_bwexpander32_factor(D, 65536 - smulbb(10 + i, i));
+        SB_SYNC();
+        if (lane < D) a_Q16[lane] = smulww(a_Q16[lane], f);
+        SB_SYNC();
+    }
+}
+
+struct PredScr {
+    alignas(4) i16 LPC_in_pre[NB_SUBFR * LPC_ORDER + FRAME];
+    i32 WLTP[NB_SUBFR * LTP_ORDER * LTP_ORDER];
+    LtpSubfr ltp[NB_SUBFR];
+    i32 invGains_Q16[NB_SUBFR], local_gains[NB_SUBFR], Wght_Q15[NB_SUBFR];
+    i32 NLSF_Q15[LPC_ORDER + 2];
+    i32 NLSFW_Q6[LPC_ORDER + 2];
+    i32 A_Q16[2][16];            // Burg results: whole frame, second half
+    i16 a_tmp_Q12[4][LPC_ORDER + 2];
+    union {
+        struct { BurgScr burg; A2nlsfScr a2n; } lpc;
+        i16 LPC_res[4][2 * (SUBFR + LPC_ORDER)];
+        struct {
+            i32 res[2][16 * LPC_ORDER];
+            i32 rate[2][16];
+            u32 path_lo[2][16]; u16 path_hi[2][16];
+            i32 cand_v[64]; i16 cand_e[64];
+            i32 best_v[16]; i16 best_e[16];
+            i32 nlsf_s[16][LPC_ORDER + 1];
+        } vq;
+    } u;
+};
+
+// SKP_Silk_quant_LTP_gains_FIX (quant_LTP_gains_FIX.c:30-103): 8 lanes per sub-frame walk each codebook
+SB_FN void c_quant_ltp_gains(i16* B_Q14, i32* cbk_index, i32* periodicity_index, const i32* W_Q18, i32 mu_Q8) {
+    const int lane = SB_LANE, j = lane >> 3, g = lane & 7;
+    i32 best_rd = SB_I32_MAX, best_k = 0, best_idx = 0;
+    const i16* in = B_Q14 + j * LTP_ORDER;
+    const i32* W = W_Q18 + j * LTP_ORDER * LTP_ORDER;
+    for (int k = 0; k < 3; k++) {
+        const i16* cl = k == 0 ? SB_T(ltp_bits0_q6) : (k == 1 ? SB_T(ltp_bits1_q6) : SB_T(ltp_bits2_q6));
+        const i16* cbk = k == 0 ? SB_T(ltp_vq0_q14) : (k == 1 ? SB_T(ltp_vq1_q14) : SB_T(ltp_vq2_q14));
+        const int size = SB_T(ltp_vq_sizes)[k];
+        i32 rd = SB_I32_MAX, idx = 0;
+        for (int e = g; e < size; e += 8) {
+            const i32 v = vq_wmat_ec_entry(in, W, cbk + e * LTP_ORDER, cl[e], mu_Q8);
+            if (v < rd) { rd = v; idx = e; }
+        }
+        gargmin<8>(rd, idx);                 // first of equal minima
+        i32 rate_dist = 0;
+        for (int jj = 0; jj < NB_SUBFR; jj++) rate_dist = add_pos_sat32(rate_dist, wshfl(rd, 8 * jj));
+        rate_dist = imin(SB_I32_MAX - 1, rate_dist);
+        if (rate_dist < best_rd) { best_rd = rate_dist; best_k = k; best_idx = idx; }
+    }
+    SB_SYNC();
+    const i16* cbk = best_k == 0 ? SB_T(ltp_vq0_q14) : (best_k == 1 ? SB_T(ltp_vq1_q14) : SB_T(ltp_vq2_q14));
+    if (g < LTP_ORDER) B_Q14[j * LTP_ORDER + g] = cbk[best_idx * LTP_ORDER + g];
+    if (g == 0) cbk_index[j] = best_idx;
+    if (lane == 0) *periodicity_index = best_k;
+    SB_SYNC();
+}
+
+// SKP_Silk_find_LPC_FIX (find_LPC_FIX.c:32-148), order 10, four blocks of 50 samples in x
+SB_FN void c_find_lpc(i32* NLSF_Q15, i32* interpIndex, const i32* prev_NLSFq_Q15, int useInterp, PredScr* Q) {
+    enum { ORD = LPC_ORDER, SL = SUBFR + LPC_ORDER };
+    const int lane = SB_LANE, h = lane >> 4;
+    const i16* x = Q->LPC_in_pre;
+    BurgScr* B = &Q->u.lpc.burg;
+    i32 rn, rq;
+    c_burg2<ORD>(&rn, &rq, Q->A_Q16, B, x, NB_SUBFR, useInterp ? x + (NB_SUBFR >> 1) * SL : x, useInterp ? (NB_SUBFR >> 1) : NB_SUBFR, SL, SB_FIXC(2.5e-5f, 32));
+    SB_SYNC();
+    {   // bwexpander_32(a, 10, 0.99995) on both results (coefficient index = lane inside each half)
+        const int k = lane & 15;
+        i32 t = SB_FIXC(0.99995f, 16), mine = t;
+        for (int i = 0; i < ORD - 1; i++) { if (k == i) mine = t; t = smulww(SB_FIXC(0.99995f, 16), t); }
+        if (k >= ORD - 1) mine = t;
+        if (k < ORD) Q->A_Q16[h][k] = smulww(Q->A_Q16[h][k], mine);
+    }
+    i32 res_nrg = wshfl(rn, 0), res_nrg_Q = wshfl(rq, 0);
+    const i32 res_tmp_nrg = wshfl(rn, 16), res_tmp_nrg_Q = wshfl(rq, 16);
+    SB_SYNC();
+    int interp = 4;
+    if (useInterp == 1) {     // uniform
+        int shift = res_tmp_nrg_Q - res_nrg_Q;
+        if (shift >= 0) {
+            if (shift < 32) res_nrg = subw(res_nrg, res_tmp_nrg >> shift);
+        } else {
+            res_nrg = subw(res_nrg >> (-shift), res_tmp_nrg);
+            res_nrg_Q = res_tmp_nrg_Q;
+        }
+        c_a2nlsf<ORD>(NLSF_Q15, Q->A_Q16[1], &Q->u.lpc.a2n);
+        // the four interpolation candidates: NLSF -> LPC on four lanes, analysis filters over all lanes
+        i32 prevv[ORD];
+        if (lane < 4) {
+            i32 NLSF0[ORD], nl[ORD];
+            for (int i = 0; i < ORD; i++) { nl[i] = NLSF_Q15[i]; prevv[i] = prev_NLSFq_Q15[i]; }
+            interpolate(NLSF0, prevv, nl, lane, ORD);
+            i16 a12[ORD];
+            nlsf2a_stable(a12, NLSF0, ORD);
+            for (int i = 0; i < ORD; i++) Q->a_tmp_Q12[lane][i] = a12[i];
+        }
+        SB_SYNC();     // also: the grid scratch of c_a2nlsf (same union) is dead from here on
+        for (int t = lane; t < 4 * 2 * SL; t += 32) {
+            const int cand = t / (2 * SL), kx = t - cand * 2 * SL;
+            const i16* bq = Q->a_tmp_Q12[cand];
+            i32 acc = 0;
+#pragma unroll
+            for (int d = 0; d < ORD; d++) if (d < kx) acc = addw(acc, (i32)x[kx - 1 - d] * (i32)bq[d]);
+            const i32 xi = x[kx];
+            Q->u.LPC_res[cand][kx] = (i16)sat16(rshift_round(sub_sat32(shl(xi, 12), acc), 12));
+        }
+        SB_SYNC();
+        i32 e = 0, sft = 0;
+        if (lane < 8) {    // (candidate, half)
+            const int cand = lane >> 1, half = lane & 1;
+            sum_sqr_shift(&e, &sft, Q->u.LPC_res[cand] + ORD + half * SL, SL - ORD, (ORD + half * SL) & 1);
+        }
+        for (int kq = 3; kq >= 0; kq--) {
+            i32 res_nrg0 = wshfl(e, 2 * kq), res_nrg1 = wshfl(e, 2 * kq + 1);
+            const i32 rshift0 = wshfl(sft, 2 * kq), rshift1 = wshfl(sft, 2 * kq + 1);
+            i32 res_nrg_interp_Q;
+            shift = rshift0 - rshift1;
+            if (shift >= 0) { res_nrg1 = res_nrg1 >> shift; res_nrg_interp_Q = -rshift0; }
+            else { res_nrg0 = res_nrg0 >> (-shift); res_nrg_interp_Q = -rshift1; }
+            const i32 res_nrg_interp = addw(res_nrg0, res_nrg1);
+            shift = res_nrg_interp_Q - res_nrg_Q;
+            int lower;
+            if (shift >= 0) lower = (res_nrg_interp >> shift) < res_nrg;
+            else if (-shift < 32) lower = res_nrg_interp < (res_nrg >> (-shift));
+            else lower = 0;
+            if (lower) { res_nrg = res_nrg_interp; res_nrg_Q = res_nrg_interp_Q; interp = kq; }
+        }
+        SB_SYNC();
+    }
+    if (interp == 4) c_a2nlsf<ORD>(NLSF_Q15, Q->A_Q16[0], &Q->u.lpc.a2n);
+    if (lane == 0) *interpIndex = interp;
+    SB_SYNC();
+}
+
+// SKP_Silk_NLSF_MSVQ_encode_FIX (NLSF_MSVQ_encode_FIX.c:33-239), order 10, 6 stages, 16 survivors.
+// Stage: lanes over (survivor, code vector) pairs; the 16 best pairs by (value, scan position) -- what the reference's stable
+// partial insertion sort returns -- are found by bounding the 16th value with the lanes' own minima, compacting the pairs
+// below the bound in scan order and ranking that short list.
+SB_FN void c_nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb, const i32* pNLSF_q_Q15_prev, const i32* pW_Q6,
+                              i32 NLSF_mu_Q15, i32 NLSF_mu_fluc_red_Q16, int deactivate_fluc_red, PredScr* Q) {
+    enum { SURV = 16, NST = 6, ORD = LPC_ORDER, MAXC = 8 };
+    const int lane = SB_LANE;
+    auto& V = Q->u.vq;
+    i32 wq[ORD];
+#pragma unroll
+    for (int m = 0; m < ORD; m++) wq[m] = pW_Q6[m];
+    int cur = 0, nxt = 1;
+    if (lane < ORD) V.res[0][lane] = pNLSF_Q15[lane];
+    if (lane < SURV) { V.rate[0][lane] = 0; V.path_lo[0][lane] = 0; V.path_hi[0][lane] = 0; }
+    SB_SYNC();
+    int prev_survivors = 1, cur_survivors = 0, cb_off = 0;
+    const int min_survivors = SURV / 2;
+    for (int s = 0; s < NST; s++) {
+        const int nVec = cb.nvec[s];
+        const i16* CB = cb.cb_q15 + cb_off * ORD;
+        const i16* Rates = cb.rates_q5 + cb_off;
+        const int ncand = prev_survivors * nVec;
+        cur_survivors = imin(SURV, ncand);
+        // values of my pairs e = lane, lane + 32, ...
+        i32 val[MAXC];
+        i32 mymin = SB_I32_MAX;
+#pragma unroll
+        for (int r = 0; r < MAXC; r++) {
+            const int e = lane + 32 * r;
+            val[r] = SB_I32_MAX;
+            if (e < ncand) {
+                const int n = e / nVec, i = e - n * nVec;
+                const i32* in = &V.res[cur][n * ORD];
+                const i16* v = CB + i * ORD;
+                i32 sum_error = 0;
+#pragma unroll
+                for (int m = 0; m < ORD; m++) { const i32 diff = in[m] - (i32)v[m]; sum_error = smlawb(sum_error, smulbb(diff, diff), wq[m]); }
+                val[r] = smlabb(sum_error, V.rate[cur][n] + Rates[i], NLSF_mu_Q15);
+                mymin = imin(mymin, val[r]);
+            }
+        }
+        // upper bound U for the SURV-th smallest value: the SURV-th smallest of the lanes' minima (>= SURV pairs are <= U)
+        i32 U;
+        {
+            int rank = 0;
+            for (int l = 0; l < 32; l++) { const i32 o = wshfl(mymin, l); rank += (o < mymin) || (o == mymin && l < lane); }
+            const u32 b = wballot(rank == SURV - 1);
+            U = wshfl(mymin, ctz32(b));
+        }
+        // compact the pairs with value <= U in scan order (e ascending)
+        int M = 0;
+#pragma unroll
+        for (int r = 0; r < MAXC; r++) {
+            if (32 * r >= ncand) break;       // uniform
+            const bool on = (lane + 32 * r) < ncand && val[r] <= U;
+            const u32 m = wballot(on);
+            if (on) { const int q = M + popc32(m & ((1u << lane) - 1)); if (q < 64) { V.cand_v[q] = val[r]; V.cand_e[q] = (i16)(lane + 32 * r); } }
+            M += popc32(m);
+        }
+        SB_SYNC();
+        if (M > 64) {
+            // more than 64 pairs share the bound (long runs of equal values): lane 0 replays the reference's sort over everything
+            // it needs the values again; rare enough to recompute them one by one
+            if (lane == 0) {
+                i32 kv[SURV]; int ke[SURV]; int filled = 0;
+                for (int e = 0; e < ncand; e++) {
+                    const int n = e / nVec, i = e - n * nVec;
+                    const i32* in = &V.res[cur][n * ORD];
+                    const i16* v = CB + i * ORD;
+                    i32 sum_error = 0;
+                    for (int m = 0; m < ORD; m++) { const i32 diff = in[m] - (i32)v[m]; sum_error = smlawb(sum_error, smulbb(diff, diff), wq[m]); }
+                    const i32 vv = smlabb(sum_error, V.rate[cur][n] + Rates[i], NLSF_mu_Q15);
+                    if (filled < cur_survivors) {
+                        int jx = filled - 1;
+                        for (; jx >= 0 && vv < kv[jx]; jx--) { kv[jx + 1] = kv[jx]; ke[jx + 1] = ke[jx]; }
+                        kv[jx + 1] = vv; ke[jx + 1] = e; filled++;
+                    } else if (vv < kv[SURV - 1]) {
+                        int jx = SURV - 2;
+                        for (; jx >= 0 && vv < kv[jx]; jx--) { kv[jx + 1] = kv[jx]; ke[jx + 1] = ke[jx]; }
+                        kv[jx + 1] = vv; ke[jx + 1] = e;
+                    }
+                }
+                for (int q = 0; q < cur_survivors; q++) { V.best_v[q] = kv[q]; V.best_e[q] = (i16)ke[q]; }
+            }
+        } else {
+            // rank inside the short list: #{(v', q') < (v, q)}
+            for (int q = lane; q < M; q += 32) {
+                const i32 v = V.cand_v[q];
+                int rank = 0;
+                for (int o = 0; o < M; o++) { const i32 ov = V.cand_v[o]; rank += (ov < v) || (ov == v && o < q); }
+                if (rank < SURV) { V.best_v[rank] = v; V.best_e[rank] = V.cand_e[q]; }
+            }
+        }
+        SB_SYNC();
+        const i32 best0 = V.best_v[0];
+        if (best0 < SB_I32_MAX / SURV) {
+            const i32 thr = smlawb(best0, mulw(SURV, best0), SB_FIXC(0.1f, 16));
+            while (V.best_v[cur_survivors - 1] > thr && cur_survivors > min_survivors) cur_survivors--;
+        }
+        // survivors of this stage: residuals, rates, paths
+        for (int t = lane; t < cur_survivors * ORD; t += 32) {
+            const int kx = t / ORD, m = t - kx * ORD;
+            const int e = V.best_e[kx];
+            const int input_index = s > 0 ? e / nVec : 0, cb_index = s > 0 ? e - input_index * nVec : e;
+            V.res[nxt][kx * ORD + m] = V.res[cur][input_index * ORD + m] - (i32)CB[cb_index * ORD + m];
+        }
+        if (lane < cur_survivors) {
+            const int e = V.best_e[lane];
+            const int input_index = s > 0 ? e / nVec : 0, cb_index = s > 0 ? e - input_index * nVec : e;
+            V.rate[nxt][lane] = V.rate[cur][input_index] + Rates[cb_index];
+            u64 pth = ((u64)V.path_hi[cur][input_index] << 32) | V.path_lo[cur][input_index];
+            pth |= (u64)(u32)cb_index << (8 * s);
+            V.path_lo[nxt][lane] = (u32)pth; V.path_hi[nxt][lane] = (u16)(pth >> 32);
+        }
+        SB_SYNC();
+        cur ^= 1; nxt ^= 1;
+        prev_survivors = cur_survivors;
+        cb_off += nVec;
+    }
+    // survivors now in [cur]; V.best_v holds their rate-distortion values in order
+    i32 bestIndex = 0;
+    if (deactivate_fluc_red != 1) {      // uniform
+        i32 wsse = SB_I32_MAX;
+        if (lane < cur_survivors) {
+            const u64 pth = ((u64)V.path_hi[cur][lane] << 32) | V.path_lo[cur][lane];
+            i32 idx[NST];
+#pragma unroll
+            for (int i = 0; i < NST; i++) idx[i] = (i32)((pth >> (8 * i)) & 0xff);
+            i32* nl = V.nlsf_s[lane];
+            nlsf_msvq_decode(nl, cb, idx);
+            i32 wsse_Q20 = 0;
+            for (int i = 0; i < ORD; i++) {
+                const i32 se = nl[i] - pNLSF_q_Q15_prev[i];
+                wsse_Q20 = smlawb(wsse_Q20, smulbb(se, se), wq[i]);
+            }
+            wsse = add_pos_sat32(V.best_v[lane], smulwb(wsse_Q20, NLSF_mu_fluc_red_Q16));
+        }
+        i32 who = lane;
+        wargmin(wsse, who);       // first of equal minima; a value equal to INT_MAX never wins in the reference either
+        bestIndex = wsse < SB_I32_MAX ? who : 0;
+    }
+    SB_SYNC();
+    const u64 pth = ((u64)V.path_hi[cur][bestIndex] << 32) | V.path_lo[cur][bestIndex];
+    if (lane < NST) NLSFIndices[lane] = (i32)((pth >> (8 * lane)) & 0xff);
+    SB_SYNC();
+    if (lane == 0) {
+        i32 idx[NST], nl[ORD];
+        for (int i = 0; i < NST; i++) idx[i] = NLSFIndices[i];
+        nlsf_msvq_decode(nl, cb, idx);
+        for (int i = 0; i < ORD; i++) pNLSF_Q15[i] = nl[i];
+    }
+    SB_SYNC();
+}
+
+// SKP_Silk_process_NLSFs_FIX (process_NLSFs_FIX.c:31-127)
+SB_FN void c_process_nlsfs(EncSilk* st, EncCtrl* c, i32* pNLSF_Q15, PredScr* Q, const NlsfFastTabs* fast) {
+    const int lane = SB_LANE;
+    const int sigtype = c->sigtype, interpQ2 = c->NLSFInterpCoef_Q2;
+    i32 NLSF_mu_Q15, NLSF_mu_fluc_red_Q16;
+    if (sigtype == 0) {
+        NLSF_mu_Q15 = smlawb(66, -8388, st->speech_activity_Q8);
+        NLSF_mu_fluc_red_Q16 = smlawb(6554, -838848, st->speech_activity_Q8);
+    } else {
+        NLSF_mu_Q15 = smlawb(164, -33554, st->speech_activity_Q8);
+        NLSF_mu_fluc_red_Q16 = smlawb(13107, -1677696, st->speech_activity_Q8 + c->sparseness_Q8);
+    }
+    NLSF_mu_Q15 = imax(NLSF_mu_Q15, 1);
+    const int doInterpolate = interpQ2 < (1 << 2);
+    // Laroia weights: lane 0 for the target vector, lane 1 for the interpolated one (eleven divisions each)
+    if (lane < 2) {
+        i32 nl[LPC_ORDER], w[LPC_ORDER];
+        if (lane == 0) { for (int i = 0; i < LPC_ORDER; i++) nl[i] = pNLSF_Q15[i]; }
+        else { i32 a[LPC_ORDER], b[LPC_ORDER]; for (int i = 0; i < LPC_ORDER; i++) { a[i] = st->prev_NLSFq_Q15[i]; b[i] = pNLSF_Q15[i]; } interpolate(nl, a, b, interpQ2, LPC_ORDER); }
+        nlsf_vq_weights_laroia(w, nl, LPC_ORDER);
+        for (int i = 0; i < LPC_ORDER; i++) Q->u.vq.nlsf_s[lane][i] = w[i];
+    }
+    SB_SYNC();
+    if (lane < LPC_ORDER) {
+        i32 w = Q->u.vq.nlsf_s[0][lane];
+        if (doInterpolate) {
+            const i32 i_sqr_Q15 = shl(smulbb(interpQ2, interpQ2), 11);
+            w = smlawb(w >> 1, Q->u.vq.nlsf_s[1][lane], i_sqr_Q15);
+        }
+        Q->NLSFW_Q6[lane] = w;
+    }
+    SB_SYNC();
+    NlsfCb cb = nlsf_cb(sigtype);
+    if (fast) {
+        cb.cb_q15 = sigtype == 0 ? fast->cb0 : fast->cb1;
+        cb.rates_q5 = sigtype == 0 ? fast->rates0 : fast->rates1;
+    }
+    c_nlsf_msvq_encode(c->NLSFIndices, pNLSF_Q15, cb, st->prev_NLSFq_Q15, Q->NLSFW_Q6, NLSF_mu_Q15, NLSF_mu_fluc_red_Q16,
+                       st->first_frame_after_reset, Q);
+    // quantised NLSFs -> prediction filters of the two half-frames (two lanes)
+    if (lane < 2) {
+        i32 nl[LPC_ORDER];
+        i16 a12[LPC_ORDER];
+        bool need = true;
+        if (lane == 1) { for (int i = 0; i < LPC_ORDER; i++) nl[i] = pNLSF_Q15[i]; }
+        else if (doInterpolate) { i32 a[LPC_ORDER], b[LPC_ORDER]; for (int i = 0; i < LPC_ORDER; i++) { a[i] = st->prev_NLSFq_Q15[i]; b[i] = pNLSF_Q15[i]; } interpolate(nl, a, b, interpQ2, LPC_ORDER); }
+        else { for (int i = 0; i < LPC_ORDER; i++) nl[i] = pNLSF_Q15[i]; need = true; }
+        if (need) nlsf2a_stable(a12, nl, LPC_ORDER);
+        for (int i = 0; i < LPC_ORDER; i++) c->PredCoef_Q12[lane][i] = a12[i];
+    }
+    SB_SYNC();
+}
+
+// SKP_Silk_find_pred_coefs_FIX (find_pred_coefs_FIX.c:31-131)
+SB_FN void c_find_pred_coefs(EncSilk* st, EncCtrl* c, PredScr* Q, const i16* res_pitch, int frame_in_packet, const NlsfFastTabs* fast) {
+    const int lane = SB_LANE;
+    const int sigtype = c->sigtype;
+    {
+        const i32 g = c->Gains_Q16[lane & 3];
+        i32 min_gain_Q16 = SB_I32_MAX >> 6;
+        for (int i = 0; i < NB_SUBFR; i++) min_gain_Q16 = imin(min_gain_Q16, c->Gains_Q16[i]);
+        if (lane < NB_SUBFR) {
+            i32 inv = div32_varq(min_gain_Q16, g, 16 - 2);
+            inv = imax(inv, 363);
+            Q->invGains_Q16[lane] = inv;
+            Q->Wght_Q15[lane] = smulwb(inv, inv) >> 1;
+            Q->local_gains[lane] = (1 << 16) / inv;
+        }
+    }
+    SB_SYNC();
+    const i16* xb = st->x_buf + FRAME - LPC_ORDER;
+    if (sigtype == 0) {       // uniform
+        if (lane < NB_SUBFR)
+            find_ltp_subfr(lane, c->LTPCoef_Q14 + lane * LTP_ORDER, Q->WLTP + lane * LTP_ORDER * LTP_ORDER, &Q->ltp[lane], res_pitch,
+                           res_pitch + (FRAME >> 1), c->pitchL[lane], Q->Wght_Q15[lane]);
+        SB_SYNC();
+        if (lane == 0) find_ltp_tail(c->LTPCoef_Q14, &c->LTPredCodGain_Q7, Q->ltp, Q->Wght_Q15);
+        SB_SYNC();
+        c_quant_ltp_gains(c->LTPCoef_Q14, c->LTPIndex, &c->PERIndex, Q->WLTP, SB_FIXC(0.03f, 8));
+        SB_SERIAL(ltp_scale_ctrl(st, c, frame_in_packet));
+        // SKP_Silk_LTP_analysis_filter_FIX (LTP_analysis_filter_FIX.c:30-80): lanes over outputs
+        for (int t = lane; t < NB_SUBFR * (SUBFR + LPC_ORDER); t += 32) {
+            const int k = t / (SUBFR + LPC_ORDER), i = t - k * (SUBFR + LPC_ORDER);
+            const i16* x_ptr = xb + k * SUBFR;
+            const i16* x_lag_ptr = x_ptr - c->pitchL[k] + i;
+            const i16* Bq = &c->LTPCoef_Q14[k * LTP_ORDER];
+            i32 est = smulbb(x_lag_ptr[LTP_ORDER / 2], Bq[0]);
+#pragma unroll
+            for (int j = 1; j < LTP_ORDER; j++) est = smlabb(est, x_lag_ptr[LTP_ORDER / 2 - j], Bq[j]);
+            est = rshift_round(est, 14);
+            const i32 r = sat16((i32)x_ptr[i] - est);
+            Q->LPC_in_pre[t] = (i16)smulwb(Q->invGains_Q16[k], r);
+        }
+    } else {
+        for (int t = lane; t < NB_SUBFR * (SUBFR + LPC_ORDER); t += 32) {
+            const int k = t / (SUBFR + LPC_ORDER), i = t - k * (SUBFR + LPC_ORDER);
+            Q->LPC_in_pre[t] = (i16)smulwb(Q->invGains_Q16[k], (xb + k * SUBFR)[i]);
+        }
+        if (lane < NB_SUBFR * LTP_ORDER) c->LTPCoef_Q14[lane] = 0;
+        if (lane == 0) c->LTPredCodGain_Q7 = 0;
+    }
+    SB_SYNC();
+    c_find_lpc(Q->NLSF_Q15, &c->NLSFInterpCoef_Q2, st->prev_NLSFq_Q15, 1 * (1 - st->first_frame_after_reset), Q);
+    c_process_nlsfs(st, c, Q->NLSF_Q15, Q, fast);
+    // SKP_Silk_residual_energy_FIX (residual_energy_FIX.c:32-92): both half-frame filters over all lanes, four energies on four lanes
+    {
+        enum { OFF = LPC_ORDER + SUBFR };
+        for (int t = lane; t < 4 * OFF; t += 32) {
+            const int hh = t / (2 * OFF), kx = t - hh * 2 * OFF;
+            const i16* xp = Q->LPC_in_pre + hh * 2 * OFF;
+            const i16* bq = c->PredCoef_Q12[hh];
+            i32 acc = 0;
+#pragma unroll
+            for (int d = 0; d < LPC_ORDER; d++) if (d < kx) acc = addw(acc, (i32)xp[kx - 1 - d] * (i32)bq[d]);
+            Q->u.LPC_res[hh][kx] = (i16)sat16(rshift_round(sub_sat32(shl((i32)xp[kx], 12), acc), 12));
+        }
+        SB_SYNC();
+        if (lane < NB_SUBFR) {
+            const int hh = lane >> 1, jj = lane & 1;
+            i32 nrg, rshift;
+            sum_sqr_shift(&nrg, &rshift, Q->u.LPC_res[hh] + LPC_ORDER + jj * OFF, SUBFR, 0);
+            i32 nq = -rshift;
+            const i32 gn = Q->local_gains[lane];
+            const int lz1 = clz32(nrg) - 1, lz2 = clz32(gn) - 1;
+            i32 tmp32 = shl(gn, lz2);
+            tmp32 = smmul(tmp32, tmp32);
+            c->ResNrg[lane] = smmul(tmp32, shl(nrg, lz1));
+            c->ResNrgQ[lane] = nq + lz1 + 2 * lz2 - 32 - 32;
+        }
+    }
+    SB_SYNC();
+    if (lane < LPC_ORDER) st->prev_NLSFq_Q15[lane] = Q->NLSF_Q15[lane];
+    SB_SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // frame / packet drivers
 // ---------------------------------------------------------------------------------------------------------------------
 // Working set of one stream during a packet (shared memory in the warp-per-stream kernel).
@@ -469,7 +1488,9 @@ struct CoopWork {
     i32 vadFlag;
     union {
         PitchScr pitch;
-        i16 vadX[4 * (FRAME / 2)];
+        ShapeScr shape;
+        PrefScr pref;
+        PredScr pred;
     } u;
 };
 
@@ -485,10 +1506,10 @@ SB_FN void c_encode_frame_analysis(EncSilk* st, CoopWork* W, const i16* pIn, int
     SB_PARFOR(i, 0, FRAME) x_frame[LA_SHAPE + i] = W->pIn_HP[i];   // LP_variable_cutoff is a copy (transition_frame_no == 0)
     SB_SYNC();
     c_find_pitch_lags(st, c, &W->u.pitch, W->res_pitch, x_frame);
+    c_noise_shape_analysis(st, c, &W->u.shape, W->res_pitch + FRAME, x_frame);
+    c_prefilter(st, c, &W->u.pref, W->xfw, x_frame);
+    c_find_pred_coefs(st, c, &W->u.pred, W->res_pitch, frame_in_packet, nullptr);
     SB_SERIAL(
-        noise_shape_analysis(st, c, W->res_pitch + FRAME, x_frame);
-        prefilter(st, c, W->xfw, x_frame);
-        find_pred_coefs(st, c, W->res_pitch, frame_in_packet, nullptr);
         process_gains(st, c, frame_in_packet);
         if (st->speech_activity_Q8 < SB_FIXC(0.1f, 8)) {
             st->vadFlag = 0;

@@ -159,62 +159,59 @@ SB_FN i32 residual_energy16_covar(const i16* c, const i32* wXX, const i32* wXx, 
 
 // ---- SKP_Silk_find_LTP_FIX.c:39-231 -----------------------------------------------------------------------
 // r_first == res_pitch (element offset 0 of a 4-byte aligned buffer), r_last == res_pitch + FRAME/2.
-SB_FN void find_ltp(i16* b_Q14, i32* WLTP, i32* LTPredCodGain_Q7, const i16* r_first, const i16* r_last, const i32* lag,
-                    const i32* Wght_Q15, i32* corr_rshifts) {
+// Split in two so that the cooperative kernel can run the four sub-frames on four lanes: the body of the sub-frame loop
+// (:67-148) and the part that couples the sub-frames (:150-231).
+struct LtpSubfr { i32 rr, nrg, w, corr_rshifts; };
+SB_FN void find_ltp_subfr(int k, i16* b_Q14_ptr, i32* WLTP_ptr, LtpSubfr* o, const i16* r_first, const i16* r_last, i32 lag_k, i32 Wght_Q15_k) {
     const int HEAD = 2;
-    i32 b_Q16[LTP_ORDER], delta_b_Q14[LTP_ORDER], d_Q14[NB_SUBFR], nrg[NB_SUBFR], w[NB_SUBFR], Rr[LTP_ORDER], rr[NB_SUBFR];
-    i16* b_Q14_ptr = b_Q14;
-    i32* WLTP_ptr = WLTP;
-    const i16* r_ptr = &r_first[FRAME];
-    for (int k = 0; k < NB_SUBFR; k++) {
-        if (k == (NB_SUBFR >> 1)) r_ptr = &r_last[FRAME];
-        const i16* lag_ptr = r_ptr - (lag[k] + LTP_ORDER / 2);
-        i32 rr_shifts;
-        sum_sqr_shift(&rr[k], &rr_shifts, r_ptr, SUBFR, 0);
-        int LZs = clz32(rr[k]);
-        if (LZs < HEAD) { rr[k] = rshift_round(rr[k], HEAD - LZs); rr_shifts += (HEAD - LZs); }
-        corr_rshifts[k] = rr_shifts;
-        corr_matrix(lag_ptr, SUBFR, LTP_ORDER, HEAD, WLTP_ptr, &corr_rshifts[k], lag[k] & 1);
-        corr_vector(lag_ptr, r_ptr, SUBFR, LTP_ORDER, Rr, corr_rshifts[k]);
-        if (corr_rshifts[k] > rr_shifts) rr[k] = rr[k] >> (corr_rshifts[k] - rr_shifts);
-        i32 regu = 1;
-        regu = smlawb(regu, rr[k], SB_FIXC(0.01f / 3, 16));
-        regu = smlawb(regu, WLTP_ptr[0], SB_FIXC(0.01f / 3, 16));
-        regu = smlawb(regu, WLTP_ptr[(LTP_ORDER - 1) * LTP_ORDER + LTP_ORDER - 1], SB_FIXC(0.01f / 3, 16));
-        for (int i = 0; i < LTP_ORDER; i++) WLTP_ptr[i * LTP_ORDER + i] = addw(WLTP_ptr[i * LTP_ORDER + i], regu);
-        rr[k] = addw(rr[k], regu);
-        solve_ldl5(WLTP_ptr, Rr, b_Q16);
-        for (int i = 0; i < LTP_ORDER; i++) b_Q14_ptr[i] = (i16)sat16(rshift_round(b_Q16[i], 2));
-        nrg[k] = residual_energy16_covar(b_Q14_ptr, WLTP_ptr, Rr, rr[k]);
-        int extra_shifts = imin(corr_rshifts[k], HEAD);
-        i32 denom32 = addw(lshift_sat32(smulwb(nrg[k], Wght_Q15[k]), 1 + extra_shifts),
-                           smulwb(SUBFR, 655) >> (corr_rshifts[k] - extra_shifts));
-        denom32 = imax(denom32, 1);
-        i32 temp32 = shl(Wght_Q15[k], 16) / denom32;
-        temp32 = temp32 >> (31 + corr_rshifts[k] - extra_shifts - 26);
-        i32 WLTP_max = 0;
-        for (int i = 0; i < LTP_ORDER * LTP_ORDER; i++) WLTP_max = imax(WLTP_ptr[i], WLTP_max);
-        int lshift = clz32(WLTP_max) - 1 - 3;
-        if (26 - 18 + lshift < 31) temp32 = imin(temp32, shl(1, 26 - 18 + lshift));
-        for (int i = 0; i < LTP_ORDER * LTP_ORDER; i++) WLTP_ptr[i] = (i32)(smull(WLTP_ptr[i], temp32) >> 8);
-        w[k] = WLTP_ptr[(LTP_ORDER >> 1) * LTP_ORDER + (LTP_ORDER >> 1)];
-        r_ptr += SUBFR;
-        b_Q14_ptr += LTP_ORDER;
-        WLTP_ptr += LTP_ORDER * LTP_ORDER;
-    }
+    i32 b_Q16[LTP_ORDER], Rr[LTP_ORDER];
+    const i16* r_ptr = (k < (NB_SUBFR >> 1) ? &r_first[FRAME] : &r_last[FRAME] - (NB_SUBFR >> 1) * SUBFR) + k * SUBFR;
+    const i16* lag_ptr = r_ptr - (lag_k + LTP_ORDER / 2);
+    i32 rr, rr_shifts;
+    sum_sqr_shift(&rr, &rr_shifts, r_ptr, SUBFR, 0);
+    int LZs = clz32(rr);
+    if (LZs < HEAD) { rr = rshift_round(rr, HEAD - LZs); rr_shifts += (HEAD - LZs); }
+    i32 corr_rshifts = rr_shifts;
+    corr_matrix(lag_ptr, SUBFR, LTP_ORDER, HEAD, WLTP_ptr, &corr_rshifts, lag_k & 1);
+    corr_vector(lag_ptr, r_ptr, SUBFR, LTP_ORDER, Rr, corr_rshifts);
+    if (corr_rshifts > rr_shifts) rr = rr >> (corr_rshifts - rr_shifts);
+    i32 regu = 1;
+    regu = smlawb(regu, rr, SB_FIXC(0.01f / 3, 16));
+    regu = smlawb(regu, WLTP_ptr[0], SB_FIXC(0.01f / 3, 16));
+    regu = smlawb(regu, WLTP_ptr[(LTP_ORDER - 1) * LTP_ORDER + LTP_ORDER - 1], SB_FIXC(0.01f / 3, 16));
+    for (int i = 0; i < LTP_ORDER; i++) WLTP_ptr[i * LTP_ORDER + i] = addw(WLTP_ptr[i * LTP_ORDER + i], regu);
+    rr = addw(rr, regu);
+    solve_ldl5(WLTP_ptr, Rr, b_Q16);
+    for (int i = 0; i < LTP_ORDER; i++) b_Q14_ptr[i] = (i16)sat16(rshift_round(b_Q16[i], 2));
+    const i32 nrg = residual_energy16_covar(b_Q14_ptr, WLTP_ptr, Rr, rr);
+    int extra_shifts = imin(corr_rshifts, HEAD);
+    i32 denom32 = addw(lshift_sat32(smulwb(nrg, Wght_Q15_k), 1 + extra_shifts), smulwb(SUBFR, 655) >> (corr_rshifts - extra_shifts));
+    denom32 = imax(denom32, 1);
+    i32 temp32 = shl(Wght_Q15_k, 16) / denom32;
+    temp32 = temp32 >> (31 + corr_rshifts - extra_shifts - 26);
+    i32 WLTP_max = 0;
+    for (int i = 0; i < LTP_ORDER * LTP_ORDER; i++) WLTP_max = imax(WLTP_ptr[i], WLTP_max);
+    int lshift = clz32(WLTP_max) - 1 - 3;
+    if (26 - 18 + lshift < 31) temp32 = imin(temp32, shl(1, 26 - 18 + lshift));
+    for (int i = 0; i < LTP_ORDER * LTP_ORDER; i++) WLTP_ptr[i] = (i32)(smull(WLTP_ptr[i], temp32) >> 8);
+    o->rr = rr; o->nrg = nrg; o->corr_rshifts = corr_rshifts;
+    o->w = WLTP_ptr[(LTP_ORDER >> 1) * LTP_ORDER + (LTP_ORDER >> 1)];
+}
+SB_FN void find_ltp_tail(i16* b_Q14, i32* LTPredCodGain_Q7, const LtpSubfr* sf, const i32* Wght_Q15) {
+    i32 delta_b_Q14[LTP_ORDER], d_Q14[NB_SUBFR];
     int maxRshifts = 0;
-    for (int k = 0; k < NB_SUBFR; k++) maxRshifts = imax(corr_rshifts[k], maxRshifts);
+    for (int k = 0; k < NB_SUBFR; k++) maxRshifts = imax(sf[k].corr_rshifts, maxRshifts);
     {
         i32 LPC_LTP_res_nrg = 0, LPC_res_nrg = 0;
         for (int k = 0; k < NB_SUBFR; k++) {
-            LPC_res_nrg = addw(LPC_res_nrg, addw(smulwb(rr[k], Wght_Q15[k]), 1) >> (1 + (maxRshifts - corr_rshifts[k])));
-            LPC_LTP_res_nrg = addw(LPC_LTP_res_nrg, addw(smulwb(nrg[k], Wght_Q15[k]), 1) >> (1 + (maxRshifts - corr_rshifts[k])));
+            LPC_res_nrg = addw(LPC_res_nrg, addw(smulwb(sf[k].rr, Wght_Q15[k]), 1) >> (1 + (maxRshifts - sf[k].corr_rshifts)));
+            LPC_LTP_res_nrg = addw(LPC_LTP_res_nrg, addw(smulwb(sf[k].nrg, Wght_Q15[k]), 1) >> (1 + (maxRshifts - sf[k].corr_rshifts)));
         }
         LPC_LTP_res_nrg = imax(LPC_LTP_res_nrg, 1);
         i32 div_Q16 = div32_varq(LPC_res_nrg, LPC_LTP_res_nrg, 16);
         *LTPredCodGain_Q7 = smulbb(3, lin2log(div_Q16) - (16 << 7));
     }
-    b_Q14_ptr = b_Q14;
+    i16* b_Q14_ptr = b_Q14;
     for (int k = 0; k < NB_SUBFR; k++) {
         d_Q14[k] = 0;
         for (int i = 0; i < LTP_ORDER; i++) d_Q14[k] += b_Q14_ptr[i];
@@ -223,7 +220,7 @@ SB_FN void find_ltp(i16* b_Q14, i32* WLTP, i32* LTPredCodGain_Q7, const i16* r_f
     i32 max_abs_d_Q14 = 0, max_w_bits = 0;
     for (int k = 0; k < NB_SUBFR; k++) {
         max_abs_d_Q14 = imax(max_abs_d_Q14, iabs(d_Q14[k]));
-        max_w_bits = imax(max_w_bits, 32 - clz32(w[k]) + corr_rshifts[k] - maxRshifts);
+        max_w_bits = imax(max_w_bits, 32 - clz32(sf[k].w) + sf[k].corr_rshifts - maxRshifts);
     }
     int extra_shifts = max_w_bits + 32 - clz32(max_abs_d_Q14) - 14;
     extra_shifts -= (32 - 1 - 2 + maxRshifts);
@@ -232,14 +229,14 @@ SB_FN void find_ltp(i16* b_Q14, i32* WLTP, i32* LTPredCodGain_Q7, const i16* r_f
     i32 temp32 = (262 >> (maxRshifts + extra_shifts)) + 1;
     i32 wd = 0;
     for (int k = 0; k < NB_SUBFR; k++) {
-        temp32 = addw(temp32, w[k] >> (maxRshifts_wxtra - corr_rshifts[k]));
-        wd = addw(wd, shl(smulww(w[k] >> (maxRshifts_wxtra - corr_rshifts[k]), d_Q14[k]), 2));
+        temp32 = addw(temp32, sf[k].w >> (maxRshifts_wxtra - sf[k].corr_rshifts));
+        wd = addw(wd, shl(smulww(sf[k].w >> (maxRshifts_wxtra - sf[k].corr_rshifts), d_Q14[k]), 2));
     }
     i32 m_Q12 = div32_varq(wd, temp32, 12);
     b_Q14_ptr = b_Q14;
     for (int k = 0; k < NB_SUBFR; k++) {
-        if (2 - corr_rshifts[k] > 0) temp32 = w[k] >> (2 - corr_rshifts[k]);
-        else temp32 = lshift_sat32(w[k], corr_rshifts[k] - 2);
+        if (2 - sf[k].corr_rshifts > 0) temp32 = sf[k].w >> (2 - sf[k].corr_rshifts);
+        else temp32 = lshift_sat32(sf[k].w, sf[k].corr_rshifts - 2);
         i32 g_Q26 = mulw(SB_FIXC(0.1f, 26) / ((SB_FIXC(0.1f, 26) >> 10) + temp32),
                          lshift_sat32(sub_sat32(m_Q12, d_Q14[k] >> 2), 4));
         temp32 = 0;
@@ -253,40 +250,54 @@ SB_FN void find_ltp(i16* b_Q14, i32* WLTP, i32* LTPredCodGain_Q7, const i16* r_f
         b_Q14_ptr += LTP_ORDER;
     }
 }
+SB_FN void find_ltp(i16* b_Q14, i32* WLTP, i32* LTPredCodGain_Q7, const i16* r_first, const i16* r_last, const i32* lag,
+                    const i32* Wght_Q15, i32* corr_rshifts) {
+    LtpSubfr sf[NB_SUBFR];
+    for (int k = 0; k < NB_SUBFR; k++) {
+        find_ltp_subfr(k, b_Q14 + k * LTP_ORDER, WLTP + k * LTP_ORDER * LTP_ORDER, &sf[k], r_first, r_last, lag[k], Wght_Q15[k]);
+        corr_rshifts[k] = sf[k].corr_rshifts;
+    }
+    find_ltp_tail(b_Q14, LTPredCodGain_Q7, sf, Wght_Q15);
+}
 
 // ---- SKP_Silk_VQ_nearest_neighbor_FIX.c:31-159 (scalar form of the packed arithmetic) -----------------------
+// weighted error + rate cost of one code vector (row) for input in_Q14
+SB_HD i32 vq_wmat_ec_entry(const i16* in_Q14, const i32* W_Q18, const i16* row, i32 cl_Q6, i32 mu_Q8) {
+    i32 d0 = (i16)(in_Q14[0] - row[0]), d1 = (i16)(in_Q14[1] - row[1]), d2 = (i16)(in_Q14[2] - row[2]);
+    i32 d3 = (i16)(in_Q14[3] - row[3]), d4 = (i16)(in_Q14[4] - row[4]);
+    i32 sum1 = smulbb(mu_Q8, cl_Q6);
+    i32 sum2 = smulwb(W_Q18[1], d1);
+    sum2 = smlawb(sum2, W_Q18[2], d2);
+    sum2 = smlawb(sum2, W_Q18[3], d3);
+    sum2 = smlawb(sum2, W_Q18[4], d4);
+    sum2 = shl(sum2, 1);
+    sum2 = smlawb(sum2, W_Q18[0], d0);
+    sum1 = smlawb(sum1, sum2, d0);
+    sum2 = smulwb(W_Q18[7], d2);
+    sum2 = smlawb(sum2, W_Q18[8], d3);
+    sum2 = smlawb(sum2, W_Q18[9], d4);
+    sum2 = shl(sum2, 1);
+    sum2 = smlawb(sum2, W_Q18[6], d1);
+    sum1 = smlawb(sum1, sum2, d1);
+    sum2 = smulwb(W_Q18[13], d3);
+    sum2 = smlawb(sum2, W_Q18[14], d4);
+    sum2 = shl(sum2, 1);
+    sum2 = smlawb(sum2, W_Q18[12], d2);
+    sum1 = smlawb(sum1, sum2, d2);
+    sum2 = smulwb(W_Q18[19], d4);
+    sum2 = shl(sum2, 1);
+    sum2 = smlawb(sum2, W_Q18[18], d3);
+    sum1 = smlawb(sum1, sum2, d3);
+    sum2 = smulwb(W_Q18[24], d4);
+    sum1 = smlawb(sum1, sum2, d4);
+    return sum1;
+}
 SB_FN void vq_wmat_ec(i32* ind, i32* rate_dist_Q14, const i16* in_Q14, const i32* W_Q18, const i16* cb_Q14, const i16* cl_Q6,
                       i32 mu_Q8, int L) {
     *rate_dist_Q14 = SB_I32_MAX;
     const i16* row = cb_Q14;
     for (int k = 0; k < L; k++) {
-        i32 d0 = (i16)(in_Q14[0] - row[0]), d1 = (i16)(in_Q14[1] - row[1]), d2 = (i16)(in_Q14[2] - row[2]);
-        i32 d3 = (i16)(in_Q14[3] - row[3]), d4 = (i16)(in_Q14[4] - row[4]);
-        i32 sum1 = smulbb(mu_Q8, cl_Q6[k]);
-        i32 sum2 = smulwb(W_Q18[1], d1);
-        sum2 = smlawb(sum2, W_Q18[2], d2);
-        sum2 = smlawb(sum2, W_Q18[3], d3);
-        sum2 = smlawb(sum2, W_Q18[4], d4);
-        sum2 = shl(sum2, 1);
-        sum2 = smlawb(sum2, W_Q18[0], d0);
-        sum1 = smlawb(sum1, sum2, d0);
-        sum2 = smulwb(W_Q18[7], d2);
-        sum2 = smlawb(sum2, W_Q18[8], d3);
-        sum2 = smlawb(sum2, W_Q18[9], d4);
-        sum2 = shl(sum2, 1);
-        sum2 = smlawb(sum2, W_Q18[6], d1);
-        sum1 = smlawb(sum1, sum2, d1);
-        sum2 = smulwb(W_Q18[13], d3);
-        sum2 = smlawb(sum2, W_Q18[14], d4);
-        sum2 = shl(sum2, 1);
-        sum2 = smlawb(sum2, W_Q18[12], d2);
-        sum1 = smlawb(sum1, sum2, d2);
-        sum2 = smulwb(W_Q18[19], d4);
-        sum2 = shl(sum2, 1);
-        sum2 = smlawb(sum2, W_Q18[18], d3);
-        sum1 = smlawb(sum1, sum2, d3);
-        sum2 = smulwb(W_Q18[24], d4);
-        sum1 = smlawb(sum1, sum2, d4);
+        const i32 sum1 = vq_wmat_ec_entry(in_Q14, W_Q18, row, cl_Q6[k], mu_Q8);
         if (sum1 < *rate_dist_Q14) { *rate_dist_Q14 = sum1; *ind = k; }
         row += LTP_ORDER;
     }

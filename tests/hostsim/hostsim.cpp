@@ -25,6 +25,9 @@ void barrier() {
     lane = (me + 1) & 31;
     swapcontext(&ctx[me], &ctx[lane]);
     lane = me;
+    if (me == 0)      // a full round has passed: every lane must have arrived at its barrier number nbar[0]
+        for (int i = 1; i < 32; i++)
+            if (nbar[i] != nbar[0]) { fprintf(stderr, "emu: divergent collective -- lane %d is at barrier %ld, lane 0 at %ld\n", i, nbar[i], nbar[0]); abort(); }
 }
 long long* scratch() { return scr; }
 static void entry() { body(); }
