@@ -40,7 +40,7 @@ SB_HD int ctz32(u32 x) {   // x != 0
 }
 // Zero-state FIR (SKP_Silk_MA_Prediction / SKP_Silk_LPC_analysis_filter with a cleared state, SKP_Silk_MA.c:41-118):
 // out[k] = sat16(rshift_round((in[k] << 12) - sum_{d < min(ORD, k)} B[d] * in[k-1-d], 12)); lanes over outputs.
-template <int ORD, bool SAT> SB_FN void c_fir_zero_state(const i16* in, const i16* B_Q12, i16* out, int len) {
+template <int ORD, bool SAT> SB_CFN void c_fir_zero_state(const i16* in, const i16* B_Q12, i16* out, int len) {
     i32 b[ORD];
 #pragma unroll
     for (int d = 0; d < ORD; d++) b[d] = B_Q12[d];
@@ -63,7 +63,7 @@ template <int ORD, bool SAT> SB_FN void c_fir_zero_state(const i16* in, const i1
 // shifting once the running sum reaches bit 31; the running sums are monotone, so when the exact total stays below 2^31
 // no shift ever happened and the result follows from the total (lanes over terms).  Otherwise lane 0 replays the scalar
 // routine.  All lanes return the same values.
-SB_FN void c_sum_sqr_shift(i32* energy, i32* shift, const i16* x, int len, int odd_start) {
+SB_CFN void c_sum_sqr_shift(i32* energy, i32* shift, const i16* x, int len, int odd_start) {
     i64 part = 0;
     SB_PARFOR(i, 0, len) part += (i64)((i32)x[i] * (i32)x[i]);
     const i64 total = wsum64(part);
@@ -81,7 +81,7 @@ SB_FN void c_sum_sqr_shift(i32* energy, i32* shift, const i16* x, int len, int o
 
 // SKP_Silk_schur (schur.c:40-93), order <= 31: lane n keeps C[n][1] and C[n+k+1][0] in registers; the second slides down
 // one lane per step.  c: correlations (shared memory); rc_Q15: shared; returns the residual energy on every lane.
-SB_FN i32 c_schur(i16* rc_Q15, const i32* c, int order) {
+SB_CFN i32 c_schur(i16* rc_Q15, const i32* c, int order) {
     const int lane = SB_LANE;
     const int lz = clz32(c[0]);
     i32 a = 0, b = 0;
@@ -101,7 +101,7 @@ SB_FN i32 c_schur(i16* rc_Q15, const i32* c, int order) {
     return wbcast(a, 0);
 }
 // SKP_Silk_schur64 (schur64.c:42-91)
-SB_FN i32 c_schur64(i32* rc_Q16, const i32* c, int order) {
+SB_CFN i32 c_schur64(i32* rc_Q16, const i32* c, int order) {
     const int lane = SB_LANE;
     if (c[0] <= 0) {        // uniform
         if (lane < order) rc_Q16[lane] = 0;
@@ -123,7 +123,7 @@ SB_FN i32 c_schur64(i32* rc_Q16, const i32* c, int order) {
     return wbcast(a, 0);
 }
 // SKP_Silk_k2a (k2a.c:40-60): lane n keeps A[n]; returns it (valid for n < order).  rc_Q15: shared memory.
-SB_FN i32 c_k2a(const i16* rc_Q15, int order) {
+SB_CFN i32 c_k2a(const i16* rc_Q15, int order) {
     const int lane = SB_LANE;
     i32 A = 0;
     for (int k = 0; k < order; k++) {
@@ -135,7 +135,7 @@ SB_FN i32 c_k2a(const i16* rc_Q15, int order) {
     return A;
 }
 // SKP_Silk_k2a_Q16 (k2a_Q16.c:40-60)
-SB_FN i32 c_k2a_q16(const i32* rc_Q16, int order) {
+SB_CFN i32 c_k2a_q16(const i32* rc_Q16, int order) {
     const int lane = SB_LANE;
     i32 A = 0;
     for (int k = 0; k < order; k++) {
@@ -147,7 +147,7 @@ SB_FN i32 c_k2a_q16(const i32* rc_Q16, int order) {
     return A;
 }
 // chirp factor that SKP_Silk_bwexpander (bwexpander.c:31-48) applies to coefficient `lane` (d coefficients)
-SB_FN i32 c_bwexpander_chirp16(int d, i32 chirp_Q16) {
+SB_CFN i32 c_bwexpander_chirp16(int d, i32 chirp_Q16) {
     const int lane = SB_LANE;
     const i32 cm1 = chirp_Q16 - 65536;
     i32 mine = chirp_Q16;
@@ -159,7 +159,7 @@ SB_FN i32 c_bwexpander_chirp16(int d, i32 chirp_Q16) {
     return mine;
 }
 // factor that SKP_Silk_bwexpander_32 (bwexpander_32.c:31-47) multiplies into coefficient `lane`
-SB_FN i32 c_bwexpander32_factor(int d, i32 chirp_Q16) {
+SB_CFN i32 c_bwexpander32_factor(int d, i32 chirp_Q16) {
     const int lane = SB_LANE;
     i32 t = chirp_Q16, mine = chirp_Q16;
     for (int i = 0; i < d - 1; i++) {
@@ -188,7 +188,7 @@ struct PitchScr {
     i16 A_Q12[16];
 };
 
-SB_FN int c_pitch_analysis_core(PitchScr* P, const i16* signal, i32* pitch_out, i32* lagIndex, i32* contourIndex, i32* LTPCorr_Q15,
+SB_CFN int c_pitch_analysis_core(PitchScr* P, const i16* signal, i32* pitch_out, i32* lagIndex, i32* contourIndex, i32* LTPCorr_Q15,
                                 i32 prevLag, i32 search_thres1_Q16, i32 search_thres2_Q15) {
     enum { FL8 = 320, FL4 = 160, SF8 = 40, MINL8 = 16, MAXL8 = 144, MINL4 = 8, MAXL4 = 72, NCB = 11, NL4 = MAXL4 - MINL4 + 1 };
     const int lane = SB_LANE;
@@ -396,7 +396,7 @@ SB_FN int c_pitch_analysis_core(PitchScr* P, const i16* signal, i32* pitch_out, 
 }
 
 // x points at x_buf + FRAME; res receives 336 samples of LPC residual.  All lanes return (and c gets) the signal type.
-SB_FN void c_find_pitch_lags(EncSilk* st, EncCtrl* c, PitchScr* P, i16* res, const i16* x) {
+SB_CFN void c_find_pitch_lags(EncSilk* st, EncCtrl* c, PitchScr* P, i16* res, const i16* x) {
     enum { BUF_LEN = LA_PITCH + 2 * FRAME, ORD = 10 };
     const int lane = SB_LANE;
     const i16* x_buf = x - FRAME;
@@ -450,6 +450,7 @@ SB_FN void c_find_pitch_lags(EncSilk* st, EncCtrl* c, PitchScr* P, i16* res, con
     thrhld_Q15 = sat16(thrhld_Q15);
     const i32 prevLag = st->prevLag;
     SB_SYNC();
+    SB_PHASE();
     const int sigtype = c_pitch_analysis_core(P, res, c->pitchL, &c->lagIndex, &c->contourIndex, &st->LTPCorr_Q15, prevLag,
                                               SB_FIXC(0.7f, 16), (i16)thrhld_Q15);
     if (lane == 0) { c->sigtype = sigtype; c->predGain_Q16 = predGain; }
@@ -468,7 +469,7 @@ struct ShapeScr {
 // Warped autocorrelation of the four shaping windows at once (SKP_Silk_warped_autocorrelation_FIX.c:36-85): the 16
 // all-pass sections run as a wavefront, lane g of an 8-lane group owns sections 2g and 2g+1 of its window and works on
 // sample t - g at step t; a section's right-hand state is its own previous output, so one shuffle per step suffices.
-SB_FN void c_warped_autocorr4(ShapeScr* S, i32 warping_Q16) {
+SB_CFN void c_warped_autocorr4(ShapeScr* S, i32 warping_Q16) {
     const int QC = 10, QS = 14;
     const int lane = SB_LANE, g = lane & 7, win = lane >> 3;
     const i16* input = S->xw[win];
@@ -504,7 +505,7 @@ SB_FN void c_warped_autocorr4(ShapeScr* S, i32 warping_Q16) {
 }
 
 // pitch_res points at res_pitch + FRAME, x at x_buf + FRAME.
-SB_FN void c_noise_shape_analysis(EncSilk* st, EncCtrl* c, ShapeScr* S, const i16* pitch_res, const i16* x) {
+SB_CFN void c_noise_shape_analysis(EncSilk* st, EncCtrl* c, ShapeScr* S, const i16* pitch_res, const i16* x) {
     const int lane = SB_LANE;
     // ---- scalars, computed by every lane from shared data; lane 0 stores ----
     const i32 sigtype = c->sigtype;
@@ -566,8 +567,10 @@ SB_FN void c_noise_shape_analysis(EncSilk* st, EncCtrl* c, ShapeScr* S, const i1
         }
     }
     SB_SYNC();
+    SB_PHASE();
     c_warped_autocorr4(S, warping_Q16);
     SB_SYNC();
+    SB_PHASE();
     // ---- per window: reflection coefficients, shaping filters, gains -- one window per lane (lanes 0..3) ----
     i32 gain_k = 0, gains_pre_k = 0;
     if (lane < NB_SUBFR) {
@@ -685,7 +688,7 @@ struct PrefScr {
     i32 par[NB_SUBFR][6];      // per sub-frame: B0, B1, Tilt_Q14, LF_shp_Q14, HarmShapeFIRPacked_Q12, lag
 };
 
-SB_FN void c_prefilter(EncSilk* st, const EncCtrl* c, PrefScr* S, i16* xw, const i16* x) {
+SB_CFN void c_prefilter(EncSilk* st, const EncCtrl* c, PrefScr* S, i16* xw, const i16* x) {
     const int lane = SB_LANE;
     // ---- warped LPC analysis filter over the whole frame: wavefront, lane j = all-pass section j (16 lanes) ----
     {
@@ -786,7 +789,7 @@ SB_FN void c_prefilter(EncSilk* st, const EncCtrl* c, PrefScr* S, i16* xw, const
 struct BurgScr {
     i32 cfr[2][NB_SUBFR][16];    // per block: first-row correlations before they are summed over the blocks
 };
-template <int D> SB_FN void c_burg2(i32* res_nrg, i32* res_nrg_Q, i32 (*A_Q16)[16], BurgScr* B, const i16* x0, int nb0, const i16* x1, int nb1, int L,
+template <int D> SB_CFN void c_burg2(i32* res_nrg, i32* res_nrg_Q, i32 (*A_Q16)[16], BurgScr* B, const i16* x0, int nb0, const i16* x1, int nb1, int L,
                                     i32 WhiteNoiseFrac_Q32) {
     const int QA = 25, MAX_RSHIFTS = 32 - QA, MIN_RSHIFTS = -16, HEAD = 2;
     const int lane = SB_LANE, h = lane >> 4, k = lane & 15, base = h << 4;
@@ -930,7 +933,7 @@ template <int D> SB_FN void c_burg2(i32* res_nrg, i32* res_nrg_Q, i32 (*A_Q16)[1
 // collected as bit masks, the walk becomes a scan for the next set bit, and the d bisections run on d lanes.
 // a_Q16: shared memory (modified when the root search has to widen the bandwidth); NLSF: shared memory.
 struct A2nlsfScr { i32 y[2][132]; i32 k_of[16]; i32 ylo_of[16]; };
-template <int D> SB_FN void c_a2nlsf(i32* NLSF, i32* a_Q16, A2nlsfScr* Z) {
+template <int D> SB_CFN void c_a2nlsf(i32* NLSF, i32* a_Q16, A2nlsfScr* Z) {
     enum { DD = D / 2, BIN = 3, TABSZ = 128, MAX_ITER = 30 };
     const int lane = SB_LANE;
     const i32* cosv = SB_T(lsf_cos_q12);
@@ -1080,7 +1083,7 @@ struct PredScr {
 };
 
 // SKP_Silk_quant_LTP_gains_FIX (quant_LTP_gains_FIX.c:30-103): 8 lanes per sub-frame walk each codebook
-SB_FN void c_quant_ltp_gains(i16* B_Q14, i32* cbk_index, i32* periodicity_index, const i32* W_Q18, i32 mu_Q8) {
+SB_CFN void c_quant_ltp_gains(i16* B_Q14, i32* cbk_index, i32* periodicity_index, const i32* W_Q18, i32 mu_Q8) {
     const int lane = SB_LANE, j = lane >> 3, g = lane & 7;
     i32 best_rd = SB_I32_MAX, best_k = 0, best_idx = 0;
     const i16* in = B_Q14 + j * LTP_ORDER;
@@ -1109,7 +1112,7 @@ SB_FN void c_quant_ltp_gains(i16* B_Q14, i32* cbk_index, i32* periodicity_index,
 }
 
 // SKP_Silk_find_LPC_FIX (find_LPC_FIX.c:32-148), order 10, four blocks of 50 samples in x
-SB_FN void c_find_lpc(i32* NLSF_Q15, i32* interpIndex, const i32* prev_NLSFq_Q15, int useInterp, PredScr* Q) {
+SB_CFN void c_find_lpc(i32* NLSF_Q15, i32* interpIndex, const i32* prev_NLSFq_Q15, int useInterp, PredScr* Q) {
     enum { ORD = LPC_ORDER, SL = SUBFR + LPC_ORDER };
     const int lane = SB_LANE, h = lane >> 4;
     const i16* x = Q->LPC_in_pre;
@@ -1189,7 +1192,7 @@ SB_FN void c_find_lpc(i32* NLSF_Q15, i32* interpIndex, const i32* prev_NLSFq_Q15
 // Stage: lanes over (survivor, code vector) pairs; the 16 best pairs by (value, scan position) -- what the reference's stable
 // partial insertion sort returns -- are found by bounding the 16th value with the lanes' own minima, compacting the pairs
 // below the bound in scan order and ranking that short list.
-SB_FN void c_nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb, const i32* pNLSF_q_Q15_prev, const i32* pW_Q6,
+SB_CFN void c_nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb, const i32* pNLSF_q_Q15_prev, const i32* pW_Q6,
                               i32 NLSF_mu_Q15, i32 NLSF_mu_fluc_red_Q16, int deactivate_fluc_red, PredScr* Q) {
     enum { SURV = 16, NST = 6, ORD = LPC_ORDER, MAXC = 8 };
     const int lane = SB_LANE;
@@ -1341,7 +1344,7 @@ SB_FN void c_nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb
 }
 
 // SKP_Silk_process_NLSFs_FIX (process_NLSFs_FIX.c:31-127)
-SB_FN void c_process_nlsfs(EncSilk* st, EncCtrl* c, i32* pNLSF_Q15, PredScr* Q, const NlsfFastTabs* fast) {
+SB_CFN void c_process_nlsfs(EncSilk* st, EncCtrl* c, i32* pNLSF_Q15, PredScr* Q, const NlsfFastTabs* fast) {
     const int lane = SB_LANE;
     const int sigtype = c->sigtype, interpQ2 = c->NLSFInterpCoef_Q2;
     i32 NLSF_mu_Q15, NLSF_mu_fluc_red_Q16;
@@ -1394,7 +1397,7 @@ SB_FN void c_process_nlsfs(EncSilk* st, EncCtrl* c, i32* pNLSF_Q15, PredScr* Q, 
 }
 
 // SKP_Silk_find_pred_coefs_FIX (find_pred_coefs_FIX.c:31-131)
-SB_FN void c_find_pred_coefs(EncSilk* st, EncCtrl* c, PredScr* Q, const i16* res_pitch, int frame_in_packet, const NlsfFastTabs* fast) {
+SB_CFN void c_find_pred_coefs(EncSilk* st, EncCtrl* c, PredScr* Q, const i16* res_pitch, int frame_in_packet, const NlsfFastTabs* fast) {
     const int lane = SB_LANE;
     const int sigtype = c->sigtype;
     {
@@ -1442,8 +1445,11 @@ SB_FN void c_find_pred_coefs(EncSilk* st, EncCtrl* c, PredScr* Q, const i16* res
         if (lane == 0) c->LTPredCodGain_Q7 = 0;
     }
     SB_SYNC();
+    SB_PHASE();
     c_find_lpc(Q->NLSF_Q15, &c->NLSFInterpCoef_Q2, st->prev_NLSFq_Q15, 1 * (1 - st->first_frame_after_reset), Q);
+    SB_PHASE();
     c_process_nlsfs(st, c, Q->NLSF_Q15, Q, fast);
+    SB_PHASE();
     // SKP_Silk_residual_energy_FIX (residual_energy_FIX.c:32-92): both half-frame filters over all lanes, four energies on four lanes
     {
         enum { OFF = LPC_ORDER + SUBFR };
@@ -1476,6 +1482,100 @@ SB_FN void c_find_pred_coefs(EncSilk* st, EncCtrl* c, PredScr* Q, const i16* res
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// high band (AGR_BWE_encode_frame_FIX.c:8-82 first half, AGR_BWE_find_HB_LPC_FIX.c:4-49, AGR_BWE_quant_highband.c:23-104)
+// ---------------------------------------------------------------------------------------------------------------------
+struct HbScr {
+    alignas(4) i16 LPC_in_pre[4 * (80 + HB_ORDER)];
+    i32 A_Q16[2][16];
+    i32 NLSF_Q15[HB_ORDER + 2];
+    i32 weight[HB_ORDER];
+    i16 coef[HB_ORDER];
+    union { BurgScr burg; A2nlsfScr a2n; } u;
+};
+// One high-band frame of F samples: buffer update, order-8 LPC (Burg over four 88-sample blocks), two-stage LSP VQ,
+// residual energy per sub-frame.  hb, H: shared memory; high: the new samples; outputs: global memory.
+template <int F> SB_CFN void c_hb_analyse_frame(EncBands* hb, HbScr* H, const i16* high, i32* lsp_idx_out, i32* nrg0_out) {
+    enum { LPCF = 80, BL = LPCF + HB_ORDER, SF = F >> 2 };
+    const int lane = SB_LANE;
+    SB_PARFOR(i, 0, F) hb->x_hb_buf[F + 40 + i] = high[i];
+    SB_SYNC();
+    SB_PARFOR(t, 0, 4 * BL) { const int k = t / BL, i = t - k * BL; H->LPC_in_pre[t] = hb->x_hb_buf[F - HB_ORDER + k * LPCF + i]; }
+    SB_SYNC();
+    i32 rn, rq;
+    c_burg2<HB_ORDER>(&rn, &rq, H->A_Q16, &H->u.burg, H->LPC_in_pre, 4, H->LPC_in_pre, 4, BL, SB_FIXC(2.5e-5f, 32));
+    SB_SYNC();
+    {
+        const i32 f = c_bwexpander32_factor(HB_ORDER, SB_FIXC(0.99995f, 16));
+        if (lane < HB_ORDER) H->A_Q16[0][lane] = smulww(H->A_Q16[0][lane], f);
+    }
+    SB_SYNC();
+    c_a2nlsf<HB_ORDER>(H->NLSF_Q15, H->A_Q16[0], &H->u.a2n);
+    // ---- AGR_Sate_lsp_quant_highband: 256-entry first stage over the lanes, 16-entry weighted second stage ----
+    if (lane == 0) { i32 w[HB_ORDER], nl[HB_ORDER]; for (int i = 0; i < HB_ORDER; i++) nl[i] = H->NLSF_Q15[i]; nlsf_vq_weights_laroia(w, nl, HB_ORDER); for (int i = 0; i < HB_ORDER; i++) H->weight[i] = w[i]; }
+    SB_SYNC();
+    i32 lsp[HB_ORDER];
+#pragma unroll
+    for (int j = 0; j < HB_ORDER; j++) lsp[j] = H->NLSF_Q15[j];
+    const i16* cb1 = SB_T(hb_lsp_cb1_fix);
+    const i16* cb2 = SB_T(hb_lsp_cb2_fix);
+    i32 best = SB_I32_MAX, idx1 = 0;
+    for (int e = lane; e < 256; e += 32) {
+        i32 dist = 0;
+#pragma unroll
+        for (int j = 0; j < HB_ORDER; j++) { const i32 t = lsp[j] - cb1[e * HB_ORDER + j]; dist = smlabb(dist, t, t); }
+        if (dist < best) { best = dist; idx1 = e; }
+    }
+    wargmin(best, idx1);
+#pragma unroll
+    for (int j = 0; j < HB_ORDER; j++) lsp[j] -= cb1[idx1 * HB_ORDER + j];
+    i32 best2 = SB_I32_MAX, idx2 = lane;
+    if (lane < 16) {
+        i32 dist = 0;
+#pragma unroll
+        for (int j = 0; j < HB_ORDER; j++) { const i32 t = subw(lsp[j], cb2[lane * HB_ORDER + j]); dist = smlawb(dist, smulbb(t, t), H->weight[j]); }
+        best2 = dist;
+    }
+    wargmin(best2, idx2);
+    if (best2 == SB_I32_MAX) idx2 = 0;      // the reference's strict comparison never accepts INT_MAX
+    SB_SYNC();
+    if (lane < HB_ORDER) H->NLSF_Q15[lane] = (i32)cb1[idx1 * HB_ORDER + lane] + (i32)cb2[idx2 * HB_ORDER + lane];
+    if (lane == 0) *lsp_idx_out = shl(idx2, 8) + idx1;
+    SB_SYNC();
+    if (lane == 0) { i32 nl[HB_ORDER]; i16 a12[HB_ORDER]; for (int i = 0; i < HB_ORDER; i++) nl[i] = H->NLSF_Q15[i]; nlsf2a_stable(a12, nl, HB_ORDER); for (int i = 0; i < HB_ORDER; i++) H->coef[i] = a12[i]; }
+    SB_SYNC();
+    // ---- residual energy of the four sub-frames (zero-state analysis filter per sub-frame) ----
+    {
+        i32 b[HB_ORDER];
+#pragma unroll
+        for (int d = 0; d < HB_ORDER; d++) b[d] = H->coef[d];
+        const i16* p_hb = hb->x_hb_buf + F;
+        i32 e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+        SB_PARFOR(t, 0, 4 * SF) {
+            const int sub = t / SF, kx = t - sub * SF;
+            const i16* in = p_hb + sub * SF;
+            i32 acc = 0;
+#pragma unroll
+            for (int d = 0; d < HB_ORDER; d++) if (d < kx) acc = addw(acc, (i32)in[kx - 1 - d] * b[d]);
+            const i32 ex = sat16(rshift_round(sub_sat32(shl((i32)in[kx], 12), acc), 12));
+            const i32 sq = ex * ex;
+            if (sub == 0) e0 = addw(e0, sq); else if (sub == 1) e1 = addw(e1, sq); else if (sub == 2) e2 = addw(e2, sq); else e3 = addw(e3, sq);
+        }
+        e0 = wsum(e0); e1 = wsum(e1); e2 = wsum(e2); e3 = wsum(e3);
+        if (lane < 4) nrg0_out[lane] = sqrt_approx(lane == 0 ? e0 : (lane == 1 ? e1 : (lane == 2 ? e2 : e3)));
+    }
+    SB_SYNC();
+    // buffer slides by one frame: [0,F) <- [F,2F), then [F,F+40) <- [2F,2F+40)
+    {
+        i32* xb = reinterpret_cast<i32*>(hb->x_hb_buf);
+        SB_PARFOR(i, 0, F / 2) xb[i] = xb[F / 2 + i];
+        SB_SYNC();
+        SB_PARFOR(i, 0, 20) xb[F / 2 + i] = xb[F + i];
+        if (lane == 0) hb->hb_first = 0;
+        SB_SYNC();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // frame / packet drivers
 // ---------------------------------------------------------------------------------------------------------------------
 // Working set of one stream during a packet (shared memory in the warp-per-stream kernel).
@@ -1495,7 +1595,7 @@ struct CoopWork {
 };
 
 // SKP_Silk_encode_frame_FIX (encode_frame_FIX.c:34-131, 151-165, 199-208) up to the quantiser, one 20 ms frame.
-SB_FN void c_encode_frame_analysis(EncSilk* st, CoopWork* W, const i16* pIn, int frame_in_packet) {
+SB_CFN void c_encode_frame_analysis(EncSilk* st, CoopWork* W, const i16* pIn, int frame_in_packet, const NlsfFastTabs* fast) {
     EncCtrl* c = &W->c;
     i16* x_frame = st->x_buf + FRAME;
     SB_SERIAL(
@@ -1505,43 +1605,35 @@ SB_FN void c_encode_frame_analysis(EncSilk* st, CoopWork* W, const i16* pIn, int
     );
     SB_PARFOR(i, 0, FRAME) x_frame[LA_SHAPE + i] = W->pIn_HP[i];   // LP_variable_cutoff is a copy (transition_frame_no == 0)
     SB_SYNC();
+    SB_PHASE();
     c_find_pitch_lags(st, c, &W->u.pitch, W->res_pitch, x_frame);
+    SB_PHASE();
     c_noise_shape_analysis(st, c, &W->u.shape, W->res_pitch + FRAME, x_frame);
+    SB_PHASE();
     c_prefilter(st, c, &W->u.pref, W->xfw, x_frame);
-    c_find_pred_coefs(st, c, &W->u.pred, W->res_pitch, frame_in_packet, nullptr);
+    SB_PHASE();
+    c_find_pred_coefs(st, c, &W->u.pred, W->res_pitch, frame_in_packet, fast);
     SB_SERIAL(
         process_gains(st, c, frame_in_packet);
-        if (st->speech_activity_Q8 < SB_FIXC(0.1f, 8)) {
-            st->vadFlag = 0;
-            st->noSpeechCounter++;
-            if (st->noSpeechCounter > 5) st->inDTX = 1;
-            if (st->noSpeechCounter > 20 + 5) { st->noSpeechCounter = 5; st->inDTX = 0; }
-        } else {
-            st->noSpeechCounter = 0; st->inDTX = 0; st->vadFlag = 1;
-        }
-        W->vadFlag = st->vadFlag;
+        vad_flag_and_dtx(st, &W->vadFlag);
         st->prev_sigtype = c->sigtype;
         st->prevLag = c->pitchL[NB_SUBFR - 1];
         st->first_frame_after_reset = 0;
     );
-    {   // x_buf slides by one frame (old values on the right-hand side)
-        i32 keep[(FRAME + LA_SHAPE) / 2 / 32 + 1];
-        const i32* src = reinterpret_cast<const i32*>(st->x_buf + FRAME);
-        i32* dst = reinterpret_cast<i32*>(st->x_buf);
-        int q = 0;
-        SB_PARFOR(i, 0, (FRAME + LA_SHAPE) / 2) keep[q++] = src[i];
+    {   // x_buf slides by one frame: [0,160) <- [160,320), then [160,200) <- [320,360) (each step reads only unwritten words)
+        i32* xb = reinterpret_cast<i32*>(st->x_buf);
+        SB_PARFOR(i, 0, FRAME / 2) xb[i] = xb[FRAME / 2 + i];
         SB_SYNC();
-        q = 0;
-        SB_PARFOR(i, 0, (FRAME + LA_SHAPE) / 2) dst[i] = keep[q++];
+        SB_PARFOR(i, 0, LA_SHAPE / 2) xb[FRAME / 2 + i] = xb[FRAME + i];
         SB_SYNC();
     }
 }
 
 // Stage A for the SILK core of one packet.  st, W: shared memory; W->low already holds the low band; scr: global memory.
-SB_FN void c_enc_packet_analysis(EncSilk* st, CoopWork* W, EncScratch* scr) {
+SB_CFN void c_enc_packet_analysis(EncSilk* st, CoopWork* W, EncScratch* scr, const NlsfFastTabs* fast = nullptr) {
     const int nf = st->frames_per_packet;
     for (int f = 0; f < nf; f++) {
-        c_encode_frame_analysis(st, W, W->low + f * FRAME, f);
+        c_encode_frame_analysis(st, W, W->low + f * FRAME, f, fast);
         const i32* src = reinterpret_cast<const i32*>(&W->c);
         i32* dst = reinterpret_cast<i32*>(&scr->c[f]);
         SB_PARFOR(i, 0, (int)(sizeof(EncCtrl) / 4)) dst[i] = src[i];

@@ -9,7 +9,6 @@
 #include "sb_enc_pred.cuh"
 #include "sb_enc_shape.cuh"
 #include "sb_nsq.cuh"
-#include "sb_par.cuh"
 
 namespace sb {
 
@@ -185,25 +184,7 @@ SB_FN void hb_pack_frame(i32 lsp_idx, const i32* nrg0, const i16* r16, u8* out4,
     out4[0] = (u8)(w >> 24); out4[1] = (u8)(w >> 16); out4[2] = (u8)(w >> 8); out4[3] = (u8)w;
 }
 
-// ---- per-packet hand-over between the encoder stages (device: global scratch, one slot per stream) -------------------
-//   stage A (analysis, one thread per stream)   : [QMF split, its own kernel on the device,] VAD .. process_gains per frame, high-band analysis
-//   stage B (MD noise-shaping quantiser)         : consumes c[f], xfw[f]; produces q_md[f], r16[f], c[f].Seed
-//   stage C (entropy coding + packing)           : range-codes both descriptions, high-band gains, payload assembly
-struct EncScratch {
-    EncCtrl c[2];
-    i16 xfw[2][FRAME];
-    i8 q_md[2][2][FRAME];  // [frame][description]
-    i16 r16[2][FRAME];
-    i32 vadFlag[2];
-    i32 hb_lsp_idx[2];
-    i32 hb_nrg0[2][4];
-    i32 dtx_drop;
-};
-
-// Working set of stage A for one stream.  Warp-per-stream kernel: shared memory; thread-per-stream / host: local memory.
-#ifndef SB_ANA_ARENA
-#define SB_ANA_ARENA 16     // grows when routines move their scratch arrays into the shared arena
-#endif
+// Working set of stage A for one stream in the scalar model (tests/hostsim); the device kernels use CoopWork (sb_coop.cuh).
 struct EncAnalysisWork {
     i16 low[PACKET / 2], high[PACKET / 2];
     i16 pIn_HP[FRAME];
@@ -211,78 +192,47 @@ struct EncAnalysisWork {
     EncCtrl c;                 // control of the frame being analysed (copied to EncScratch when the frame is done)
     i16 xfw[FRAME];
     i32 vadFlag;
-    const NlsfFastTabs* nlsf_fast;   // shared-memory copies of the NLSF codebooks (null: use the global tables)
-    alignas(16) unsigned char arena_mem[SB_ANA_ARENA];
+    const NlsfFastTabs* nlsf_fast;   // optional copies of the NLSF codebooks (null: use the global tables)
 };
 
-// SKP_Silk_encode_frame_FIX (encode_frame_FIX.c:34-131, 151-165, 199-208) up to the quantiser, for one frame.
-// Cooperative: called by every lane of the stream; routines that are still single-lane are wrapped in SB_SERIAL.
-SB_FN void encode_frame_analysis(EncCore* st, EncAnalysisWork* W, Arena* A, const i16* pIn, int frame_in_packet) {
+// SKP_Silk_encode_frame_FIX (encode_frame_FIX.c:34-131, 151-165, 199-208) up to the quantiser, for one frame (scalar model).
+SB_FN void encode_frame_analysis(EncCore* st, EncAnalysisWork* W, const i16* pIn, int frame_in_packet) {
     EncCtrl* c = &W->c;
     i16* x_frame = st->x_buf + FRAME;
-    SB_SERIAL(
-        c->Seed = st->frameCounter++ & 3;
-        vad_get_sa_q8(&st->vad, &st->speech_activity_Q8, c->input_quality_bands_Q15, &c->input_tilt_Q15, pIn);
-        hp_variable_cutoff(st, c, W->pIn_HP, pIn);
-        for (int i = 0; i < FRAME; i++) x_frame[LA_SHAPE + i] = W->pIn_HP[i];  // LP_variable_cutoff is a copy (transition_frame_no == 0)
-        find_pitch_lags(st, c, W->res_pitch, x_frame);
-        noise_shape_analysis(st, c, W->res_pitch + FRAME, x_frame);
-        prefilter(st, c, W->xfw, x_frame);
-        find_pred_coefs(st, c, W->res_pitch, frame_in_packet, W->nlsf_fast);
-        process_gains(st, c, frame_in_packet);
-        if (st->speech_activity_Q8 < SB_FIXC(0.1f, 8)) {
-            st->vadFlag = 0;
-            st->noSpeechCounter++;
-            if (st->noSpeechCounter > 5) st->inDTX = 1;
-            if (st->noSpeechCounter > 20 + 5) { st->noSpeechCounter = 5; st->inDTX = 0; }
-        } else {
-            st->noSpeechCounter = 0; st->inDTX = 0; st->vadFlag = 1;
-        }
-        W->vadFlag = st->vadFlag;
-        for (int i = 0; i < FRAME + LA_SHAPE; i++) st->x_buf[i] = st->x_buf[FRAME + i];
-        st->prev_sigtype = c->sigtype;
-        st->prevLag = c->pitchL[NB_SUBFR - 1];
-        st->first_frame_after_reset = 0;
-    );
-    (void)A;
+    c->Seed = st->frameCounter++ & 3;
+    vad_get_sa_q8(&st->vad, &st->speech_activity_Q8, c->input_quality_bands_Q15, &c->input_tilt_Q15, pIn);
+    hp_variable_cutoff(st, c, W->pIn_HP, pIn);
+    for (int i = 0; i < FRAME; i++) x_frame[LA_SHAPE + i] = W->pIn_HP[i];  // LP_variable_cutoff is a copy (transition_frame_no == 0)
+    find_pitch_lags(st, c, W->res_pitch, x_frame);
+    noise_shape_analysis(st, c, W->res_pitch + FRAME, x_frame);
+    prefilter(st, c, W->xfw, x_frame);
+    find_pred_coefs(st, c, W->res_pitch, frame_in_packet, W->nlsf_fast);
+    process_gains(st, c, frame_in_packet);
+    vad_flag_and_dtx(st, &W->vadFlag);
+    for (int i = 0; i < FRAME + LA_SHAPE; i++) st->x_buf[i] = st->x_buf[FRAME + i];
+    st->prev_sigtype = c->sigtype;
+    st->prevLag = c->pitchL[NB_SUBFR - 1];
+    st->first_frame_after_reset = 0;
 }
 
-// stage A (cooperative).  st and W: shared memory in the warp-per-stream kernel; pcm and scr: global memory.
-// bands: the packet already split into [low | high] by the QMF kernel (device pipeline), or null: split it here.
+// stage A (scalar model): band split, two core frames, high-band frames
 SB_FN void enc_packet_analysis(EncCore* st, EncAnalysisWork* W, const i16* pcm, EncScratch* scr, const i16* bands = nullptr) {
-    Arena A;
-    arena_init(&A, W->arena_mem, SB_ANA_ARENA);
     const int nf = st->frames_per_packet;
     if (bands) {
         const int half = nf * FRAME;
-#ifdef __CUDA_ARCH__
-        const int4* src = reinterpret_cast<const int4*>(bands);          // rows are 16-byte aligned (spp * 2 = 1280 or 640 bytes)
-        int4* dl = reinterpret_cast<int4*>(W->low);
-        int4* dh = reinterpret_cast<int4*>(W->high);
-        for (int i = 0; i < half / 8; i++) { dl[i] = src[i]; dh[i] = src[half / 8 + i]; }
-#else
         for (int i = 0; i < half; i++) { W->low[i] = bands[i]; W->high[i] = bands[half + i]; }
-#endif
     } else {
-        SB_SERIAL(qmf_decomp(pcm, W->low, W->high, st->qmf_mem, nf * 2 * FRAME));
+        qmf_decomp(pcm, W->low, W->high, st->qmf_mem, nf * 2 * FRAME);
     }
     for (int f = 0; f < nf; f++) {
-        encode_frame_analysis(st, W, &A, W->low + f * FRAME, f);
-        // hand the frame over to stages B / C (32-bit words; EncCtrl and xfw are both 4-byte multiples)
-        {
-            const i32* src = reinterpret_cast<const i32*>(&W->c);
-            i32* dst = reinterpret_cast<i32*>(&scr->c[f]);
-            SB_PARFOR(i, 0, (int)(sizeof(EncCtrl) / 4)) dst[i] = src[i];
-            const i32* xs = reinterpret_cast<const i32*>(W->xfw);
-            i32* xd = reinterpret_cast<i32*>(scr->xfw[f]);
-            SB_PARFOR(i, 0, FRAME / 2) xd[i] = xs[i];
-            if (SB_LANE0) scr->vadFlag[f] = W->vadFlag;
-        }
-        SB_SYNC();
+        encode_frame_analysis(st, W, W->low + f * FRAME, f);
+        scr->c[f] = W->c;
+        for (int i = 0; i < FRAME; i++) scr->xfw[f][i] = W->xfw[i];
+        scr->vadFlag[f] = W->vadFlag;
     }
-    if (SB_LANE0) scr->dtx_drop = (st->useDTX && st->inDTX) ? 1 : 0;
+    scr->dtx_drop = (st->useDTX && st->inDTX) ? 1 : 0;
     const int nhb = nf * FRAME / st->hb_frame;    // high-band frames per packet
-    for (int f = 0; f < nhb; f++) SB_SERIAL(hb_analyse_frame(st, W->high + f * st->hb_frame, &scr->hb_lsp_idx[f], scr->hb_nrg0[f]));
+    for (int f = 0; f < nhb; f++) hb_analyse_frame(st, W->high + f * st->hb_frame, &scr->hb_lsp_idx[f], scr->hb_nrg0[f]);
 }
 
 // stage C: AGR_Sate_Encoder_Encode tail -- returns the byte count; nBytesOut[0] = total, nBytesOut[1] = len(MD2) + 8

@@ -137,6 +137,19 @@ SB_FN void hp_variable_cutoff(EncSilk* st, EncCtrl* c, i16* out, const i16* in) 
     biquad_alt(in, B_Q28, A_Q28, st->In_HP_State, out, FRAME);
 }
 
+// ---- encode_frame_FIX.c:151-165: VAD flag and the DTX counter ----------------------------------------------
+SB_FN void vad_flag_and_dtx(EncSilk* st, i32* vadFlag) {
+    if (st->speech_activity_Q8 < SB_FIXC(0.1f, 8)) {
+        st->vadFlag = 0;
+        st->noSpeechCounter++;
+        if (st->noSpeechCounter > 5) st->inDTX = 1;
+        if (st->noSpeechCounter > 20 + 5) { st->noSpeechCounter = 5; st->inDTX = 0; }
+    } else {
+        st->noSpeechCounter = 0; st->inDTX = 0; st->vadFlag = 1;
+    }
+    *vadFlag = st->vadFlag;
+}
+
 // ---- SKP_Silk_pitch_analysis_core.c:680-706 ---------------------------------------------------------
 SB_FN i32 pitch_find_scaling(const i16* signal, int signal_length, int sum_sqr_len) {
     // int16_array_maxabs (SKP_Silk_array_maxabs.c:40-66)

@@ -20,7 +20,7 @@
 #pragma once
 #include "sb_common.cuh"
 
-#if defined(__CUDA_ARCH__) && defined(SB_COOP)
+#if defined(__CUDACC__) && defined(SB_COOP)
 #define SB_COOP_ACTIVE 1
 #define SB_NLANES 32
 #define SB_LANE ((int)(threadIdx.x & 31))
@@ -43,6 +43,19 @@ long long* scratch();   // 32 x 8-byte slots shared by the lanes of the current 
 #endif
 
 #define SB_LANE0 (SB_LANE == 0)
+// Phase alignment: the warps of a block (one stream each) pass the analysis phases together, so that the instruction lines a
+// phase needs are fetched once per SM and not once per warp (the per-stream code path is long and mostly straight-line).
+#if defined(__CUDA_ARCH__) && defined(SB_COOP) && defined(SB_PHASE_ALIGN)
+#define SB_PHASE() __syncthreads()
+#else
+#define SB_PHASE() ((void)0)
+#endif
+// cooperative routines: device-only in the CUDA build, plain functions under the host emulation
+#if defined(__CUDACC__)
+#define SB_CFN __device__ inline
+#else
+#define SB_CFN inline
+#endif
 // iterations lo <= i < hi, spread over the lanes (all of them on the single lane of a serial build)
 #define SB_PARFOR(i, lo, hi) for (int i = (lo) + SB_LANE; i < (hi); i += SB_NLANES)
 // run a statement block on lane 0 only, then make its effects visible to the other lanes
@@ -51,7 +64,7 @@ long long* scratch();   // 32 x 8-byte slots shared by the lanes of the current 
 namespace sb {
 
 // ---- reductions / broadcasts over the lanes of a stream (identity in serial builds) --------------------------------
-#if defined(__CUDA_ARCH__) && defined(SB_COOP)
+#if defined(__CUDACC__) && defined(SB_COOP)
 __device__ __forceinline__ i32 wsum(i32 v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = (i32)((u32)v + (u32)__shfl_xor_sync(0xffffffffu, v, o));

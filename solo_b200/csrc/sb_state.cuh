@@ -133,6 +133,21 @@ struct EncCtrl {
     i32 ResNrgQ[NB_SUBFR];
 };
 
+// ---- per-packet hand-over between the encoder stages (device: global scratch, one slot per stream) -------------------
+//   stage A (analysis, one thread per stream)   : [QMF split, its own kernel on the device,] VAD .. process_gains per frame, high-band analysis
+//   stage B (MD noise-shaping quantiser)         : consumes c[f], xfw[f]; produces q_md[f], r16[f], c[f].Seed
+//   stage C (entropy coding + packing)           : range-codes both descriptions, high-band gains, payload assembly
+struct EncScratch {
+    EncCtrl c[2];
+    i16 xfw[2][FRAME];
+    i8 q_md[2][2][FRAME];  // [frame][description]
+    i16 r16[2][FRAME];
+    i32 vadFlag[2];
+    i32 hb_lsp_idx[2];
+    i32 hb_nrg0[2][4];
+    i32 dtx_drop;
+};
+
 // Range coder (SKP_Silk_range_coder_state, structs.h:85-92); the byte buffer lives with the caller.
 struct RangeEnc {
     u32 base_Q32, range_Q16;

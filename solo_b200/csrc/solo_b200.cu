@@ -46,9 +46,10 @@ using namespace sb;
 #define SB_QMF_KERNEL 1       // band split as its own warp-per-stream kernel with a TMA-fetched PCM tile (0: inside kernel A)
 #endif
 #ifndef SB_ANALYSIS_WARP
-#define SB_ANALYSIS_WARP 0   // 1: stage A runs as the warp-per-stream kernel of sb_analysis.cu
+#define SB_ANALYSIS_WARP 1   // 1: stage A = the warp-per-stream kernels of sb_analysis.cu; 0: the thread-per-stream kernel below
 #endif
-extern "C" int sb_launch_enc_analysis_warp(void* states, void* scratch, const void* pcm, int spp, int n, void* stream);
+extern "C" int sb_launch_enc_analysis_warp(void* states, void* scratch, const void* bands, int spp, int n, void* stream);
+extern "C" int sb_launch_enc_hb_warp(void* states, void* scratch, const void* bands, int spp, int n, void* stream);
 #ifndef SB_ANALYSIS_MINB
 #define SB_ANALYSIS_MINB 4   // min resident blocks per SM of the analysis kernel (register cap = 65536 / (64 * MINB) = 255)
 #endif
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(SB_QMF_SPB * 32) sb_enc_qmf_kernel(EncState* s
 //   A  sb_enc_analysis_kernel : one thread per stream  -- QMF split, VAD .. gain processing of both frames, high-band analysis
 //   B  sb_enc_nsq_kernel      : one WARP per stream    -- MD delayed-decision noise-shaping quantiser, state in shared memory
 //   C  sb_enc_finish_kernel   : one thread per stream  -- range coding of both descriptions, high-band gains, payload assembly
+#if !SB_ANALYSIS_WARP
 __global__ void __launch_bounds__(SB_ANA_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ pcm, const i16* __restrict__ bands, int spp, int n) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
 #if SB_ANA_SMEM_TABS
@@ -154,6 +156,8 @@ __global__ void __launch_bounds__(SB_ANA_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_
     enc_packet_analysis(&states[s], &W, x, &scratch[s], bands ? bands + (size_t)s * spp : nullptr);
 #endif
 }
+
+#endif
 
 #ifndef SB_NSQ_WARPS
 #define SB_NSQ_WARPS 1      // one warp = two streams = 2 x 12.2 KB of shared memory; 9 blocks (18 streams) per SM
@@ -433,7 +437,11 @@ static int enc_launch(solo_b200_enc_batch* b, int lo, int n, const i16* d_pcm, u
     EvPair ev;
     prof_begin(st, 0, &ev);
 #if SB_ANALYSIS_WARP
-    { int e = sb_launch_enc_analysis_warp(states, scratch, pcm, b->spp, n, st); if (e) return fail("analysis launch", (cudaError_t)e); }
+    i16* bands = b->d_bands + (size_t)lo * b->spp;
+    sb_enc_qmf_kernel<<<(n + SB_QMF_SPB - 1) / SB_QMF_SPB, SB_QMF_SPB * 32, 0, st>>>(states, pcm, bands, b->spp, n);
+    { int e = sb_launch_enc_hb_warp(states, scratch, bands, b->spp, n, st); if (e) return fail("high-band analysis launch", (cudaError_t)e); }
+    { int e = sb_launch_enc_analysis_warp(states, scratch, bands, b->spp, n, st); if (e) return fail("analysis launch", (cudaError_t)e); }
+    count_launch(); count_launch();
 #else
 #if SB_QMF_KERNEL
     i16* bands = b->d_bands + (size_t)lo * b->spp;

@@ -78,8 +78,13 @@ int hs_enc_encode(void* p, const short* pcm, unsigned char* out, int cap, short*
     sb::qmf_decomp(pcm, h->w.a.low, h->w.a.high, h->st.qmf_mem, nf * 2 * sb::FRAME);
     for (int i = 0; i < nf * sb::FRAME; i++) cw.low[i] = h->w.a.low[i];
     sb::emu::run32([=]() { sb::c_enc_packet_analysis(&h->st, &cw, &h->w.scr); });
-    for (int f = 0; f < nf * sb::FRAME / h->st.hb_frame; f++)
-        sb::hb_analyse_frame(&h->st, h->w.a.high + f * h->st.hb_frame, &h->w.scr.hb_lsp_idx[f], h->w.scr.hb_nrg0[f]);
+    static sb::HbScr hs;
+    sb::emu::run32([=]() {
+        for (int f = 0; f < nf * sb::FRAME / h->st.hb_frame; f++) {
+            if (h->st.hb_frame == sb::HB_FRAME) sb::c_hb_analyse_frame<sb::HB_FRAME>(&h->st, &hs, h->w.a.high + f * h->st.hb_frame, &h->w.scr.hb_lsp_idx[f], h->w.scr.hb_nrg0[f]);
+            else sb::c_hb_analyse_frame<2 * sb::HB_FRAME>(&h->st, &hs, h->w.a.high + f * h->st.hb_frame, &h->w.scr.hb_lsp_idx[f], h->w.scr.hb_nrg0[f]);
+        }
+    });
     return sb::enc_packet_quantise_and_code(&h->st, &h->w, out, cap, nb);
 #else
     return sb::enc_packet(&h->st, &h->w, pcm, out, cap, nb);

@@ -8,7 +8,7 @@ for f in os.listdir(root):
     if not f.endswith((".cuh",".cu")): continue
     L=[]
     for n,l in enumerate(open(root+f),1):
-        m=re.match(r"^(?:template.*>\s*)?(?:SB_FN|SB_HD|__device__|__global__|static)\s.*?\b(\w+)\s*\(",l)
+        m=re.match(r"^(?:template.*>\s*)?(?:SB_FN|SB_CFN|SB_FN_BIG|SB_HD|__device__|__global__|static)\s.*?\b(\w+)\s*\(",l)
         if m and not l.startswith(" "): L.append((n,m.group(1)))
     starts[f]=L
 def fn(f,ln):
