@@ -10,25 +10,24 @@
 #ifndef SB_NO_PHASE_ALIGN
 #define SB_PHASE_ALIGN 1
 #endif
+#ifndef SB_ANA_WARPS
+#define SB_ANA_WARPS 8      // streams per block of the core-analysis kernel; its warps pass the phases together, two blocks per SM
+#endif
+#ifndef SB_NO_XPOSE
+#define SB_XPOSE 1          // scalar recursions of all streams of a block run side by side on consecutive threads (sb_par.cuh)
+#define SB_BLOCK_STREAMS SB_ANA_WARPS
+#endif
 #include <cuda_runtime.h>
 #include "sb_coop.cuh"
-#include "sb_enc.cuh"
 
 using namespace sb;
 
-#ifndef SB_ANA_WARPS
-#define SB_ANA_WARPS 16     // streams per block of the core-analysis kernel: one block per SM, its warps pass the phases together
-#endif
 #ifndef SB_HB_WARPS
 #define SB_HB_WARPS 4
 #endif
 
 namespace {
 
-struct AnaSmem {
-    EncSilk st;
-    CoopWork W;
-};
 struct HbSmem {
     EncBands hb;
     HbScr H;
@@ -55,7 +54,11 @@ __global__ void __launch_bounds__(SB_ANA_WARPS * 32) sb_enc_analysis_warp_kernel
     // same values stored to the same scratch slot) and does not write state back
     const bool live = s < n;
     if (!live) s = n - 1;
-    AnaSmem* S = reinterpret_cast<AnaSmem*>(smem_raw + ((sizeof(NlsfFastTabs) + 15) & ~15)) + w;
+    // the slot address as an opaque 32-bit shared-window offset: kept in a register instead of being recomputed from threadIdx
+    // at every use (the compiler otherwise rematerialises it ~130 times)
+    unsigned slot = (unsigned)__cvta_generic_to_shared(smem_raw + ((sizeof(NlsfFastTabs) + 15) & ~15)) + (unsigned)w * (unsigned)sizeof(AnaSmem);
+    asm volatile("" : "+r"(slot));
+    AnaSmem* S = reinterpret_cast<AnaSmem*>(__cvta_shared_to_generic(slot));
     copy16(&S->st, static_cast<EncSilk*>(&states[s]), (int)sizeof(EncSilk), lane);
     copy16(S->W.low, bands + (size_t)s * spp, spp, lane);          // low band = first half of the row (spp / 2 samples)
     __syncwarp();

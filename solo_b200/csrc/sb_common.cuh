@@ -211,13 +211,30 @@ SB_HD i32 sigm_q15(i32 in_q5) {
     return pos[ind] + smulbb(slope[ind], in_q5 & 0x1F);
 }
 
+// (SKP_int32_MAX >> 2) / d as the reference's C division computes it, for the divisors its normalisation produces
+// (16384 <= |d| <= 32768): float reciprocal + one exact correction step instead of a generic 32-bit integer division
+// (exhaustively checked against the integer division for every such d: tests/test_hostsim_parity.py).
+SB_HD i32 div_q29(i32 d) {
+    const i32 N = SB_I32_MAX >> 2;
+    if ((u32)(iabs(d) - 16384) > 16384u) return d == 0 ? 0 : N / d;   // not reachable from normalised inputs
+#ifdef __CUDA_ARCH__
+    i32 q = __float2int_rz((float)N * __frcp_rn((float)d));
+#else
+    i32 q = (i32)((float)N * (1.0f / (float)d));
+#endif
+    const i32 rem = N - q * d;
+    if (d > 0) { if (rem < 0) q--; else if (rem >= d) q++; }
+    else { if (rem < 0) q++; else if (rem >= -d) q--; }
+    return q;
+}
+
 // ---- approximate division (Inlines.h:124-217); reproduced step by step, never an exact divide --------
 SB_HD i32 div32_varq(i32 a32, i32 b32, int qres) {
     int a_headrm = clz32(iabs(a32)) - 1;
     i32 a_nrm = shl(a32, a_headrm);
     int b_headrm = clz32(iabs(b32)) - 1;
     i32 b_nrm = shl(b32, b_headrm);
-    i32 b_inv = (SB_I32_MAX >> 2) / (b_nrm >> 16);
+    i32 b_inv = div_q29(b_nrm >> 16);
     i32 result = smulwb(a_nrm, b_inv);
     a_nrm = subw(a_nrm, shl(smmul(b_nrm, result), 3));
     result = smlawb(result, a_nrm, b_inv);
@@ -229,7 +246,7 @@ SB_HD i32 div32_varq(i32 a32, i32 b32, int qres) {
 SB_HD i32 inverse32_varq(i32 b32, int qres) {
     int b_headrm = clz32(iabs(b32)) - 1;
     i32 b_nrm = shl(b32, b_headrm);
-    i32 b_inv = (SB_I32_MAX >> 2) / (b_nrm >> 16);
+    i32 b_inv = div_q29(b_nrm >> 16);
     i32 result = shl(b_inv, 16);
     i32 err_q32 = shl(negw(smulwb(b_nrm, b_inv)), 3);
     result = smlaww(result, err_q32, b_inv);

@@ -197,8 +197,7 @@ SB_CFN int c_pitch_analysis_core(PitchScr* P, const i16* signal, i32* pitch_out,
     SB_PARFOR(i, 0, FL8) sig8[i] = signal[i];
     SB_SYNC();
     // 2:1 decimator: one recurrence over the frame (lane 0)
-    if (lane == 0) { i32 fs[2] = {0, 0}; resampler_down2(fs, sig4, sig8, FL8); }
-    SB_SYNC();
+    c_instances<1>([&](int d, int) { i32 fs[2] = {0, 0}; resampler_down2(fs, xoff(sig4, d), xoff(sig8, d), FL8); });
     // low-pass (descending in-place loop of the reference = old values on the right-hand side) + scaling
     i32 v[5];
 #pragma unroll
@@ -251,7 +250,7 @@ SB_CFN int c_pitch_analysis_core(PitchScr* P, const i16* signal, i32* pitch_out,
     for (int j = 0; j < 3; j++) { const int i = lane + 32 * j; if (i < NL4) P->C1[0][i] = (i16)cs[j]; }
     SB_SYNC();
     int length_d_srch = 4 + 2 * 2;
-    if (lane == 0) insertion_sort_decreasing_i16(&P->C1[0][0], P->d_srch, NL4, length_d_srch);
+    c_instances<1>([&](int d, int) { PitchScr* Pj = xoff(P, d); insertion_sort_decreasing_i16(&Pj->C1[0][0], Pj->d_srch, NL4, 4 + 2 * 2); });
     i32 energy;
     {
         i32 part = 0;
@@ -464,6 +463,8 @@ struct ShapeScr {
     i16 xw[NB_SUBFR][SHAPE_WIN];
     i32 acorr[NB_SUBFR][SHAPE_ORDER + 1];
     i32 scale[NB_SUBFR];
+    i32 par3[3];                 // warping_Q16, BWExp1_Q16, BWExp2_Q16 for the per-window instances
+    i32 gains[NB_SUBFR][2];      // their results: Gains_Q16, GainsPre_Q14 before the frame-level tweaks
 };
 
 // Warped autocorrelation of the four shaping windows at once (SKP_Silk_warped_autocorrelation_FIX.c:36-85): the 16
@@ -571,37 +572,41 @@ SB_CFN void c_noise_shape_analysis(EncSilk* st, EncCtrl* c, ShapeScr* S, const i
     c_warped_autocorr4(S, warping_Q16);
     SB_SYNC();
     SB_PHASE();
-    // ---- per window: reflection coefficients, shaping filters, gains -- one window per lane (lanes 0..3) ----
-    i32 gain_k = 0, gains_pre_k = 0;
-    if (lane < NB_SUBFR) {
-        const int k = lane;
+    // ---- per window: reflection coefficients, shaping filters, gains -- one scalar instance per window ----
+    if (lane == 0) { S->par3[0] = warping_Q16; S->par3[1] = BWExp1_Q16; S->par3[2] = BWExp2_Q16; }
+    c_instances<NB_SUBFR>([&](int d, int k) {
+        ShapeScr* Sj = xoff(S, d);
+        EncCtrl* cj = xoff(c, d);
+        const i32 warp_Q16 = Sj->par3[0], bw1 = Sj->par3[1], bw2 = Sj->par3[2];
         i32 auto_corr[SHAPE_ORDER + 1], refl_coef_Q16[SHAPE_ORDER], AR1_Q24[SHAPE_ORDER], AR2_Q24[SHAPE_ORDER];
-        for (int i = 0; i <= SHAPE_ORDER; i++) auto_corr[i] = S->acorr[k][i];
+        for (int i = 0; i <= SHAPE_ORDER; i++) auto_corr[i] = Sj->acorr[k][i];
         auto_corr[0] = addw(auto_corr[0], imax(smulwb(auto_corr[0] >> 4, SB_FIXC(1e-5f, 20)), 1));
         i32 nrg = schur64(refl_coef_Q16, auto_corr, SHAPE_ORDER);
         k2a_q16(AR2_Q24, refl_coef_Q16, SHAPE_ORDER);
-        int Qnrg = -S->scale[k];
+        int Qnrg = -Sj->scale[k];
         if (Qnrg & 1) { Qnrg -= 1; nrg >>= 1; }
         const i32 tmp32 = sqrt_approx(nrg);
         Qnrg >>= 1;
-        gain_k = lshift_sat32(tmp32, 16 - Qnrg);
-        const i32 gain_mult_Q16 = warped_gain(AR2_Q24, warping_Q16, SHAPE_ORDER);
-        gain_k = smulww(gain_k, gain_mult_Q16);
-        if (gain_k < 0) gain_k = SB_I32_MAX;
-        bwexpander_32(AR2_Q24, SHAPE_ORDER, BWExp2_Q16);
+        i32 gk = lshift_sat32(tmp32, 16 - Qnrg);
+        const i32 gain_mult_Q16 = warped_gain(AR2_Q24, warp_Q16, SHAPE_ORDER);
+        gk = smulww(gk, gain_mult_Q16);
+        if (gk < 0) gk = SB_I32_MAX;
+        bwexpander_32(AR2_Q24, SHAPE_ORDER, bw2);
         for (int i = 0; i < SHAPE_ORDER; i++) AR1_Q24[i] = AR2_Q24[i];
-        bwexpander_32(AR1_Q24, SHAPE_ORDER, BWExp1_Q16);
+        bwexpander_32(AR1_Q24, SHAPE_ORDER, bw1);
         i32 pre_nrg_Q30;
         lpc_inv_pred_gain_q24(&pre_nrg_Q30, AR2_Q24, SHAPE_ORDER);
         lpc_inv_pred_gain_q24(&nrg, AR1_Q24, SHAPE_ORDER);
         pre_nrg_Q30 = shl(smulwb(pre_nrg_Q30, SB_FIXC(0.7, 15)), 1);
-        gains_pre_k = SB_FIXC(0.3, 14) + div32_varq(pre_nrg_Q30, nrg, 14);
-        limit_warped_coefs(AR2_Q24, AR1_Q24, warping_Q16, SB_FIXC(3.999, 24), SHAPE_ORDER);
+        Sj->gains[k][0] = gk;
+        Sj->gains[k][1] = SB_FIXC(0.3, 14) + div32_varq(pre_nrg_Q30, nrg, 14);
+        limit_warped_coefs(AR2_Q24, AR1_Q24, warp_Q16, SB_FIXC(3.999, 24), SHAPE_ORDER);
         for (int i = 0; i < SHAPE_ORDER; i++) {
-            c->AR1_Q13[k * SHAPE_ORDER + i] = (i16)sat16(rshift_round(AR1_Q24[i], 11));
-            c->AR2_Q13[k * SHAPE_ORDER + i] = (i16)sat16(rshift_round(AR2_Q24[i], 11));
+            cj->AR1_Q13[k * SHAPE_ORDER + i] = (i16)sat16(rshift_round(AR1_Q24[i], 11));
+            cj->AR2_Q13[k * SHAPE_ORDER + i] = (i16)sat16(rshift_round(AR2_Q24[i], 11));
         }
-    }
+    });
+    i32 gain_k = S->gains[lane & 3][0], gains_pre_k = S->gains[lane & 3][1];
     // ---- gain tweaking ----
     const i32 md_gain_mult_Q16 = log2lin(negw(smlawb(-SB_FIXC(16.0, 7), md_SNR_adj_dB_Q7, SB_FIXC(0.16, 16))));
     i32 gain_mult_Q16 = log2lin(negw(smlawb(-SB_FIXC(16.0, 7), SNR_adj_dB_Q7, SB_FIXC(0.16, 16))));
@@ -695,18 +700,21 @@ SB_CFN void c_prefilter(EncSilk* st, const EncCtrl* c, PrefScr* S, i16* xw, cons
         const int j = lane;
         const i32 lambda = WARPING_Q16;
         i32 p0 = 0, p1 = 0, out = 0, acc_out = 0;
-        if (j < SHAPE_ORDER) { p0 = st->pf_sAR_shp[j]; p1 = st->pf_sAR_shp[j + 1]; }
-        for (int t = 0; t < FRAME + SHAPE_ORDER - 1; t++) {
-            const int n = t - j;
+        const bool mine = j < SHAPE_ORDER;
+        if (mine) { p0 = st->pf_sAR_shp[j]; p1 = st->pf_sAR_shp[j + 1]; }
+        const i16* cf = &c->AR1_Q13[mine ? j : 0];
+        i32 coef = cf[0];
+        int n = -j, left = SUBFR;        // sample this lane works on at the current step; samples left in its sub-frame
+        for (int t = 0; t < FRAME + SHAPE_ORDER - 1; t++, n++) {
             const i32 in_prev = wshfl_up(out, 1), acc_prev = wshfl_up(acc_out, 1);
-            if (j < SHAPE_ORDER && n >= 0 && n < FRAME) {
+            if (mine && (unsigned)n < (unsigned)FRAME) {
                 const i32 xin = x[n];
                 const i32 in = j == 0 ? shl(xin, 14) : in_prev;
-                const i32 o = j == 0 ? smlawb(p0, p1, lambda) : smlawb(p0, subw(p1, in), lambda);
-                const i32 coef = c->AR1_Q13[(n / SUBFR) * SHAPE_ORDER + j];
-                const i32 a = j == 0 ? smulwb(o, coef) : smlawb(acc_prev, o, coef);
+                const i32 o = smlawb(p0, j == 0 ? p1 : subw(p1, in), lambda);
+                const i32 a = smlawb(j == 0 ? 0 : acc_prev, o, coef);
                 p0 = in; p1 = o; out = o; acc_out = a;
                 if (j == SHAPE_ORDER - 1) S->st_res[n] = (i16)sat16(xin - rshift_round(a, 11));
+                if (--left == 0) { left = SUBFR; cf += SHAPE_ORDER; coef = n + 1 < FRAME ? cf[0] : 0; }
             }
         }
         SB_SYNC();      // state is read above by every lane before anyone writes it
@@ -738,27 +746,28 @@ SB_CFN void c_prefilter(EncSilk* st, const EncCtrl* c, PrefScr* S, i16* xw, cons
         const i32 prev = i > 0 ? (i32)S->st_res[i - 1] : sHarmHP;
         S->sLF_MA[i] = smlabb(smulbb(S->st_res[i], S->par[k][0]), prev, S->par[k][1]);
     }
-    SB_SYNC();
     // ---- low-frequency shaping recursion (SKP_Silk_prefilt_FIX :174-224): one chain per frame, lane 0 ----
-    if (lane == 0) {
-        i32 sLF_AR = st->pf_sLF_AR_shp_Q12, sLF_MA = st->pf_sLF_MA_shp_Q12;
+    c_instances<1>([&](int d, int) {
+        EncSilk* sj = xoff(st, d);
+        PrefScr* Sj = xoff(S, d);
+        const EncCtrl* cj = xoff(c, d);
+        i32 sLF_AR = sj->pf_sLF_AR_shp_Q12, sLF_MA = sj->pf_sLF_MA_shp_Q12;
         for (int k = 0; k < NB_SUBFR; k++) {
-            const i32 Tilt_Q14 = S->par[k][2], LF_shp_Q14 = S->par[k][3];
+            const i32 Tilt_Q14 = Sj->par[k][2], LF_shp_Q14 = Sj->par[k][3];
             for (int i = k * SUBFR; i < (k + 1) * SUBFR; i++) {
                 const i32 n_Tilt_Q10 = smulwb(sLF_AR, Tilt_Q14);
                 const i32 n_LF_Q10 = smlawb(smulwt(sLF_AR, LF_shp_Q14), sLF_MA, LF_shp_Q14);
-                sLF_AR = subw(S->sLF_MA[i], shl(n_Tilt_Q10, 2));
+                sLF_AR = subw(Sj->sLF_MA[i], shl(n_Tilt_Q10, 2));
                 sLF_MA = subw(sLF_AR, shl(n_LF_Q10, 2));
-                S->sLF_MA[i] = sLF_MA;
+                Sj->sLF_MA[i] = sLF_MA;
             }
         }
-        st->pf_sLF_AR_shp_Q12 = sLF_AR;
-        st->pf_sLF_MA_shp_Q12 = sLF_MA;
-        st->pf_sHarmHP = S->st_res[FRAME - 1];
-        st->pf_sLTP_shp_buf_idx = (idx_start - FRAME) & LTP_MASK;
-        st->pf_lagPrev = c->pitchL[NB_SUBFR - 1];
-    }
-    SB_SYNC();
+        sj->pf_sLF_AR_shp_Q12 = sLF_AR;
+        sj->pf_sLF_MA_shp_Q12 = sLF_MA;
+        sj->pf_sHarmHP = Sj->st_res[FRAME - 1];
+        sj->pf_sLTP_shp_buf_idx = (sj->pf_sLTP_shp_buf_idx - FRAME) & LTP_MASK;
+        sj->pf_lagPrev = cj->pitchL[NB_SUBFR - 1];
+    });
     // shaping-buffer writes of the whole frame first, harmonic taps afterwards: a tap of sample i reaches lag - 2 .. lag
     // samples back (lag >= 16), i.e. only positions written before sample i
     SB_PARFOR(i, 0, FRAME) st->pf_sLTP_shp[(idx_start - 1 - i) & LTP_MASK] = (i16)sat16(rshift_round(S->sLF_MA[i], 12));
@@ -1067,6 +1076,10 @@ struct PredScr {
     i32 NLSF_Q15[LPC_ORDER + 2];
     i32 NLSFW_Q6[LPC_ORDER + 2];
     i32 A_Q16[2][16];            // Burg results: whole frame, second half
+    i32 flag_interp;             // this frame searches the NLSF interpolation factor
+    i32 ie[8][2];                // residual energy and shift of (candidate, half-frame)
+    i32 vq_meta[5];              // MSVQ: survivor set, survivors, fluctuation reduction off, its weight, signal type
+    i32 vq_wsse[16];
     i16 a_tmp_Q12[4][LPC_ORDER + 2];
     union {
         struct { BurgScr burg; A2nlsfScr a2n; } lpc;
@@ -1131,7 +1144,9 @@ SB_CFN void c_find_lpc(i32* NLSF_Q15, i32* interpIndex, const i32* prev_NLSFq_Q1
     const i32 res_tmp_nrg = wshfl(rn, 16), res_tmp_nrg_Q = wshfl(rq, 16);
     SB_SYNC();
     int interp = 4;
-    if (useInterp == 1) {     // uniform
+    const bool interpOn = useInterp == 1;      // per stream: the instance sections below are entered by every warp of the block
+    if (lane == 0) Q->flag_interp = interpOn ? 1 : 0;
+    if (interpOn) {
         int shift = res_tmp_nrg_Q - res_nrg_Q;
         if (shift >= 0) {
             if (shift < 32) res_nrg = subw(res_nrg, res_tmp_nrg >> shift);
@@ -1140,17 +1155,21 @@ SB_CFN void c_find_lpc(i32* NLSF_Q15, i32* interpIndex, const i32* prev_NLSFq_Q1
             res_nrg_Q = res_tmp_nrg_Q;
         }
         c_a2nlsf<ORD>(NLSF_Q15, Q->A_Q16[1], &Q->u.lpc.a2n);
-        // the four interpolation candidates: NLSF -> LPC on four lanes, analysis filters over all lanes
-        i32 prevv[ORD];
-        if (lane < 4) {
-            i32 NLSF0[ORD], nl[ORD];
-            for (int i = 0; i < ORD; i++) { nl[i] = NLSF_Q15[i]; prevv[i] = prev_NLSFq_Q15[i]; }
-            interpolate(NLSF0, prevv, nl, lane, ORD);
-            i16 a12[ORD];
-            nlsf2a_stable(a12, NLSF0, ORD);
-            for (int i = 0; i < ORD; i++) Q->a_tmp_Q12[lane][i] = a12[i];
-        }
-        SB_SYNC();     // also: the grid scratch of c_a2nlsf (same union) is dead from here on
+    }
+    // the four interpolation candidates: NLSF -> LPC as four scalar instances, analysis filters over all lanes
+    c_instances<4>([&](int d, int k) {
+        PredScr* Qj = xoff(Q, d);
+        if (!Qj->flag_interp) return;
+        const i32* nlj = xoff(NLSF_Q15, d);
+        const i32* pvj = xoff(prev_NLSFq_Q15, d);
+        i32 NLSF0[ORD], nl[ORD], prevv[ORD];
+        for (int i = 0; i < ORD; i++) { nl[i] = nlj[i]; prevv[i] = pvj[i]; }
+        interpolate(NLSF0, prevv, nl, k, ORD);
+        i16 a12[ORD];
+        nlsf2a_stable(a12, NLSF0, ORD);
+        for (int i = 0; i < ORD; i++) Qj->a_tmp_Q12[k][i] = a12[i];
+    });
+    if (interpOn) {     // (the grid scratch of c_a2nlsf, same union as LPC_res, is dead from here on)
         for (int t = lane; t < 4 * 2 * SL; t += 32) {
             const int cand = t / (2 * SL), kx = t - cand * 2 * SL;
             const i16* bq = Q->a_tmp_Q12[cand];
@@ -1160,17 +1179,21 @@ SB_CFN void c_find_lpc(i32* NLSF_Q15, i32* interpIndex, const i32* prev_NLSFq_Q1
             const i32 xi = x[kx];
             Q->u.LPC_res[cand][kx] = (i16)sat16(rshift_round(sub_sat32(shl(xi, 12), acc), 12));
         }
-        SB_SYNC();
-        i32 e = 0, sft = 0;
-        if (lane < 8) {    // (candidate, half)
-            const int cand = lane >> 1, half = lane & 1;
-            sum_sqr_shift(&e, &sft, Q->u.LPC_res[cand] + ORD + half * SL, SL - ORD, (ORD + half * SL) & 1);
-        }
+    }
+    c_instances<8>([&](int d, int k) {     // (candidate, half) residual energies
+        PredScr* Qj = xoff(Q, d);
+        if (!Qj->flag_interp) return;
+        const int cand = k >> 1, half = k & 1;
+        i32 e, sft;
+        sum_sqr_shift(&e, &sft, Qj->u.LPC_res[cand] + ORD + half * SL, SL - ORD, (ORD + half * SL) & 1);
+        Qj->ie[k][0] = e; Qj->ie[k][1] = sft;
+    });
+    if (interpOn) {
         for (int kq = 3; kq >= 0; kq--) {
-            i32 res_nrg0 = wshfl(e, 2 * kq), res_nrg1 = wshfl(e, 2 * kq + 1);
-            const i32 rshift0 = wshfl(sft, 2 * kq), rshift1 = wshfl(sft, 2 * kq + 1);
+            i32 res_nrg0 = Q->ie[2 * kq][0], res_nrg1 = Q->ie[2 * kq + 1][0];
+            const i32 rshift0 = Q->ie[2 * kq][1], rshift1 = Q->ie[2 * kq + 1][1];
             i32 res_nrg_interp_Q;
-            shift = rshift0 - rshift1;
+            int shift = rshift0 - rshift1;
             if (shift >= 0) { res_nrg1 = res_nrg1 >> shift; res_nrg_interp_Q = -rshift0; }
             else { res_nrg0 = res_nrg0 >> (-shift); res_nrg_interp_Q = -rshift1; }
             const i32 res_nrg_interp = addw(res_nrg0, res_nrg1);
@@ -1193,7 +1216,7 @@ SB_CFN void c_find_lpc(i32* NLSF_Q15, i32* interpIndex, const i32* prev_NLSFq_Q1
 // partial insertion sort returns -- are found by bounding the 16th value with the lanes' own minima, compacting the pairs
 // below the bound in scan order and ranking that short list.
 SB_CFN void c_nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& cb, const i32* pNLSF_q_Q15_prev, const i32* pW_Q6,
-                              i32 NLSF_mu_Q15, i32 NLSF_mu_fluc_red_Q16, int deactivate_fluc_red, PredScr* Q) {
+                              i32 NLSF_mu_Q15, i32 NLSF_mu_fluc_red_Q16, int deactivate_fluc_red, int sigtype, PredScr* Q) {
     enum { SURV = 16, NST = 6, ORD = LPC_ORDER, MAXC = 8 };
     const int lane = SB_LANE;
     auto& V = Q->u.vq;
@@ -1211,6 +1234,7 @@ SB_CFN void c_nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& c
         const i16* CB = cb.cb_q15 + cb_off * ORD;
         const i16* Rates = cb.rates_q5 + cb_off;
         const int ncand = prev_survivors * nVec;
+        const int lg = 31 - clz32(nVec);
         cur_survivors = imin(SURV, ncand);
         // values of my pairs e = lane, lane + 32, ...
         i32 val[MAXC];
@@ -1220,7 +1244,7 @@ SB_CFN void c_nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& c
             const int e = lane + 32 * r;
             val[r] = SB_I32_MAX;
             if (e < ncand) {
-                const int n = e / nVec, i = e - n * nVec;
+                const int n = e >> lg, i = e & (nVec - 1);      // nVec is a power of two in both codebooks
                 const i32* in = &V.res[cur][n * ORD];
                 const i16* v = CB + i * ORD;
                 i32 sum_error = 0;
@@ -1235,8 +1259,7 @@ SB_CFN void c_nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& c
         {
             int rank = 0;
             for (int l = 0; l < 32; l++) { const i32 o = wshfl(mymin, l); rank += (o < mymin) || (o == mymin && l < lane); }
-            const u32 b = wballot(rank == SURV - 1);
-            U = wshfl(mymin, ctz32(b));
+            U = wshfl(mymin, ctz32(wballot(rank == SURV - 1)));
         }
         // compact the pairs with value <= U in scan order (e ascending)
         int M = 0;
@@ -1292,12 +1315,12 @@ SB_CFN void c_nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& c
         for (int t = lane; t < cur_survivors * ORD; t += 32) {
             const int kx = t / ORD, m = t - kx * ORD;
             const int e = V.best_e[kx];
-            const int input_index = s > 0 ? e / nVec : 0, cb_index = s > 0 ? e - input_index * nVec : e;
+            const int input_index = s > 0 ? e >> lg : 0, cb_index = s > 0 ? e & (nVec - 1) : e;
             V.res[nxt][kx * ORD + m] = V.res[cur][input_index * ORD + m] - (i32)CB[cb_index * ORD + m];
         }
         if (lane < cur_survivors) {
             const int e = V.best_e[lane];
-            const int input_index = s > 0 ? e / nVec : 0, cb_index = s > 0 ? e - input_index * nVec : e;
+            const int input_index = s > 0 ? e >> lg : 0, cb_index = s > 0 ? e & (nVec - 1) : e;
             V.rate[nxt][lane] = V.rate[cur][input_index] + Rates[cb_index];
             u64 pth = ((u64)V.path_hi[cur][input_index] << 32) | V.path_lo[cur][input_index];
             pth |= (u64)(u32)cb_index << (8 * s);
@@ -1309,23 +1332,35 @@ SB_CFN void c_nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& c
         cb_off += nVec;
     }
     // survivors now in [cur]; V.best_v holds their rate-distortion values in order
-    i32 bestIndex = 0;
-    if (deactivate_fluc_red != 1) {      // uniform
+    // fluctuation reduction: decode every survivor (one scalar instance each) and weigh its distance to the previous frame
+    if (lane == 0) { Q->vq_meta[0] = cur; Q->vq_meta[1] = cur_survivors; Q->vq_meta[2] = deactivate_fluc_red; Q->vq_meta[3] = NLSF_mu_fluc_red_Q16; Q->vq_meta[4] = sigtype; }
+    c_instances<SURV>([&](int d, int k) {
+        PredScr* Qj = xoff(Q, d);
+        if (Qj->vq_meta[2] == 1) return;
         i32 wsse = SB_I32_MAX;
-        if (lane < cur_survivors) {
-            const u64 pth = ((u64)V.path_hi[cur][lane] << 32) | V.path_lo[cur][lane];
+        if (k < Qj->vq_meta[1]) {
+            auto& Vj = Qj->u.vq;
+            const int cj = Qj->vq_meta[0];
+            const NlsfCb cbj = nlsf_cb(Qj->vq_meta[4]);
+            const i32* prevj = xoff(pNLSF_q_Q15_prev, d);
+            const u64 pth = ((u64)Vj.path_hi[cj][k] << 32) | Vj.path_lo[cj][k];
             i32 idx[NST];
 #pragma unroll
             for (int i = 0; i < NST; i++) idx[i] = (i32)((pth >> (8 * i)) & 0xff);
-            i32* nl = V.nlsf_s[lane];
-            nlsf_msvq_decode(nl, cb, idx);
+            i32* nl = Vj.nlsf_s[k];
+            nlsf_msvq_decode(nl, cbj, idx);
             i32 wsse_Q20 = 0;
             for (int i = 0; i < ORD; i++) {
-                const i32 se = nl[i] - pNLSF_q_Q15_prev[i];
-                wsse_Q20 = smlawb(wsse_Q20, smulbb(se, se), wq[i]);
+                const i32 se = nl[i] - prevj[i];
+                wsse_Q20 = smlawb(wsse_Q20, smulbb(se, se), Qj->NLSFW_Q6[i]);
             }
-            wsse = add_pos_sat32(V.best_v[lane], smulwb(wsse_Q20, NLSF_mu_fluc_red_Q16));
+            wsse = add_pos_sat32(Vj.best_v[k], smulwb(wsse_Q20, Qj->vq_meta[3]));
         }
+        Qj->vq_wsse[k] = wsse;
+    });
+    i32 bestIndex = 0;
+    if (deactivate_fluc_red != 1) {      // per stream
+        i32 wsse = lane < SURV ? Q->vq_wsse[lane] : SB_I32_MAX;
         i32 who = lane;
         wargmin(wsse, who);       // first of equal minima; a value equal to INT_MAX never wins in the reference either
         bestIndex = wsse < SB_I32_MAX ? who : 0;
@@ -1333,14 +1368,15 @@ SB_CFN void c_nlsf_msvq_encode(i32* NLSFIndices, i32* pNLSF_Q15, const NlsfCb& c
     SB_SYNC();
     const u64 pth = ((u64)V.path_hi[cur][bestIndex] << 32) | V.path_lo[cur][bestIndex];
     if (lane < NST) NLSFIndices[lane] = (i32)((pth >> (8 * lane)) & 0xff);
-    SB_SYNC();
-    if (lane == 0) {
+    c_instances<1>([&](int d, int) {
+        PredScr* Qj = xoff(Q, d);
+        const i32* ixj = xoff(NLSFIndices, d);
+        i32* outj = xoff(pNLSF_Q15, d);
         i32 idx[NST], nl[ORD];
-        for (int i = 0; i < NST; i++) idx[i] = NLSFIndices[i];
-        nlsf_msvq_decode(nl, cb, idx);
-        for (int i = 0; i < ORD; i++) pNLSF_Q15[i] = nl[i];
-    }
-    SB_SYNC();
+        for (int i = 0; i < NST; i++) idx[i] = ixj[i];
+        nlsf_msvq_decode(nl, nlsf_cb(Qj->vq_meta[4]), idx);
+        for (int i = 0; i < ORD; i++) outj[i] = nl[i];
+    });
 }
 
 // SKP_Silk_process_NLSFs_FIX (process_NLSFs_FIX.c:31-127)
@@ -1357,15 +1393,21 @@ SB_CFN void c_process_nlsfs(EncSilk* st, EncCtrl* c, i32* pNLSF_Q15, PredScr* Q,
     }
     NLSF_mu_Q15 = imax(NLSF_mu_Q15, 1);
     const int doInterpolate = interpQ2 < (1 << 2);
-    // Laroia weights: lane 0 for the target vector, lane 1 for the interpolated one (eleven divisions each)
-    if (lane < 2) {
+    // Laroia weights: one scalar instance for the target vector, one for the interpolated one (eleven divisions each)
+    c_instances<2>([&](int d, int k) {
+        PredScr* Qj = xoff(Q, d);
+        const i32* nlj = xoff(pNLSF_Q15, d);
         i32 nl[LPC_ORDER], w[LPC_ORDER];
-        if (lane == 0) { for (int i = 0; i < LPC_ORDER; i++) nl[i] = pNLSF_Q15[i]; }
-        else { i32 a[LPC_ORDER], b[LPC_ORDER]; for (int i = 0; i < LPC_ORDER; i++) { a[i] = st->prev_NLSFq_Q15[i]; b[i] = pNLSF_Q15[i]; } interpolate(nl, a, b, interpQ2, LPC_ORDER); }
+        if (k == 0) { for (int i = 0; i < LPC_ORDER; i++) nl[i] = nlj[i]; }
+        else {
+            const EncSilk* sj = xoff(st, d);
+            i32 a[LPC_ORDER], b[LPC_ORDER];
+            for (int i = 0; i < LPC_ORDER; i++) { a[i] = sj->prev_NLSFq_Q15[i]; b[i] = nlj[i]; }
+            interpolate(nl, a, b, xoff(c, d)->NLSFInterpCoef_Q2, LPC_ORDER);
+        }
         nlsf_vq_weights_laroia(w, nl, LPC_ORDER);
-        for (int i = 0; i < LPC_ORDER; i++) Q->u.vq.nlsf_s[lane][i] = w[i];
-    }
-    SB_SYNC();
+        for (int i = 0; i < LPC_ORDER; i++) Qj->u.vq.nlsf_s[k][i] = w[i];
+    });
     if (lane < LPC_ORDER) {
         i32 w = Q->u.vq.nlsf_s[0][lane];
         if (doInterpolate) {
@@ -1381,19 +1423,24 @@ SB_CFN void c_process_nlsfs(EncSilk* st, EncCtrl* c, i32* pNLSF_Q15, PredScr* Q,
         cb.rates_q5 = sigtype == 0 ? fast->rates0 : fast->rates1;
     }
     c_nlsf_msvq_encode(c->NLSFIndices, pNLSF_Q15, cb, st->prev_NLSFq_Q15, Q->NLSFW_Q6, NLSF_mu_Q15, NLSF_mu_fluc_red_Q16,
-                       st->first_frame_after_reset, Q);
-    // quantised NLSFs -> prediction filters of the two half-frames (two lanes)
-    if (lane < 2) {
+                       st->first_frame_after_reset, sigtype, Q);
+    // quantised NLSFs -> prediction filters of the two half-frames (two scalar instances)
+    c_instances<2>([&](int d, int k) {
+        const i32* nlj = xoff(pNLSF_Q15, d);
+        EncCtrl* cj = xoff(c, d);
         i32 nl[LPC_ORDER];
         i16 a12[LPC_ORDER];
-        bool need = true;
-        if (lane == 1) { for (int i = 0; i < LPC_ORDER; i++) nl[i] = pNLSF_Q15[i]; }
-        else if (doInterpolate) { i32 a[LPC_ORDER], b[LPC_ORDER]; for (int i = 0; i < LPC_ORDER; i++) { a[i] = st->prev_NLSFq_Q15[i]; b[i] = pNLSF_Q15[i]; } interpolate(nl, a, b, interpQ2, LPC_ORDER); }
-        else { for (int i = 0; i < LPC_ORDER; i++) nl[i] = pNLSF_Q15[i]; need = true; }
-        if (need) nlsf2a_stable(a12, nl, LPC_ORDER);
-        for (int i = 0; i < LPC_ORDER; i++) c->PredCoef_Q12[lane][i] = a12[i];
-    }
-    SB_SYNC();
+        const int iq = cj->NLSFInterpCoef_Q2;
+        if (k == 1 || iq >= (1 << 2)) { for (int i = 0; i < LPC_ORDER; i++) nl[i] = nlj[i]; }
+        else {
+            const EncSilk* sj = xoff(st, d);
+            i32 a[LPC_ORDER], b[LPC_ORDER];
+            for (int i = 0; i < LPC_ORDER; i++) { a[i] = sj->prev_NLSFq_Q15[i]; b[i] = nlj[i]; }
+            interpolate(nl, a, b, iq, LPC_ORDER);
+        }
+        nlsf2a_stable(a12, nl, LPC_ORDER);
+        for (int i = 0; i < LPC_ORDER; i++) cj->PredCoef_Q12[k][i] = a12[i];
+    });
 }
 
 // SKP_Silk_find_pred_coefs_FIX (find_pred_coefs_FIX.c:31-131)
@@ -1414,15 +1461,24 @@ SB_CFN void c_find_pred_coefs(EncSilk* st, EncCtrl* c, PredScr* Q, const i16* re
     }
     SB_SYNC();
     const i16* xb = st->x_buf + FRAME - LPC_ORDER;
-    if (sigtype == 0) {       // uniform
-        if (lane < NB_SUBFR)
-            find_ltp_subfr(lane, c->LTPCoef_Q14 + lane * LTP_ORDER, Q->WLTP + lane * LTP_ORDER * LTP_ORDER, &Q->ltp[lane], res_pitch,
-                           res_pitch + (FRAME >> 1), c->pitchL[lane], Q->Wght_Q15[lane]);
-        SB_SYNC();
-        if (lane == 0) find_ltp_tail(c->LTPCoef_Q14, &c->LTPredCodGain_Q7, Q->ltp, Q->Wght_Q15);
-        SB_SYNC();
+    // LTP analysis of the voiced streams: the four sub-frames as four scalar instances, then the part that couples them
+    c_instances<NB_SUBFR>([&](int d, int k) {
+        EncCtrl* cj = xoff(c, d);
+        if (cj->sigtype != 0) return;
+        PredScr* Qj = xoff(Q, d);
+        const i16* rp = xoff(res_pitch, d);
+        find_ltp_subfr(k, cj->LTPCoef_Q14 + k * LTP_ORDER, Qj->WLTP + k * LTP_ORDER * LTP_ORDER, &Qj->ltp[k], rp, rp + (FRAME >> 1),
+                       cj->pitchL[k], Qj->Wght_Q15[k]);
+    });
+    c_instances<1>([&](int d, int) {
+        EncCtrl* cj = xoff(c, d);
+        if (cj->sigtype != 0) return;
+        PredScr* Qj = xoff(Q, d);
+        find_ltp_tail(cj->LTPCoef_Q14, &cj->LTPredCodGain_Q7, Qj->ltp, Qj->Wght_Q15);
+        ltp_scale_ctrl(xoff(st, d), cj, frame_in_packet);      // independent of the gain quantisation below
+    });
+    if (sigtype == 0) {       // per stream
         c_quant_ltp_gains(c->LTPCoef_Q14, c->LTPIndex, &c->PERIndex, Q->WLTP, SB_FIXC(0.03f, 8));
-        SB_SERIAL(ltp_scale_ctrl(st, c, frame_in_packet));
         // SKP_Silk_LTP_analysis_filter_FIX (LTP_analysis_filter_FIX.c:30-80): lanes over outputs
         for (int t = lane; t < NB_SUBFR * (SUBFR + LPC_ORDER); t += 32) {
             const int k = t / (SUBFR + LPC_ORDER), i = t - k * (SUBFR + LPC_ORDER);
@@ -1594,15 +1650,26 @@ struct CoopWork {
     } u;
 };
 
+// One stream's slot in the shared memory of the core-analysis kernel: persistent state + working set of the packet.
+struct AnaSmem {
+    EncSilk st;
+    CoopWork W;
+};
+SB_CFN int sb_slot_bytes() { return (int)sizeof(AnaSmem); }
+
 // SKP_Silk_encode_frame_FIX (encode_frame_FIX.c:34-131, 151-165, 199-208) up to the quantiser, one 20 ms frame.
 SB_CFN void c_encode_frame_analysis(EncSilk* st, CoopWork* W, const i16* pIn, int frame_in_packet, const NlsfFastTabs* fast) {
     EncCtrl* c = &W->c;
     i16* x_frame = st->x_buf + FRAME;
-    SB_SERIAL(
-        c->Seed = st->frameCounter++ & 3;
-        vad_get_sa_q8(&st->vad, &st->speech_activity_Q8, c->input_quality_bands_Q15, &c->input_tilt_Q15, pIn);
-        hp_variable_cutoff(st, c, W->pIn_HP, pIn);
-    );
+    c_instances<1>([&](int d, int) {
+        EncSilk* sj = xoff(st, d);
+        CoopWork* Wj = xoff(W, d);
+        EncCtrl* cj = &Wj->c;
+        const i16* pj = xoff(pIn, d);
+        cj->Seed = sj->frameCounter++ & 3;
+        vad_get_sa_q8(&sj->vad, &sj->speech_activity_Q8, cj->input_quality_bands_Q15, &cj->input_tilt_Q15, pj);
+        hp_variable_cutoff(sj, cj, Wj->pIn_HP, pj);
+    });
     SB_PARFOR(i, 0, FRAME) x_frame[LA_SHAPE + i] = W->pIn_HP[i];   // LP_variable_cutoff is a copy (transition_frame_no == 0)
     SB_SYNC();
     SB_PHASE();
@@ -1613,13 +1680,15 @@ SB_CFN void c_encode_frame_analysis(EncSilk* st, CoopWork* W, const i16* pIn, in
     c_prefilter(st, c, &W->u.pref, W->xfw, x_frame);
     SB_PHASE();
     c_find_pred_coefs(st, c, &W->u.pred, W->res_pitch, frame_in_packet, fast);
-    SB_SERIAL(
-        process_gains(st, c, frame_in_packet);
-        vad_flag_and_dtx(st, &W->vadFlag);
-        st->prev_sigtype = c->sigtype;
-        st->prevLag = c->pitchL[NB_SUBFR - 1];
-        st->first_frame_after_reset = 0;
-    );
+    c_instances<1>([&](int d, int) {
+        EncSilk* sj = xoff(st, d);
+        CoopWork* Wj = xoff(W, d);
+        process_gains(sj, &Wj->c, frame_in_packet);
+        vad_flag_and_dtx(sj, &Wj->vadFlag);
+        sj->prev_sigtype = Wj->c.sigtype;
+        sj->prevLag = Wj->c.pitchL[NB_SUBFR - 1];
+        sj->first_frame_after_reset = 0;
+    });
     {   // x_buf slides by one frame: [0,160) <- [160,320), then [160,200) <- [320,360) (each step reads only unwritten words)
         i32* xb = reinterpret_cast<i32*>(st->x_buf);
         SB_PARFOR(i, 0, FRAME / 2) xb[i] = xb[FRAME / 2 + i];

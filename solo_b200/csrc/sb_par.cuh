@@ -245,6 +245,36 @@ SB_HD i64 wshfl64(i64 v, int) { return v; }
 SB_HD u32 wballot(bool p) { return p ? 1u : 0u; }
 #endif
 
+// ---- per-stream serial work, transposed over the block ---------------------------------------------------------------
+// A block of the analysis kernel holds SB_BLOCK_STREAMS streams, one warp and one shared-memory slot each.  Work that exists
+// K times per stream as a short scalar recursion (K = 1: the signal-rate recurrences; K = 4: shaping windows, LTP
+// sub-frames, interpolation candidates ...) would occupy K lanes of every warp; c_instances<K> instead hands all
+// SB_BLOCK_STREAMS * K instances of the block to consecutive threads (stream = id / K), so that the issue slots it costs do
+// not grow with the number of streams -- while another block of the SM is in a wide phase.  f(d, k): d = byte offset from
+// the caller's own slot to the instance's slot (apply with xoff), k = instance number inside the stream.
+#if defined(__CUDA_ARCH__) && defined(SB_COOP) && defined(SB_XPOSE)
+#define SB_XPOSE_ACTIVE 1
+#else
+#define SB_XPOSE_ACTIVE 0
+#endif
+#if SB_COOP_ACTIVE
+SB_CFN int sb_slot_bytes();      // stride of the per-stream slots (defined with the slot layout)
+template <class T> SB_HD T* xoff(T* p, int d) { return reinterpret_cast<T*>(reinterpret_cast<char*>(p) + d); }
+template <class T> SB_HD const T* xoff(const T* p, int d) { return reinterpret_cast<const T*>(reinterpret_cast<const char*>(p) + d); }
+template <int K, class F> SB_CFN void c_instances(F f) {
+#if SB_XPOSE_ACTIVE
+    __syncthreads();
+    const int id = (int)threadIdx.x;
+    if (id < SB_BLOCK_STREAMS * K) { const int sj = id / K; f((sj - (id >> 5)) * sb_slot_bytes(), id - sj * K); }
+    __syncthreads();
+#else
+    SB_SYNC();
+    if (SB_LANE < K) f(0, SB_LANE);
+    SB_SYNC();
+#endif
+}
+#endif
+
 // ---- Arena: LIFO scratch shared by the lanes of a stream (shared memory on the device) ------------------------------
 // Every lane executes the same alloc / release sequence, so the pointers are uniform without any communication.
 struct Arena {
