@@ -7,6 +7,11 @@
 // State moves between HBM and shared memory with 128-bit accesses, 512 contiguous bytes per warp instruction; both kernels
 // read the band-split rows [low | high] that the QMF kernel (solo_b200.cu) wrote.
 #define SB_COOP 1
+// Code size is a first-order cost here: a warp executes most of its instructions once per packet, so the kernel streams its
+// code through the 32 KB instruction cache.  Routines with many call sites are kept out of line in this translation unit.
+#ifndef SB_ANA_INLINE_ALL
+#define SB_DIV_OUTLINE 1
+#endif
 #ifndef SB_NO_PHASE_ALIGN
 #define SB_PHASE_ALIGN 1
 #endif
@@ -43,11 +48,22 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, int bytes, in
     for (int i = lane; i < bytes / 16; i += 32) d[i] = s[i];
 }
 
-__global__ void __launch_bounds__(SB_ANA_WARPS * 32) sb_enc_analysis_warp_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ bands, int spp, int n) {
+#ifndef SB_ANA_SMEM_TABS
+#define SB_ANA_SMEM_TABS 1  // a copy of the NLSF codebooks (4.2 KB) per block in shared memory
+#endif
+#define SB_ANA_TABS_BYTES (SB_ANA_SMEM_TABS ? ((sizeof(NlsfFastTabs) + 15) & ~15) : 0)
+#ifndef SB_ANA_MINB
+#define SB_ANA_MINB 2      // resident blocks per SM the register budget is sized for
+#endif
+__global__ void __launch_bounds__(SB_ANA_WARPS * 32, SB_ANA_MINB) sb_enc_analysis_warp_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ bands, int spp, int n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#if SB_ANA_SMEM_TABS
     NlsfFastTabs* tabs = reinterpret_cast<NlsfFastTabs*>(smem_raw);
     nlsf_fast_tabs_fill(tabs, threadIdx.x, blockDim.x);
     __syncthreads();
+#else
+    NlsfFastTabs* tabs = nullptr;        // code vectors come from the global tables (L1 / L2 resident)
+#endif
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int s = blockIdx.x * SB_ANA_WARPS + w;
     // every warp of the block takes part in the phase barriers: a warp beyond the batch shadows the last stream (same inputs,
@@ -56,7 +72,7 @@ __global__ void __launch_bounds__(SB_ANA_WARPS * 32) sb_enc_analysis_warp_kernel
     if (!live) s = n - 1;
     // the slot address as an opaque 32-bit shared-window offset: kept in a register instead of being recomputed from threadIdx
     // at every use (the compiler otherwise rematerialises it ~130 times)
-    unsigned slot = (unsigned)__cvta_generic_to_shared(smem_raw + ((sizeof(NlsfFastTabs) + 15) & ~15)) + (unsigned)w * (unsigned)sizeof(AnaSmem);
+    unsigned slot = (unsigned)__cvta_generic_to_shared(smem_raw + SB_ANA_TABS_BYTES) + (unsigned)w * (unsigned)sizeof(AnaSmem);
     asm volatile("" : "+r"(slot));
     AnaSmem* S = reinterpret_cast<AnaSmem*>(__cvta_shared_to_generic(slot));
     copy16(&S->st, static_cast<EncSilk*>(&states[s]), (int)sizeof(EncSilk), lane);
@@ -92,7 +108,7 @@ __global__ void __launch_bounds__(SB_HB_WARPS * 32) sb_enc_hb_warp_kernel(EncSta
 // called from the host code in solo_b200.cu; return a CUDA error code
 extern "C" int sb_launch_enc_analysis_warp(void* states, void* scratch, const void* bands, int spp, int n, void* stream) {
     static bool configured = false;
-    const int smem = (int)((sizeof(NlsfFastTabs) + 15) & ~15) + SB_ANA_WARPS * (int)sizeof(AnaSmem);
+    const int smem = (int)SB_ANA_TABS_BYTES + SB_ANA_WARPS * (int)sizeof(AnaSmem);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(sb_enc_analysis_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
@@ -114,4 +130,17 @@ extern "C" int sb_launch_enc_hb_warp(void* states, void* scratch, const void* ba
         (EncState*)states, (EncScratch*)scratch, (const i16*)bands, spp, n);
     return (int)cudaGetLastError();
 }
+#ifdef SB_PHASE_TIMING
+extern "C" int sb_phase_times_read(long long* stamps, int* lines, int cap) {
+    int n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, sb_phase_count, sizeof(int));
+    if (n > cap) n = cap;
+    cudaMemcpyFromSymbol(stamps, sb_phase_stamp, sizeof(long long) * n);
+    cudaMemcpyFromSymbol(lines, sb_phase_line, sizeof(int) * n);
+    int zero = 0;
+    cudaMemcpyToSymbol(sb_phase_count, &zero, sizeof(int));
+    return n;
+}
+#endif
 extern "C" int sb_analysis_smem_bytes(int which) { return which == 0 ? (int)sizeof(AnaSmem) : (int)sizeof(HbSmem); }

@@ -31,6 +31,13 @@
 #define SB_FN inline
 #define SB_FN_BIG inline
 #endif
+// the two approximate-division helpers (~40 instructions, > 100 call sites in the analysis kernel): one out-of-line copy where
+// code size matters more than the call (the warp-per-stream kernels execute most instructions once per packet)
+#if defined(__CUDACC__) && defined(SB_DIV_OUTLINE)
+#define SB_HD_DIV __host__ __device__ __noinline__ inline
+#else
+#define SB_HD_DIV SB_HD
+#endif
 
 namespace sb {
 
@@ -229,7 +236,7 @@ SB_HD i32 div_q29(i32 d) {
 }
 
 // ---- approximate division (Inlines.h:124-217); reproduced step by step, never an exact divide --------
-SB_HD i32 div32_varq(i32 a32, i32 b32, int qres) {
+SB_HD_DIV i32 div32_varq(i32 a32, i32 b32, int qres) {
     int a_headrm = clz32(iabs(a32)) - 1;
     i32 a_nrm = shl(a32, a_headrm);
     int b_headrm = clz32(iabs(b32)) - 1;
@@ -243,7 +250,7 @@ SB_HD i32 div32_varq(i32 a32, i32 b32, int qres) {
     if (lshift < 32) return result >> lshift;
     return 0;
 }
-SB_HD i32 inverse32_varq(i32 b32, int qres) {
+SB_HD_DIV i32 inverse32_varq(i32 b32, int qres) {
     int b_headrm = clz32(iabs(b32)) - 1;
     i32 b_nrm = shl(b32, b_headrm);
     i32 b_inv = div_q29(b_nrm >> 16);

@@ -250,7 +250,21 @@ SB_CFN int c_pitch_analysis_core(PitchScr* P, const i16* signal, i32* pitch_out,
     for (int j = 0; j < 3; j++) { const int i = lane + 32 * j; if (i < NL4) P->C1[0][i] = (i16)cs[j]; }
     SB_SYNC();
     int length_d_srch = 4 + 2 * 2;
-    c_instances<1>([&](int d, int) { PitchScr* Pj = xoff(P, d); insertion_sort_decreasing_i16(&Pj->C1[0][0], Pj->d_srch, NL4, 4 + 2 * 2); });
+    {   // the eight largest of the 65 smoothed correlations, in the order the reference's stable partial insertion sort
+        // (sort.c:79-124) leaves them: by value, equal values by position.  Eight rounds of a warp-wide arg-max.
+        i32 v3[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) { const int i = lane + 32 * j; v3[j] = i < NL4 ? (i32)P->C1[0][i] : SB_I32_MIN; }
+        SB_SYNC();
+        for (int r = 0; r < 4 + 2 * 2; r++) {
+            i32 bv = v3[0], bi = lane;
+            if (v3[1] > bv) { bv = v3[1]; bi = lane + 32; }
+            if (v3[2] > bv) { bv = v3[2]; bi = lane + 64; }
+            wargmax(bv, bi);        // ties: smallest position
+            if (lane == (bi & 31)) { const int j = bi >> 5; if (j == 0) v3[0] = SB_I32_MIN; else if (j == 1) v3[1] = SB_I32_MIN; else v3[2] = SB_I32_MIN; }
+            if (lane == 0) { P->C1[0][r] = (i16)bv; P->d_srch[r] = bi; }
+        }
+    }
     i32 energy;
     {
         i32 part = 0;
@@ -465,6 +479,8 @@ struct ShapeScr {
     i32 scale[NB_SUBFR];
     i32 par3[3];                 // warping_Q16, BWExp1_Q16, BWExp2_Q16 for the per-window instances
     i32 gains[NB_SUBFR][2];      // their results: Gains_Q16, GainsPre_Q14 before the frame-level tweaks
+    i32 ar[NB_SUBFR][2][SHAPE_ORDER];   // AR2_Q24, AR1_Q24 between the instance stages
+    i32 invgain[NB_SUBFR][2];
 };
 
 // Warped autocorrelation of the four shaping windows at once (SKP_Silk_warped_autocorrelation_FIX.c:36-85): the 16
@@ -503,6 +519,135 @@ SB_CFN void c_warped_autocorr4(ShapeScr* S, i32 warping_Q16) {
         if (g == 7) corr[16] = (i32)(c2 >> (-lsh));
     }
     if (g == 0) S->scale[win] = -(QC + lsh);
+}
+
+// ---- the per-window recursions with every array in registers (fixed order, fully unrolled): on the device these run as
+// one scalar instance per window, where a local-memory array would put a ~30-cycle load into every step of a long
+// dependent chain.  Same arithmetic as schur64 / k2a_q16 / lpc_inv_pred_gain_qa / limit_warped_coefs (sb_sigproc.cuh,
+// sb_enc_shape.cuh), which remain the reference statements.
+template <int ORD> SB_CFN i32 schur64_r(i32 (&rc_Q16)[ORD], const i32 (&c)[ORD + 1]) {
+    i32 C0[ORD + 1], C1[ORD + 1];
+    if (c[0] <= 0) {
+#pragma unroll
+        for (int k = 0; k < ORD; k++) rc_Q16[k] = 0;
+        return 0;
+    }
+#pragma unroll
+    for (int k = 0; k < ORD + 1; k++) C0[k] = C1[k] = c[k];
+#pragma unroll
+    for (int k = 0; k < ORD; k++) {
+        const i32 rc_Q31 = div32_varq(negw(C0[k + 1]), C1[0], 31);
+        rc_Q16[k] = rshift_round(rc_Q31, 15);
+#pragma unroll
+        for (int n = 0; n < ORD - k; n++) {
+            const i32 t1 = C0[n + k + 1], t2 = C1[n];
+            C0[n + k + 1] = addw(t1, smmul(shl(t2, 1), rc_Q31));
+            C1[n] = addw(t2, smmul(shl(t1, 1), rc_Q31));
+        }
+    }
+    return C1[0];
+}
+template <int ORD> SB_CFN void k2a_q16_r(i32 (&A_Q24)[ORD], const i32 (&rc_Q16)[ORD]) {
+#pragma unroll
+    for (int k = 0; k < ORD; k++) {
+        i32 Atmp[ORD];
+#pragma unroll
+        for (int n = 0; n < k; n++) Atmp[n] = A_Q24[n];
+#pragma unroll
+        for (int n = 0; n < k; n++) A_Q24[n] = smlaww(A_Q24[n], Atmp[k - n - 1], rc_Q16[k]);
+        A_Q24[k] = negw(shl(rc_Q16[k], 8));
+    }
+}
+// SKP_Silk_LPC_inverse_pred_gain_Q24 (LPC_inv_pred_gain.c:42-153 + :170-185); returns 1 when unstable
+template <int ORD> SB_CFN int lpc_inv_pred_gain_q24_r(i32* invGain_Q30, const i32 (&A_Q24)[ORD]) {
+    const i32 A_LIMIT = SB_FIXC(0.99975, 16);
+    i32 A[ORD];
+#pragma unroll
+    for (int k = 0; k < ORD; k++) A[k] = rshift_round(A_Q24[k], 8);
+    i32 inv = 1 << 30;
+    bool bad = false;
+#pragma unroll
+    for (int k = ORD - 1; k > 0; k--) {
+        if (!bad) {
+            if (A[k] > A_LIMIT || A[k] < -A_LIMIT) bad = true;
+            else {
+                const i32 rc_Q31 = negw(shl(A[k], 31 - 16));
+                const i32 rc_mult1_Q30 = (SB_I32_MAX >> 1) - smmul(rc_Q31, rc_Q31);
+                i32 rc_mult2_Q16 = inverse32_varq(rc_mult1_Q30, 46);
+                inv = shl(smmul(inv, rc_mult1_Q30), 2);
+                const int headrm = clz32(rc_mult2_Q16) - 1;
+                rc_mult2_Q16 = shl(rc_mult2_Q16, headrm);
+                i32 An[ORD];
+#pragma unroll
+                for (int n = 0; n < k; n++) {
+                    const i32 tmp = subw(A[n], shl(smmul(A[k - n - 1], rc_Q31), 1));
+                    An[n] = shl(smmul(tmp, rc_mult2_Q16), 16 - headrm);
+                }
+#pragma unroll
+                for (int n = 0; n < k; n++) A[n] = An[n];
+            }
+        }
+    }
+    if (bad) { *invGain_Q30 = inv; return 1; }
+    if (A[0] > A_LIMIT || A[0] < -A_LIMIT) { *invGain_Q30 = inv; return 1; }
+    const i32 rc_Q31 = negw(shl(A[0], 31 - 16));
+    const i32 rc_mult1_Q30 = (SB_I32_MAX >> 1) - smmul(rc_Q31, rc_Q31);
+    *invGain_Q30 = shl(smmul(inv, rc_mult1_Q30), 2);
+    return 0;
+}
+template <int ORD> SB_CFN void bwexpander_32_r(i32 (&ar)[ORD], i32 chirp_Q16) {
+    i32 t = chirp_Q16;
+#pragma unroll
+    for (int i = 0; i < ORD - 1; i++) { ar[i] = smulww(ar[i], t); t = smulww(chirp_Q16, t); }
+    ar[ORD - 1] = smulww(ar[ORD - 1], t);
+}
+// SKP_Silk_noise_shape_analysis_FIX.c:52-132
+template <int ORD> SB_CFN void limit_warped_coefs_r(i32 (&syn)[ORD], i32 (&ana)[ORD], i32 lambda_Q16, i32 limit_Q24) {
+    i32 nom_Q16, den_Q24, gain_syn_Q16, gain_ana_Q16;
+    lambda_Q16 = -lambda_Q16;
+#pragma unroll
+    for (int i = ORD - 1; i > 0; i--) { syn[i - 1] = smlawb(syn[i - 1], syn[i], lambda_Q16); ana[i - 1] = smlawb(ana[i - 1], ana[i], lambda_Q16); }
+    lambda_Q16 = -lambda_Q16;
+    nom_Q16 = smlawb(SB_FIXC(1.0, 16), -lambda_Q16, lambda_Q16);
+    den_Q24 = smlawb(SB_FIXC(1.0, 24), syn[0], lambda_Q16);
+    gain_syn_Q16 = div32_varq(nom_Q16, den_Q24, 24);
+    den_Q24 = smlawb(SB_FIXC(1.0, 24), ana[0], lambda_Q16);
+    gain_ana_Q16 = div32_varq(nom_Q16, den_Q24, 24);
+#pragma unroll
+    for (int i = 0; i < ORD; i++) { syn[i] = smulww(gain_syn_Q16, syn[i]); ana[i] = smulww(gain_ana_Q16, ana[i]); }
+    for (int iter = 0; iter < 10; iter++) {
+        i32 maxabs_Q24 = -1; int ind = 0;
+#pragma unroll
+        for (int i = 0; i < ORD; i++) {
+            i32 a = syn[i], b = ana[i];
+            a = (a ^ (a >> 31)) - (a >> 31);
+            b = (b ^ (b >> 31)) - (b >> 31);
+            const i32 tmp = imax(a, b);
+            if (tmp > maxabs_Q24) { maxabs_Q24 = tmp; ind = i; }
+        }
+        if (maxabs_Q24 <= limit_Q24) return;
+#pragma unroll
+        for (int i = 1; i < ORD; i++) { syn[i - 1] = smlawb(syn[i - 1], syn[i], lambda_Q16); ana[i - 1] = smlawb(ana[i - 1], ana[i], lambda_Q16); }
+        gain_syn_Q16 = inverse32_varq(gain_syn_Q16, 32);
+        gain_ana_Q16 = inverse32_varq(gain_ana_Q16, 32);
+#pragma unroll
+        for (int i = 0; i < ORD; i++) { syn[i] = smulww(gain_syn_Q16, syn[i]); ana[i] = smulww(gain_ana_Q16, ana[i]); }
+        const i32 chirp_Q16 = SB_FIXC(0.99, 16) - div32_varq(
+            smulwb(maxabs_Q24 - limit_Q24, smlabb(SB_FIXC(0.8, 10), SB_FIXC(0.1, 10), iter)), mulw(maxabs_Q24, ind + 1), 22);
+        bwexpander_32_r<ORD>(syn, chirp_Q16);
+        bwexpander_32_r<ORD>(ana, chirp_Q16);
+        lambda_Q16 = -lambda_Q16;
+#pragma unroll
+        for (int i = ORD - 1; i > 0; i--) { syn[i - 1] = smlawb(syn[i - 1], syn[i], lambda_Q16); ana[i - 1] = smlawb(ana[i - 1], ana[i], lambda_Q16); }
+        lambda_Q16 = -lambda_Q16;
+        nom_Q16 = smlawb(SB_FIXC(1.0, 16), -lambda_Q16, lambda_Q16);
+        den_Q24 = smlawb(SB_FIXC(1.0, 24), syn[0], lambda_Q16);
+        gain_syn_Q16 = div32_varq(nom_Q16, den_Q24, 24);
+        den_Q24 = smlawb(SB_FIXC(1.0, 24), ana[0], lambda_Q16);
+        gain_ana_Q16 = div32_varq(nom_Q16, den_Q24, 24);
+#pragma unroll
+        for (int i = 0; i < ORD; i++) { syn[i] = smulww(gain_syn_Q16, syn[i]); ana[i] = smulww(gain_ana_Q16, ana[i]); }
+    }
 }
 
 // pitch_res points at res_pitch + FRAME, x at x_buf + FRAME.
@@ -579,28 +724,57 @@ SB_CFN void c_noise_shape_analysis(EncSilk* st, EncCtrl* c, ShapeScr* S, const i
         EncCtrl* cj = xoff(c, d);
         const i32 warp_Q16 = Sj->par3[0], bw1 = Sj->par3[1], bw2 = Sj->par3[2];
         i32 auto_corr[SHAPE_ORDER + 1], refl_coef_Q16[SHAPE_ORDER], AR1_Q24[SHAPE_ORDER], AR2_Q24[SHAPE_ORDER];
+#pragma unroll
         for (int i = 0; i <= SHAPE_ORDER; i++) auto_corr[i] = Sj->acorr[k][i];
         auto_corr[0] = addw(auto_corr[0], imax(smulwb(auto_corr[0] >> 4, SB_FIXC(1e-5f, 20)), 1));
-        i32 nrg = schur64(refl_coef_Q16, auto_corr, SHAPE_ORDER);
-        k2a_q16(AR2_Q24, refl_coef_Q16, SHAPE_ORDER);
+        i32 nrg = schur64_r<SHAPE_ORDER>(refl_coef_Q16, auto_corr);
+        k2a_q16_r<SHAPE_ORDER>(AR2_Q24, refl_coef_Q16);
         int Qnrg = -Sj->scale[k];
         if (Qnrg & 1) { Qnrg -= 1; nrg >>= 1; }
         const i32 tmp32 = sqrt_approx(nrg);
         Qnrg >>= 1;
         i32 gk = lshift_sat32(tmp32, 16 - Qnrg);
-        const i32 gain_mult_Q16 = warped_gain(AR2_Q24, warp_Q16, SHAPE_ORDER);
+        i32 gain_mult_Q16;
+        {   // warped_gain (noise_shape_analysis_FIX.c:33-50)
+            const i32 lam = -warp_Q16;
+            i32 g24 = AR2_Q24[SHAPE_ORDER - 1];
+#pragma unroll
+            for (int i = SHAPE_ORDER - 2; i >= 0; i--) g24 = smlawb(AR2_Q24[i], g24, lam);
+            g24 = smlawb(SB_FIXC(1.0, 24), g24, -lam);
+            gain_mult_Q16 = inverse32_varq(g24, 40);
+        }
         gk = smulww(gk, gain_mult_Q16);
         if (gk < 0) gk = SB_I32_MAX;
-        bwexpander_32(AR2_Q24, SHAPE_ORDER, bw2);
+        bwexpander_32_r<SHAPE_ORDER>(AR2_Q24, bw2);
+#pragma unroll
         for (int i = 0; i < SHAPE_ORDER; i++) AR1_Q24[i] = AR2_Q24[i];
-        bwexpander_32(AR1_Q24, SHAPE_ORDER, bw1);
-        i32 pre_nrg_Q30;
-        lpc_inv_pred_gain_q24(&pre_nrg_Q30, AR2_Q24, SHAPE_ORDER);
-        lpc_inv_pred_gain_q24(&nrg, AR1_Q24, SHAPE_ORDER);
-        pre_nrg_Q30 = shl(smulwb(pre_nrg_Q30, SB_FIXC(0.7, 15)), 1);
+        bwexpander_32_r<SHAPE_ORDER>(AR1_Q24, bw1);
         Sj->gains[k][0] = gk;
+#pragma unroll
+        for (int i = 0; i < SHAPE_ORDER; i++) { Sj->ar[k][0][i] = AR2_Q24[i]; Sj->ar[k][1][i] = AR1_Q24[i]; }
+    });
+    // inverse prediction gains of the eight filters (window x {AR2, AR1}): eight scalar instances side by side
+    c_instances<2 * NB_SUBFR>([&](int d, int q) {
+        ShapeScr* Sj = xoff(S, d);
+        i32 A[SHAPE_ORDER];
+#pragma unroll
+        for (int i = 0; i < SHAPE_ORDER; i++) A[i] = Sj->ar[q >> 1][q & 1][i];
+        i32 g;
+        lpc_inv_pred_gain_q24_r<SHAPE_ORDER>(&g, A);
+        Sj->invgain[q >> 1][q & 1] = g;
+    });
+    c_instances<NB_SUBFR>([&](int d, int k) {
+        ShapeScr* Sj = xoff(S, d);
+        EncCtrl* cj = xoff(c, d);
+        i32 AR1_Q24[SHAPE_ORDER], AR2_Q24[SHAPE_ORDER];
+#pragma unroll
+        for (int i = 0; i < SHAPE_ORDER; i++) { AR2_Q24[i] = Sj->ar[k][0][i]; AR1_Q24[i] = Sj->ar[k][1][i]; }
+        i32 pre_nrg_Q30 = Sj->invgain[k][0];
+        const i32 nrg = Sj->invgain[k][1];
+        pre_nrg_Q30 = shl(smulwb(pre_nrg_Q30, SB_FIXC(0.7, 15)), 1);
         Sj->gains[k][1] = SB_FIXC(0.3, 14) + div32_varq(pre_nrg_Q30, nrg, 14);
-        limit_warped_coefs(AR2_Q24, AR1_Q24, warp_Q16, SB_FIXC(3.999, 24), SHAPE_ORDER);
+        limit_warped_coefs_r<SHAPE_ORDER>(AR2_Q24, AR1_Q24, Sj->par3[0], SB_FIXC(3.999, 24));
+#pragma unroll
         for (int i = 0; i < SHAPE_ORDER; i++) {
             cj->AR1_Q13[k * SHAPE_ORDER + i] = (i16)sat16(rshift_round(AR1_Q24[i], 11));
             cj->AR2_Q13[k * SHAPE_ORDER + i] = (i16)sat16(rshift_round(AR2_Q24[i], 11));
@@ -1643,6 +1817,7 @@ struct CoopWork {
     alignas(16) i16 xfw[FRAME];
     i32 vadFlag;
     union {
+        i16 vadX[4][FRAME / 2];
         PitchScr pitch;
         ShapeScr shape;
         PrefScr pref;
@@ -1667,7 +1842,7 @@ SB_CFN void c_encode_frame_analysis(EncSilk* st, CoopWork* W, const i16* pIn, in
         EncCtrl* cj = &Wj->c;
         const i16* pj = xoff(pIn, d);
         cj->Seed = sj->frameCounter++ & 3;
-        vad_get_sa_q8(&sj->vad, &sj->speech_activity_Q8, cj->input_quality_bands_Q15, &cj->input_tilt_Q15, pj);
+        vad_get_sa_q8_x(&sj->vad, &sj->speech_activity_Q8, cj->input_quality_bands_Q15, &cj->input_tilt_Q15, pj, Wj->u.vadX);
         hp_variable_cutoff(sj, cj, Wj->pIn_HP, pj);
     });
     SB_PARFOR(i, 0, FRAME) x_frame[LA_SHAPE + i] = W->pIn_HP[i];   // LP_variable_cutoff is a copy (transition_frame_no == 0)

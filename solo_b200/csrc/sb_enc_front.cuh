@@ -39,9 +39,9 @@ SB_FN void vad_get_noise_levels(const i32* pX, VadState* v) {
 }
 
 // ---- SKP_Silk_VAD.c:75-255 (frame length 160) ------------------------------------------------------
-SB_FN void vad_get_sa_q8(VadState* v, i32* pSA_Q8, i32* pQuality_Q15, i32* pTilt_Q15, const i16* pIn) {
+// X: scratch for the four band signals (the device kernel passes shared memory)
+SB_FN void vad_get_sa_q8_x(VadState* v, i32* pSA_Q8, i32* pQuality_Q15, i32* pTilt_Q15, const i16* pIn, i16 (*X)[FRAME / 2]) {
     const i32 tiltWeights[4] = {30000, 6000, -12000, -12000};
-    i16 X[4][FRAME / 2];
     i32 Xnrg[4], NrgToNoiseRatio_Q8[4];
     ana_filt_bank_1(pIn, v->AnaState, X[0], X[3], FRAME);
     ana_filt_bank_1(X[0], v->AnaState1, X[0], X[2], FRAME >> 1);
@@ -107,6 +107,11 @@ SB_FN void vad_get_sa_q8(VadState* v, i32* pSA_Q8, i32* pQuality_Q15, i32* pTilt
         i32 SNR_Q7 = 3 * (lin2log(v->NrgRatioSmth_Q8[b]) - 8 * 128);
         pQuality_Q15[b] = sigm_q15((SNR_Q7 - 16 * 128) >> 4);
     }
+}
+
+SB_FN void vad_get_sa_q8(VadState* v, i32* pSA_Q8, i32* pQuality_Q15, i32* pTilt_Q15, const i16* pIn) {
+    i16 X[4][FRAME / 2];
+    vad_get_sa_q8_x(v, pSA_Q8, pQuality_Q15, pTilt_Q15, pIn, X);
 }
 
 // ---- SKP_Silk_HP_variable_cutoff_FIX.c:37-118 ---------------------------------------------------------

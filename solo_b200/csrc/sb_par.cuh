@@ -45,8 +45,20 @@ long long* scratch();   // 32 x 8-byte slots shared by the lanes of the current 
 #define SB_LANE0 (SB_LANE == 0)
 // Phase alignment: the warps of a block (one stream each) pass the analysis phases together, so that the instruction lines a
 // phase needs are fetched once per SM and not once per warp (the per-stream code path is long and mostly straight-line).
+#if defined(__CUDACC__) && defined(SB_PHASE_TIMING)
+// development aid: cycle stamps of one block at every phase boundary (tools/phase_times.py)
+__device__ long long sb_phase_stamp[512];
+__device__ int sb_phase_line[512];
+__device__ int sb_phase_count;
+__device__ __forceinline__ void sb_mark(int line) {
+    if (threadIdx.x == 0 && blockIdx.x == 300) { const int i = sb_phase_count; if (i < 512) { sb_phase_stamp[i] = clock64(); sb_phase_line[i] = line; sb_phase_count = i + 1; } }
+}
+#define SB_MARK() sb_mark(__LINE__)
+#else
+#define SB_MARK() ((void)0)
+#endif
 #if defined(__CUDA_ARCH__) && defined(SB_COOP) && defined(SB_PHASE_ALIGN)
-#define SB_PHASE() __syncthreads()
+#define SB_PHASE() do { __syncthreads(); SB_MARK(); } while (0)
 #else
 #define SB_PHASE() ((void)0)
 #endif
@@ -257,6 +269,11 @@ SB_HD u32 wballot(bool p) { return p ? 1u : 0u; }
 #else
 #define SB_XPOSE_ACTIVE 0
 #endif
+#if defined(__CUDACC__) && defined(SB_PHASE_TIMING)
+__device__ __forceinline__ void sb_mark_end(int k) { sb_mark(-k); }
+#else
+SB_HD void sb_mark_end(int) {}
+#endif
 #if SB_COOP_ACTIVE
 SB_CFN int sb_slot_bytes();      // stride of the per-stream slots (defined with the slot layout)
 template <class T> SB_HD T* xoff(T* p, int d) { return reinterpret_cast<T*>(reinterpret_cast<char*>(p) + d); }
@@ -264,9 +281,11 @@ template <class T> SB_HD const T* xoff(const T* p, int d) { return reinterpret_c
 template <int K, class F> SB_CFN void c_instances(F f) {
 #if SB_XPOSE_ACTIVE
     __syncthreads();
+    SB_MARK();
     const int id = (int)threadIdx.x;
     if (id < SB_BLOCK_STREAMS * K) { const int sj = id / K; f((sj - (id >> 5)) * sb_slot_bytes(), id - sj * K); }
     __syncthreads();
+    sb_mark_end(K);
 #else
     SB_SYNC();
     if (SB_LANE < K) f(0, SB_LANE);

@@ -239,60 +239,70 @@ SB_FN void apply_sine_window(i16* px_win, const i16* px, int win_type, int lengt
 }
 
 // ---- SKP_Silk_resampler_down2.c:41-78 --------------------------------------------------------------
-SB_FN void resampler_down2(i32* S, i16* out, const i16* in, int inLen) {
+SB_FN void resampler_down2(i32* S, i16* __restrict__ out, const i16* __restrict__ in, int inLen) {   // out and in never overlap
     int len2 = inLen >> 1;
     const i32 c0 = SB_T(resampler_down2_0)[0], c1 = SB_T(resampler_down2_1)[0];
+    i32 S0 = S[0], S1 = S[1];
     for (int k = 0; k < len2; k++) {
         i32 in32 = shl((i32)in[2 * k], 10);
-        i32 Y = subw(in32, S[0]);
+        i32 Y = subw(in32, S0);
         i32 X = smlawb(Y, Y, c1);
-        i32 out32 = addw(S[0], X);
-        S[0] = addw(in32, X);
+        i32 out32 = addw(S0, X);
+        S0 = addw(in32, X);
         in32 = shl((i32)in[2 * k + 1], 10);
-        Y = subw(in32, S[1]);
+        Y = subw(in32, S1);
         X = smulwb(Y, c0);
-        out32 = addw(out32, S[1]);
+        out32 = addw(out32, S1);
         out32 = addw(out32, X);
-        S[1] = addw(in32, X);
+        S1 = addw(in32, X);
         out[k] = (i16)sat16(rshift_round(out32, 11));
     }
+    S[0] = S0; S[1] = S1;
 }
 
 // ---- SKP_Silk_ana_filt_bank_1.c:45-80 (in-place on outL == in is safe: in[2k], in[2k+1] are read before outL[k] is written)
 SB_FN void ana_filt_bank_1(const i16* in, i32* S, i16* outL, i16* outH, int N) {
     const i32 A20 = (i16)(5394 << 1), A21 = (i16)(20623 << 1);
     int N2 = N >> 1;
+    i32 S0 = S[0], S1 = S[1];
+    i32 x0 = in[0], x1 = in[1];          // the next input pair is fetched before outL[k] is stored (outL may be in: index k < 2k + 2)
     for (int k = 0; k < N2; k++) {
-        i32 in32 = shl((i32)in[2 * k], 10);
-        i32 Y = subw(in32, S[0]);
+        const i32 a = x0, b = x1;
+        if (k + 1 < N2) { x0 = in[2 * k + 2]; x1 = in[2 * k + 3]; }
+        i32 in32 = shl(a, 10);
+        i32 Y = subw(in32, S0);
         i32 X = smlawb(Y, Y, A21);
-        i32 out_1 = addw(S[0], X);
-        S[0] = addw(in32, X);
-        in32 = shl((i32)in[2 * k + 1], 10);
-        Y = subw(in32, S[1]);
+        i32 out_1 = addw(S0, X);
+        S0 = addw(in32, X);
+        in32 = shl(b, 10);
+        Y = subw(in32, S1);
         X = smulwb(Y, A20);
-        i32 out_2 = addw(S[1], X);
-        S[1] = addw(in32, X);
+        i32 out_2 = addw(S1, X);
+        S1 = addw(in32, X);
         outL[k] = (i16)sat16(rshift_round(addw(out_2, out_1), 11));
         outH[k] = (i16)sat16(rshift_round(subw(out_2, out_1), 11));
     }
+    S[0] = S0; S[1] = S1;
 }
 
 // ---- SKP_Silk_biquad_alt.c:38-72 ------------------------------------------------------------------
-SB_FN void biquad_alt(const i16* in, const i32* B_Q28, const i32* A_Q28, i32* S, i16* out, int len) {
-    i32 A0_L = (-A_Q28[0]) & 0x3FFF, A0_U = (-A_Q28[0]) >> 14;
-    i32 A1_L = (-A_Q28[1]) & 0x3FFF, A1_U = (-A_Q28[1]) >> 14;
+SB_FN void biquad_alt(const i16* __restrict__ in, const i32* B_Q28, const i32* A_Q28, i32* S, i16* __restrict__ out, int len) {   // in and out never overlap
+    const i32 A0_L = (-A_Q28[0]) & 0x3FFF, A0_U = (-A_Q28[0]) >> 14;
+    const i32 A1_L = (-A_Q28[1]) & 0x3FFF, A1_U = (-A_Q28[1]) >> 14;
+    const i32 B0 = B_Q28[0], B1 = B_Q28[1], B2 = B_Q28[2];
+    i32 S0 = S[0], S1 = S[1];
     for (int k = 0; k < len; k++) {
-        i32 inval = in[k];
-        i32 out32_Q14 = shl(smlawb(S[0], B_Q28[0], inval), 2);
-        S[0] = addw(S[1], rshift_round(smulwb(out32_Q14, A0_L), 14));
-        S[0] = smlawb(S[0], out32_Q14, A0_U);
-        S[0] = smlawb(S[0], B_Q28[1], inval);
-        S[1] = rshift_round(smulwb(out32_Q14, A1_L), 14);
-        S[1] = smlawb(S[1], out32_Q14, A1_U);
-        S[1] = smlawb(S[1], B_Q28[2], inval);
+        const i32 inval = in[k];
+        const i32 out32_Q14 = shl(smlawb(S0, B0, inval), 2);
+        S0 = addw(S1, rshift_round(smulwb(out32_Q14, A0_L), 14));
+        S0 = smlawb(S0, out32_Q14, A0_U);
+        S0 = smlawb(S0, B1, inval);
+        S1 = rshift_round(smulwb(out32_Q14, A1_L), 14);
+        S1 = smlawb(S1, out32_Q14, A1_U);
+        S1 = smlawb(S1, B2, inval);
         out[k] = (i16)sat16(addw(out32_Q14, (1 << 14) - 1) >> 14);
     }
+    S[0] = S0; S[1] = S1;
 }
 
 // ---- SKP_Silk_sort.c:34-124 (partial insertion sorts; tie-breaking is part of the bitstream, Q22)
