@@ -251,15 +251,41 @@ def test_long_run_with_level_changes_dtx_and_loss_bursts(sim, ref):
             o.close()
 
 
-def test_cooperative_form_under_32_thread_emulation(sim):
-    """The analysis stage in its cooperative form (sb_par.cuh: SB_PARFOR / SB_SERIAL / barriers), executed by 32 OS threads
-    per stream, still reproduces the golden bitstream -- the CPU-side check of the warp-per-stream kernel's scaffolding
-    (sb_analysis.cu; every routine that has not been made cooperative yet runs on lane 0 behind a barrier)."""
+def test_cooperative_analysis_under_32_lane_emulation(sim):
+    """The warp-per-stream analysis code of the device kernels (sb_coop.cuh: lanes over outputs, wavefronts, shuffles, ballots)
+    executed by 32 fibres per stream (sb_par.cuh SB_EMU: round-robin between barriers, divergent collectives abort) reproduces
+    the golden bitstream of the whole clip, and equals the scalar model on the other input classes, packet modes and rates."""
     g = load_golden()
     clip = load_clip()
     e = sim.SimEncoder(rate=13600, emu=True)
     assert e.L.hs_is_emu() == 1
-    for p in range(16):
+    for p in range(len(clip) // 640):
         b, nb, n = e.encode(clip[p * 640:(p + 1) * 640])
         assert nb == tuple(g["fix_nbytes"][p]) and b[:n] == bytes(g["fix_bits"][p, :n]), p
     e.close()
+    cases = [(name, x, dict(kw)) for name, x, kw in synth_inputs(clip)]
+    cases += [("20ms", clip[:320 * 80], dict(framesize_ms=20)), ("joint1", clip[:640 * 60], dict(joint_hb=1)),
+              ("20ms_rate8000", clip[:320 * 60], dict(framesize_ms=20, rate=8000))]
+    for name, x, kw in cases:
+        if "mdi" in kw:
+            kw["use_md_index"] = kw.pop("mdi")
+        e0, e1 = sim.SimEncoder(emu=False, **kw), sim.SimEncoder(emu=True, **kw)
+        spp = e0.samples
+        for p in range(min(len(x) // spp, 50)):
+            assert e0.encode(x[p * spp:(p + 1) * spp]) == e1.encode(x[p * spp:(p + 1) * spp]), (name, p)
+        e0.close(); e1.close()
+
+
+def test_fast_reciprocal_division_is_exact():
+    """div_q29 (sb_common.cuh): (INT32_MAX >> 2) / d through a float reciprocal + one correction equals C integer division for
+    every divisor the approximate-division helpers can produce (16384 <= |d| <= 32768) -- same float operations as the device."""
+    N = np.int64(0x7FFFFFFF >> 2)
+    d = np.concatenate([np.arange(-32768, -16383), np.arange(16384, 32768)]).astype(np.int64)
+    r = (np.float32(1.0) / d.astype(np.float32)).astype(np.float32)
+    q = (np.float32(N) * r).astype(np.float32).astype(np.int64)      # truncation toward zero
+    rem = N - q * d
+    pos = d > 0
+    q = np.where(pos & (rem < 0), q - 1, np.where(pos & (rem >= d), q + 1, q))
+    q = np.where(~pos & (rem < 0), q + 1, np.where(~pos & (rem >= -d), q - 1, q))
+    want = np.trunc(N.astype(np.float64) / d.astype(np.float64)).astype(np.int64)
+    assert np.array_equal(q, want)
