@@ -247,6 +247,58 @@ def main():
         dev_ms = float(t_.item())
     value = world * N * K / (dev_ms / 1e3)
 
+    # ---------------- configs[3] as BASELINE words it: one ingest point (`root_ingest`, N > 1 only) ----------------
+    # Rank 0 owns the PCM of ALL streams and receives all payloads / decoded PCM in its HBM; the other ranks map those buffers
+    # (CUDA IPC, solo_b200/shard.py) and hand their rows to the same *_device entry points: the band-split kernel pulls PCM
+    # over NVLink / NVSwitch, the entropy-coding and decoder kernels push their rows back -- scatter and gather are fused into
+    # the kernels that consume / produce the data, no NCCL transfer step and no staging copy.
+    root = None
+    if dist:
+        from solo_b200.shard import share_from_root
+        lo = rank * N
+        if rank == 0:
+            r_pcm = torch.empty((T, world * N, 640), dtype=torch.int16, device=dev)
+            r_bits = torch.zeros((world * N, CAP), dtype=torch.uint8, device=dev)
+            r_nb = torch.zeros((world * N, 2), dtype=torch.int16, device=dev)
+            r_out = torch.zeros((world * N, 640), dtype=torch.int16, device=dev)
+        else:
+            r_pcm = r_bits = r_nb = r_out = None
+        r_pcm, r_bits, r_nb, r_out = (share_from_root(t_) for t_ in (r_pcm, r_bits, r_nb, r_out))
+        r_pcm[:, lo:lo + N].copy_(d_pcm)                 # setup (untimed): every rank deposits its input rows at the root
+        torch.cuda.synchronize()
+        dist.barrier()
+        enc_r = solo_b200.EncoderBatch(N, rate=RATE, device=local_rank)
+        dec_r = solo_b200.DecoderBatch(N, device=local_rank)
+        pb, pn, po = r_bits[lo:lo + N].data_ptr(), r_nb[lo:lo + N].data_ptr(), r_out[lo:lo + N].data_ptr()
+
+        def step_root(t):
+            enc_r.encode_device(r_pcm[t, lo:lo + N].data_ptr(), pb, CAP, pn, stream)
+            dec_r.decode_device(po, pb, CAP, pn, d_flags.data_ptr(), d_ret.data_ptr(), stream)
+
+        for t in range(W):
+            step_root(t)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0r, e1r = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0r.record()
+        for t in range(W, T):
+            step_root(t)
+        e1r.record()
+        torch.cuda.synchronize()
+        t_ = torch.tensor([e0r.elapsed_time(e1r)], device=dev)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        root_ms = float(t_.item())
+        dist.barrier()
+        same = bool(torch.equal(r_out[lo:lo + N], d_out)) and bool(torch.equal(r_nb[lo:lo + N], d_nb))   # same streams, same packets
+        root = {"value": world * N * K / (root_ms / 1e3), "unit": UNIT, "ms_per_step": root_ms / K,
+                "vs_rank_ingest": (world * N * K / (root_ms / 1e3)) / value,
+                "nvlink_bytes_per_step": (world - 1) * N * (1280 + 2 * (CAP + 4) + 1280),
+                "identical_to_rank_ingest": same,
+                "how": "rank 0 holds PCM in / payloads + PCM out of all %d streams; peers read / write them inside the codec kernels over NVLink (CUDA IPC mapping), max over ranks" % (world * N)}
+        enc_r.close(); dec_r.close()
+        del r_pcm, r_bits, r_nb, r_out, pb, pn, po
+        dist.barrier()
+
     # ---------------- end-to-end through the host entry points (`e2e`) ----------------
     # fresh codec objects are not needed: the streams simply continue with the next packets of the same input
     # Public host API (solo_b200_enc_batch_encode_host / solo_b200_dec_batch_decode_host): every call copies its step's
@@ -316,6 +368,8 @@ def main():
                          "note": "integer-issue / latency bound codec: HBM fraction is small by construction (SURVEY 7.3-1)"},
             "decode_ret_ok": ret_ok,
         }
+        if root:
+            line["root_ingest"] = root
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             spt, pk = 8, 60

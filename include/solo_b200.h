@@ -79,6 +79,13 @@ int solo_b200_bitfile_unpack(const uint8_t *in, int in_len, const uint8_t **payl
 int solo_b200_apply_loss_device(const uint8_t *d_bits_in, const int16_t *d_nbytes_in, const int32_t *d_lostflag, uint8_t *d_bits_out,
                                 int16_t *d_nbytes_out, int cap, int n, void *cuda_stream);
 
+/* Multi-GPU ingest through peer memory: after this call kernels launched on `device` may read and write buffers that live in
+   `peer_device`'s memory (same process, or another process's allocation mapped with CUDA IPC).  The *_device entry points
+   then accept such addresses for pcm / bits / nbytes / lostflag: the band-split kernel pulls its PCM rows over NVLink and
+   the entropy-coding and decoder kernels push their result rows back, so a single-ingest deployment needs no separate
+   scatter / gather step (solo_b200/shard.py shows the plumbing with torch.distributed). */
+int solo_b200_enable_peer_access(int device, int peer_device);
+
 /* Bytes of device state held per stream (encoder / decoder). */
 int solo_b200_enc_state_bytes(void);
 int solo_b200_dec_state_bytes(void);

@@ -64,6 +64,7 @@ def lib():
         L.solo_b200_bitfile_pack.argtypes = [vp, vp, vp, C.c_int]
         L.solo_b200_bitfile_unpack.argtypes = [vp, C.c_int, pp, vp]
         L.solo_b200_apply_loss_device.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
+        L.solo_b200_enable_peer_access.argtypes = [C.c_int, C.c_int]
         L.solo_b200_enc_state_bytes.restype = C.c_int
         L.solo_b200_dec_state_bytes.restype = C.c_int
         L.solo_b200_profile_enable.argtypes = [C.c_int]
@@ -329,6 +330,11 @@ def bitfile_unpack(data, offset=0):
     if n < 0:
         raise SoloError("bitfile_unpack: truncated record")
     return bytes(view[4:n]), (int(nb[0]), int(nb[1])), offset + n
+
+
+def enable_peer_access(device, peer_device):
+    if lib().solo_b200_enable_peer_access(int(device), int(peer_device)):
+        raise SoloError(_err())
 
 
 def apply_loss_device(d_bits_in, d_nbytes_in, d_lostflag, d_bits_out, d_nbytes_out, cap, n, stream=0):

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(SB_TPB) sb_enc_init_kernel(EncState* states, i
 #define SB_QMF_SPB 1        // one-warp blocks of 2.8 KB: they fit in the shared memory the quantiser kernel leaves free on an SM
 #endif
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__global__ void __launch_bounds__(SB_QMF_SPB * 32) sb_enc_qmf_kernel(EncState* states, const i16* __restrict__ pcm, i16* __restrict__ bands, int spp, int n) {
+__global__ void __launch_bounds__(SB_QMF_SPB * 32) sb_enc_qmf_kernel(EncState* states, const i16* __restrict__ pcm, i16* __restrict__ bands, int spp, int n, int bulk_ok) {
     __shared__ __align__(16) i16 tile[SB_QMF_SPB][PACKET];
     __shared__ __align__(16) i16 xs[SB_QMF_SPB][PACKET + 64];
     __shared__ i16 coef[64];
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(SB_QMF_SPB * 32) sb_enc_qmf_kernel(EncState* s
     const int rows = min(SB_QMF_SPB, n - s0);
     const i16* src = pcm + (size_t)s0 * spp;
     const unsigned bytes = (unsigned)(rows * spp * 2);
-    const bool bulk = (((size_t)src) & 15) == 0;            // 16-byte aligned source: use the copy engine
+    const bool bulk = bulk_ok && (((size_t)src) & 15) == 0;  // 16-byte aligned source in this GPU's memory: use the copy engine
     const unsigned mb = smem_u32(&mbar);
     if (threadIdx.x == 0 && bulk) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
@@ -428,6 +428,14 @@ solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_e
     return b;
 }
 
+// PCM rows in another GPU's memory (peer ingest) are read with ordinary loads over NVLink; the bulk-copy engine path is for
+// rows in this GPU's HBM
+static int pcm_is_local(int device, const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 1; }
+    return (a.type == cudaMemoryTypeDevice && a.device != device) ? 0 : 1;
+}
+
 // the encoder kernels (A0, A, B, C) for streams [lo, lo + n) on one CUDA stream
 static int enc_launch(solo_b200_enc_batch* b, int lo, int n, const i16* d_pcm, u8* d_bits, int cap, i16* d_nbytes, cudaStream_t st) {
     if (n <= 0) return 0;
@@ -438,14 +446,14 @@ static int enc_launch(solo_b200_enc_batch* b, int lo, int n, const i16* d_pcm, u
     prof_begin(st, 0, &ev);
 #if SB_ANALYSIS_WARP
     i16* bands = b->d_bands + (size_t)lo * b->spp;
-    sb_enc_qmf_kernel<<<(n + SB_QMF_SPB - 1) / SB_QMF_SPB, SB_QMF_SPB * 32, 0, st>>>(states, pcm, bands, b->spp, n);
+    sb_enc_qmf_kernel<<<(n + SB_QMF_SPB - 1) / SB_QMF_SPB, SB_QMF_SPB * 32, 0, st>>>(states, pcm, bands, b->spp, n, pcm_is_local(b->device, pcm));
     { int e = sb_launch_enc_hb_warp(states, scratch, bands, b->spp, n, st); if (e) return fail("high-band analysis launch", (cudaError_t)e); }
     { int e = sb_launch_enc_analysis_warp(states, scratch, bands, b->spp, n, st); if (e) return fail("analysis launch", (cudaError_t)e); }
     count_launch(); count_launch();
 #else
 #if SB_QMF_KERNEL
     i16* bands = b->d_bands + (size_t)lo * b->spp;
-    sb_enc_qmf_kernel<<<(n + SB_QMF_SPB - 1) / SB_QMF_SPB, SB_QMF_SPB * 32, 0, st>>>(states, pcm, bands, b->spp, n);
+    sb_enc_qmf_kernel<<<(n + SB_QMF_SPB - 1) / SB_QMF_SPB, SB_QMF_SPB * 32, 0, st>>>(states, pcm, bands, b->spp, n, pcm_is_local(b->device, pcm));
     count_launch();
 #else
     const i16* bands = nullptr;
@@ -718,6 +726,23 @@ int solo_b200_apply_loss_device(const uint8_t* d_bits_in, const int16_t* d_nbyte
     sb_apply_loss_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)cuda_stream>>>(d_bits_in, d_nbytes_in, d_lostflag, d_bits_out, d_nbytes_out, cap, n);
     count_launch();
     CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- multi-GPU ingest through peer memory --------------------------------------------------------------------------------
+// The *_device entry points take any device-visible address.  With peer access enabled, a rank passes rows of a buffer that
+// lives in ANOTHER GPU's HBM (mapped through CUDA IPC by the caller): the band-split kernel then pulls its PCM rows over
+// NVLink / NVSwitch (bulk copies) and the entropy-coding / decoder kernels push their result rows back -- the "scatter" and
+// "gather" of a single-ingest deployment happen inside the kernels that consume / produce the data.
+int solo_b200_enable_peer_access(int device, int peer_device) {
+    if (device == peer_device) return 0;
+    if (require_gpu(device)) return -2;
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, device, peer_device));
+    if (!can) { snprintf(g_err, sizeof g_err, "device %d cannot access device %d", device, peer_device); return -1; }
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) return fail("cudaDeviceEnablePeerAccess", e);
     return 0;
 }
 

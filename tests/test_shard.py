@@ -86,3 +86,25 @@ def test_scatter_encode_gather_equals_single_process(world, n_streams):
         bits, nb = _encode_rows(encs, x[p])
         assert np.array_equal(got[p][1], nb)
         assert np.array_equal(got[p][0], bits)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_single_ingest_on_two_real_gpus(mode):
+    """configs[3] plumbing with the real CUDA encoder on >= 2 GPUs of one node (skipped on a single-GPU box): rank 0 owns all
+    PCM rows; `peer`: every rank encodes / decodes straight out of and into rank 0's HBM (CUDA IPC + NVLink, no transfer
+    step), `nccl`: explicit scatter / gather.  tools/shard_check.py compares the gathered bytes with a single-GPU run."""
+    import json
+    import subprocess
+    import sys
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541" if mode == "peer" else "29542", os.path.join(root, "tools", "shard_check.py"), "4096", "3", mode]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert out.returncode == 0 and lines, out.stderr[-2000:]
+    assert json.loads(lines[-1])["ok"] is True
