@@ -114,6 +114,36 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def usable_cores():
+    """Cores this process may actually use: the affinity mask, capped by the cgroup CPU quota (a container that sees 128
+    CPUs but is throttled to a few would otherwise run the baseline 10x oversubscribed -- round 1's 5x spread between hosts)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read().split()[0])
+            break
+        except Exception:
+            continue
+    if quota:
+        n = max(1, min(n, int(quota)))
+    return min(n, 256)
+
+
+# CPU baseline sample: one pinned thread per usable core, 8 streams x 250 packets = 2 000 timed packets per thread
+CPU_SPT, CPU_PK = 8, 250
+
+
 def run_cpu_baseline(threads, streams_per_thread, packets):
     """Unmodified reference on the host cores: oracle/_ref/cpu_baseline (built by `make -C oracle`)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "cpu_baseline")
@@ -124,7 +154,7 @@ def run_cpu_baseline(threads, streams_per_thread, packets):
         load_clip().tofile(f)
         path = f.name
     try:
-        out = subprocess.run([exe, libdir, path, str(threads), str(streams_per_thread), str(packets), str(RATE)],
+        out = subprocess.run([exe, libdir, path, str(threads), str(streams_per_thread), str(packets), str(RATE), "1"],
                              capture_output=True, text=True, timeout=600).stdout.strip().splitlines()[-1]
         return json.loads(out)
     finally:
@@ -134,9 +164,9 @@ def run_cpu_baseline(threads, streams_per_thread, packets):
 def bench_reference(args, rank):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     vals = []
-    spt, pk = 8, 50
+    spt, pk = CPU_SPT, CPU_PK
     t0 = time.time()
     res = None
     for i in range(args.warmup + args.steps):
@@ -147,18 +177,38 @@ def bench_reference(args, rank):
         if i >= args.warmup:
             vals.append(res["packets_per_s"])
     v = float(np.mean(vals))
-    sample = "%d threads x %d streams x %d packets per step, speech-replay input, rate %d" % (cores, spt, pk, RATE)
+    sample = "%d pinned threads (one per usable core; %d CPUs visible) x %d streams x %d packets per step, speech-replay input, rate %d" % (cores, os.cpu_count() or 0, spt, pk, RATE)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * cores * spt * pk / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32/int16 fixed point (encoder), f32 (decoder high band)", "data": "synthetic (speech-replay of the codec's test clip)",
         "config": {"workload": "configs[2]: enc+dec round trip, speech-replay, 13.6 kb/s (bounded CPU sample)", "streams": cores * spt},
         "streams_rt": v / 25.0,
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
+                         "packets_per_s_per_core": v / cores, "cpus_visible": os.cpu_count()},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.time() - t0,
     }
     print(json.dumps(line))
+
+
+def bind_to_gpu_numa(index):
+    """Run this rank (and first-touch its pinned host buffers) on the CPUs next to its GPU: NVML's CPU affinity of the device,
+    intersected with what the process may use.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, v in enumerate(words) for b in range(64) if (int(v) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d CPUs of the GPU's NUMA node (%d..%d)" % (len(cpus), min(cpus), max(cpus))
+    except Exception as ex:
+        return "not bound (%s)" % type(ex).__name__
+    return "not bound"
 
 
 def main():
@@ -186,6 +236,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- libsolo_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -354,7 +405,8 @@ def main():
                        "arithmetic": "int32/int16 fixed point (encoder, SILK decoder), f32 (decoder high band + QMF synthesis)",
                        "streams_per_gpu": N, "streams_total": world * N, "pipeline_chunks": int(os.environ.get("SOLO_B200_CHUNKS", "2")), "payload_cap": CAP, "mean_payload_bytes": mean_payload,
                        "l2": "no flush: every step reads a new 84 MB PCM wave and ~0.9 GB of per-stream state (> 126 MB L2)",
-                       "parallelism": "streams sharded contiguously across GPUs, no collective on the data path"},
+                       "parallelism": "streams sharded contiguously across GPUs, no collective on the data path",
+                       "host_binding": numa},
             "streams_rt": value / 25.0,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": host_ms / K, "streams_rt": e2e_value / 25.0, "pcm_checksum": checksum},
@@ -371,12 +423,13 @@ def main():
         if root:
             line["root_ingest"] = root
         if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count() or 1
-            spt, pk = 8, 60
+            cores = usable_cores()
+            spt, pk = CPU_SPT, CPU_PK
             res = run_cpu_baseline(cores, spt, pk)
             if res:
                 line["cpu_baseline"] = {"value": res["packets_per_s"], "unit": UNIT, "cores": cores, "kind": "reference",
-                                        "sample": "%d threads x %d streams x %d packets, same speech-replay input, FIX encode + FLP decode" % (cores, spt, pk)}
+                                        "packets_per_s_per_core": res["packets_per_s"] / cores, "cpus_visible": os.cpu_count(),
+                                        "sample": "%d pinned threads (one per usable core) x %d streams x %d packets, same speech-replay input, FIX encode + FLP decode" % (cores, spt, pk)}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "oracle/_ref missing"}
         print(json.dumps(line))

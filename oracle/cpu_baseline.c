@@ -7,7 +7,8 @@
  * through the public six-function API (reference: JC1_SDK_SRC_ARM/interface/AGR_JC1_SDK_API.h:33-64,
  * call pattern of JC1_SDK_SRC_ARM/test/enc_main.c:178-184 and JC1_SDK_SRC_FLP/test/dec_main.c:343).
  *
- * usage: cpu_baseline <dir-with-libs> <pcm-file> <threads> <streams-per-thread> <packets-per-stream> [rate_bps]
+ * usage: cpu_baseline <dir-with-libs> <pcm-file> <threads> <streams-per-thread> <packets-per-stream> [rate_bps] [pin]
+ * pin = 1: thread t is bound to the t-th CPU of the process's affinity mask (one thread per usable core).
  * Input is the "speech-replay" batch of SURVEY.md 8(d): stream s reads the clip circularly from
  * sample offset (s*7919*640) mod nsamples with gain 2^-(s mod 4).
  * Timing: wall clock over all threads, Init and the first packet of every stream excluded.
@@ -16,6 +17,7 @@
 #define _GNU_SOURCE
 #include <dlfcn.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -50,8 +52,14 @@ static void fill(short *dst, long stream, int pkt) {
     for (int i = 0; i < 640; i++) dst[i] = (short)(clip[(off + i) % clip_n] >> sh);
 }
 
+static int pin_threads, n_allowed, allowed[1024];
+
 static void *worker(void *arg) {
     long tid = (long)arg;
+    if (pin_threads && n_allowed > 0) {
+        cpu_set_t one; CPU_ZERO(&one); CPU_SET(allowed[tid % n_allowed], &one);
+        pthread_setaffinity_np(pthread_self(), sizeof one, &one);
+    }
     void **enc = malloc(sizeof(void *) * streams_per_thread), **dec = malloc(sizeof(void *) * streams_per_thread);
     for (int s = 0; s < streams_per_thread; s++) {
         enc_ctrl_t ec = {2, rate_bps, 16000, 0, 40, 0, 0, 0};
@@ -96,6 +104,12 @@ int main(int argc, char **argv) {
     clip = malloc(clip_n * 2); if (fread(clip, 2, clip_n, f) != (size_t)clip_n) return 1; fclose(f);
     n_threads = atoi(argv[3]); streams_per_thread = atoi(argv[4]); packets = atoi(argv[5]);
     rate_bps = argc > 6 ? atoi(argv[6]) : 13600;
+    pin_threads = argc > 7 ? atoi(argv[7]) : 0;
+    {
+        cpu_set_t set; CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof set, &set) == 0)
+            for (int c = 0; c < CPU_SETSIZE && n_allowed < 1024; c++) if (CPU_ISSET(c, &set)) allowed[n_allowed++] = c;
+    }
     if (n_threads < 1 || n_threads > 256) return 2;
     pthread_barrier_init(&bar, NULL, n_threads);
     pthread_t th[256];
@@ -105,7 +119,8 @@ int main(int argc, char **argv) {
     for (int t = 0; t < n_threads; t++) { if (t_start[t] < t0) t0 = t_start[t]; if (t_end[t] > t1) t1 = t_end[t]; nb += bytes_out[t]; h ^= pcm_hash[t]; }
     double npk = (double)n_threads * streams_per_thread * packets;
     printf("{\"packets\": %.0f, \"seconds\": %.6f, \"packets_per_s\": %.2f, \"threads\": %d, \"streams\": %d, \"packets_per_stream\": %d, "
-           "\"mean_payload_bytes\": %.3f, \"pcm_hash\": \"%016llx\"}\n",
-           npk, t1 - t0, npk / (t1 - t0), n_threads, n_threads * streams_per_thread, packets, nb / npk, h);
+           "\"mean_payload_bytes\": %.3f, \"pcm_hash\": \"%016llx\", \"pinned\": %d, \"cpus_allowed\": %d, \"packets_per_s_per_thread\": %.1f}\n",
+           npk, t1 - t0, npk / (t1 - t0), n_threads, n_threads * streams_per_thread, packets, nb / npk, h, pin_threads, n_allowed,
+           npk / (t1 - t0) / n_threads);
     return 0;
 }
