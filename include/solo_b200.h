@@ -86,6 +86,11 @@ int solo_b200_apply_loss_device(const uint8_t *d_bits_in, const int16_t *d_nbyte
    scatter / gather step (solo_b200/shard.py shows the plumbing with torch.distributed). */
 int solo_b200_enable_peer_access(int device, int peer_device);
 
+/* The six AGR_Sate_* functions (AGR_JC1_SDK_API.h) hand out slots of a process-wide arena: segments of 256 streams that are
+   created on demand and shared by the handles.  out[4] = {encoder segments, encoder slots in use, decoder segments, decoder
+   slots in use}. */
+int solo_b200_arena_stats(int out[4]);
+
 /* Bytes of device state held per stream (encoder / decoder). */
 int solo_b200_enc_state_bytes(void);
 int solo_b200_dec_state_bytes(void);

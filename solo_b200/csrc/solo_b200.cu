@@ -406,7 +406,9 @@ int solo_b200_profile_read(double* ms_total, long long* launches) {
 }
 
 // ---- encoder batch --------------------------------------------------------------------------------
-solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_enc* ctrl, int device) {
+static solo_b200_enc_batch* enc_batch_create_impl(int n_streams, const USER_Ctrl_enc* ctrl, int device, bool with_pipe);
+solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_enc* ctrl, int device) { return enc_batch_create_impl(n_streams, ctrl, device, true); }
+static solo_b200_enc_batch* enc_batch_create_impl(int n_streams, const USER_Ctrl_enc* ctrl, int device, bool with_pipe) {
     if (n_streams <= 0 || check_enc_ctrl(ctrl)) { snprintf(g_err, sizeof g_err, "bad encoder configuration"); return nullptr; }
     if (require_gpu(device)) return nullptr;
     solo_b200_enc_batch* b = new solo_b200_enc_batch();
@@ -415,7 +417,7 @@ solo_b200_enc_batch* solo_b200_enc_batch_create(int n_streams, const USER_Ctrl_e
     if (cudaMalloc(&b->d_states, sizeof(EncState) * (size_t)n_streams) != cudaSuccess ||
         cudaMalloc(&b->d_scratch, sizeof(EncScratch) * (size_t)n_streams) != cudaSuccess ||
         cudaMalloc(&b->d_bands, sizeof(i16) * (size_t)b->spp * (size_t)n_streams) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || pipe_create(&b->pipe) != 0 ||
+        cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || (with_pipe && pipe_create(&b->pipe) != 0) ||
         cudaFuncSetAttribute(sb_enc_nsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SB_NSQ_SPB * sizeof(NsqSmem))) != cudaSuccess) {
         fail("enc_batch_create", cudaGetLastError());
         solo_b200_enc_batch_destroy(b); return nullptr;
@@ -541,7 +543,9 @@ void solo_b200_enc_batch_destroy(solo_b200_enc_batch* b) {
 }
 
 // ---- decoder batch --------------------------------------------------------------------------------
-solo_b200_dec_batch* solo_b200_dec_batch_create(int n_streams, const USER_Ctrl_dec* ctrl, int device) {
+static solo_b200_dec_batch* dec_batch_create_impl(int n_streams, const USER_Ctrl_dec* ctrl, int device, bool with_pipe);
+solo_b200_dec_batch* solo_b200_dec_batch_create(int n_streams, const USER_Ctrl_dec* ctrl, int device) { return dec_batch_create_impl(n_streams, ctrl, device, true); }
+static solo_b200_dec_batch* dec_batch_create_impl(int n_streams, const USER_Ctrl_dec* ctrl, int device, bool with_pipe) {
     if (n_streams <= 0 || check_dec_ctrl(ctrl)) { snprintf(g_err, sizeof g_err, "bad decoder configuration"); return nullptr; }
     if (require_gpu(device)) return nullptr;
     solo_b200_dec_batch* b = new solo_b200_dec_batch();
@@ -549,7 +553,7 @@ solo_b200_dec_batch* solo_b200_dec_batch_create(int n_streams, const USER_Ctrl_d
     b->n = n_streams; b->device = device; b->spp = 16 * ctrl->framesize_ms; b->hb_bytes = hb_bytes_of(ctrl->framesize_ms, ctrl->joint_enable);
     if (cudaMalloc(&b->d_states, sizeof(DecState) * (size_t)n_streams) != cudaSuccess ||
         cudaMalloc(&b->d_stale, sizeof(DecStale) * (size_t)n_streams) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || pipe_create(&b->pipe) != 0) {
+        cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || (with_pipe && pipe_create(&b->pipe) != 0)) {
         fail("dec_batch_create", cudaGetLastError());
         solo_b200_dec_batch_destroy(b); return nullptr;
     }
@@ -747,7 +751,40 @@ int solo_b200_enable_peer_access(int device, int peer_device) {
 }
 
 // ---- single-stream drop-in entry points (AGR_JC1_SDK_API.h) -------------------------------------------------------
-// A handle is a batch of one stream.  Same names / return conventions as AGR_BWE_SDK_API.c:11-296.
+// A handle is a SLOT of a process-wide, lazily grown arena: segments of SB_ARENA_SEG streams (ordinary batch objects without
+// the chunk pipeline: one CUDA stream and one set of staging buffers per segment, shared by its slots).  Init takes a free
+// slot of a segment with the same packet layout and (re)initialises that one stream on the device; Uninit gives it back.
+// 10 000 handles are 40 segments = 40 CUDA streams and 240 device allocations, not 10 000 batches.  Calls on handles of the
+// same segment are serialised by the segment's mutex; different segments run concurrently.
+// Same names / return conventions as AGR_BWE_SDK_API.c:11-296 and libBWE/AGR_BWE_init.c:6-76.
+#ifndef SB_ARENA_SEG
+#define SB_ARENA_SEG 256
+#endif
+extern "C++" {
+struct ArenaKey { int device, framesize_ms, joint; };
+template <class Batch> struct ArenaSeg {
+    ArenaKey key;
+    Batch* b;
+    std::vector<char> used;
+    int n_used;
+    std::mutex mu;
+};
+struct EncHandle { unsigned magic; ArenaSeg<solo_b200_enc_batch>* seg; int slot; };
+struct DecHandle { unsigned magic; ArenaSeg<solo_b200_dec_batch>* seg; int slot; };
+static const unsigned ENC_MAGIC = 0x53424531u, DEC_MAGIC = 0x53424431u;   // "SBE1", "SBD1"
+static std::mutex g_arena_mu;
+static std::vector<ArenaSeg<solo_b200_enc_batch>*> g_enc_segs;
+static std::vector<ArenaSeg<solo_b200_dec_batch>*> g_dec_segs;
+
+template <class Batch> static ArenaSeg<Batch>* arena_take(std::vector<ArenaSeg<Batch>*>& segs, ArenaKey k, int* slot) {
+    for (auto* sg : segs)
+        if (sg->key.device == k.device && sg->key.framesize_ms == k.framesize_ms && sg->key.joint == k.joint && sg->n_used < SB_ARENA_SEG)
+            for (int i = 0; i < SB_ARENA_SEG; i++)
+                if (!sg->used[i]) { sg->used[i] = 1; sg->n_used++; *slot = i; return sg; }
+    return nullptr;
+}
+}  // extern "C++"
+
 void* AGR_Sate_Encoder_Init(USER_Ctrl_enc* enc_Ctrl) {
     if (!enc_Ctrl) return nullptr;
     if (enc_Ctrl->targetRate_bps <= 0) enc_Ctrl->targetRate_bps = 15600;  // written back (AGR_BWE_SDK_API.c:34-36)
@@ -755,20 +792,52 @@ void* AGR_Sate_Encoder_Init(USER_Ctrl_enc* enc_Ctrl) {
         printf("Error in setting joint mode! It must be 0, 1, 2, 3\n");
         return nullptr;
     }
+    if (check_enc_ctrl(enc_Ctrl)) { fprintf(stderr, "solo_b200: AGR_Sate_Encoder_Init: unsupported configuration\n"); return nullptr; }
     int dev = 0;
     cudaGetDevice(&dev);
-    solo_b200_enc_batch* b = solo_b200_enc_batch_create(1, enc_Ctrl, dev);
-    if (!b) fprintf(stderr, "solo_b200: AGR_Sate_Encoder_Init failed: %s\n", g_err);
-    return b;
+    const ArenaKey k = {dev, enc_Ctrl->framesize_ms, enc_Ctrl->joint_enable ? 1 : 0};
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    int slot = -1;
+    auto* sg = arena_take(g_enc_segs, k, &slot);
+    if (!sg) {
+        solo_b200_enc_batch* b = enc_batch_create_impl(SB_ARENA_SEG, enc_Ctrl, dev, false);
+        if (!b) { fprintf(stderr, "solo_b200: AGR_Sate_Encoder_Init failed: %s\n", g_err); return nullptr; }
+        sg = new ArenaSeg<solo_b200_enc_batch>();
+        sg->key = k; sg->b = b; sg->used.assign(SB_ARENA_SEG, 0); sg->n_used = 0;
+        g_enc_segs.push_back(sg);
+        sg->used[0] = 1; sg->n_used = 1; slot = 0;
+    }
+    {   // (re)initialise this one stream with the caller's rate / DTX / MD-index settings
+        std::lock_guard<std::mutex> lk2(sg->mu);
+        cudaSetDevice(dev);
+        sb_enc_init_kernel<<<1, SB_TPB, 0, sg->b->stream>>>(sg->b->d_states + slot, 1, enc_Ctrl->targetRate_bps, enc_Ctrl->dtx_enable, enc_Ctrl->useMDIndex,
+                                                          enc_Ctrl->framesize_ms, enc_Ctrl->joint_enable ? 1 : 0);
+        count_launch();
+        if (cudaStreamSynchronize(sg->b->stream) != cudaSuccess) { sg->used[slot] = 0; sg->n_used--; fprintf(stderr, "solo_b200: encoder slot init failed\n"); return nullptr; }
+    }
+    EncHandle* h = new EncHandle{ENC_MAGIC, sg, slot};
+    return h;
 }
 SKP_int32 AGR_Sate_Encoder_Encode(void* SATEEnc_State, const SKP_int16* AGR_Sate_PCM, SKP_uint8* AGR_Sate_Bit, SKP_int32 AGR_Sate_Buf_Size,
                                   SKP_int16* nBytesOut) {
-    if (!SATEEnc_State) return -1;
-    solo_b200_enc_batch* b = (solo_b200_enc_batch*)SATEEnc_State;
+    EncHandle* h = (EncHandle*)SATEEnc_State;
+    if (!h || h->magic != ENC_MAGIC) return -1;
+    solo_b200_enc_batch* b = h->seg->b;
+    const int cap = MAX_PAYLOAD + 8;
     uint8_t tmp[MAX_PAYLOAD + 8];
     int16_t nb[2] = {0, 0};
-    int r = solo_b200_enc_batch_encode_host(b, AGR_Sate_PCM, tmp, MAX_PAYLOAD + 8, nb);
-    if (r) { fprintf(stderr, "solo_b200: encode failed: %s\n", g_err); return -1; }
+    {
+        std::lock_guard<std::mutex> lk(h->seg->mu);
+        if (cudaSetDevice(b->device) != cudaSuccess || enc_staging(b, cap)) { fprintf(stderr, "solo_b200: encode failed: %s\n", g_err); return -1; }
+        const size_t s = (size_t)h->slot;
+        cudaStream_t st = b->stream;
+        bool ok = cudaMemcpyAsync(b->d_pcm + s * b->spp, AGR_Sate_PCM, sizeof(i16) * b->spp, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        ok = ok && enc_launch(b, h->slot, 1, b->d_pcm, b->d_bits, cap, b->d_nbytes, st) == 0;
+        ok = ok && cudaMemcpyAsync(tmp, b->d_bits + s * cap, cap, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(nb, b->d_nbytes + 2 * s, sizeof nb, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
+        if (!ok) { fprintf(stderr, "solo_b200: encode failed: %s\n", g_err[0] ? g_err : cudaGetErrorString(cudaGetLastError())); return -1; }
+    }
     // DTX packets return the high-band bytes (4 per 20 ms frame) with nBytesOut[0] == 0 (App. A Q16)
     int total = nb[0] ? nb[0] : b->hb_bytes;
     int n = total < AGR_Sate_Buf_Size ? total : AGR_Sate_Buf_Size;
@@ -779,8 +848,15 @@ SKP_int32 AGR_Sate_Encoder_Encode(void* SATEEnc_State, const SKP_int16* AGR_Sate
     return n;
 }
 int AGR_Sate_Encoder_Uninit(void* SATEEnc_State) {
-    if (!SATEEnc_State) return -1;
-    solo_b200_enc_batch_destroy((solo_b200_enc_batch*)SATEEnc_State);
+    EncHandle* h = (EncHandle*)SATEEnc_State;
+    if (!h || h->magic != ENC_MAGIC) return -1;
+    {
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        h->seg->used[h->slot] = 0;
+        h->seg->n_used--;
+    }
+    h->magic = 0;
+    delete h;
     return 0;
 }
 
@@ -790,35 +866,84 @@ void* AGR_Sate_Decoder_Init(USER_Ctrl_dec* dec_Ctrl) {
         fprintf(stderr, "Error in setting joint mode! It must be 0, 1, 2, 3\n");
         return nullptr;
     }
+    if (check_dec_ctrl(dec_Ctrl)) { fprintf(stderr, "solo_b200: AGR_Sate_Decoder_Init: unsupported configuration\n"); return nullptr; }
     int dev = 0;
     cudaGetDevice(&dev);
-    solo_b200_dec_batch* b = solo_b200_dec_batch_create(1, dec_Ctrl, dev);
-    if (!b) fprintf(stderr, "solo_b200: AGR_Sate_Decoder_Init failed: %s\n", g_err);
-    return b;
+    const ArenaKey k = {dev, dec_Ctrl->framesize_ms, dec_Ctrl->joint_enable ? 1 : 0};
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    int slot = -1;
+    auto* sg = arena_take(g_dec_segs, k, &slot);
+    if (!sg) {
+        solo_b200_dec_batch* b = dec_batch_create_impl(SB_ARENA_SEG, dec_Ctrl, dev, false);
+        if (!b) { fprintf(stderr, "solo_b200: AGR_Sate_Decoder_Init failed: %s\n", g_err); return nullptr; }
+        sg = new ArenaSeg<solo_b200_dec_batch>();
+        sg->key = k; sg->b = b; sg->used.assign(SB_ARENA_SEG, 0); sg->n_used = 0;
+        g_dec_segs.push_back(sg);
+        sg->used[0] = 1; sg->n_used = 1; slot = 0;
+    }
+    {
+        std::lock_guard<std::mutex> lk2(sg->mu);
+        cudaSetDevice(dev);
+        sb_dec_init_kernel<<<1, SB_TPB, 0, sg->b->stream>>>(sg->b->d_states + slot, 1, dec_Ctrl->useMDIndex, dec_Ctrl->framesize_ms, dec_Ctrl->joint_enable ? 1 : 0);
+        count_launch();
+        if (cudaStreamSynchronize(sg->b->stream) != cudaSuccess) { sg->used[slot] = 0; sg->n_used--; fprintf(stderr, "solo_b200: decoder slot init failed\n"); return nullptr; }
+    }
+    DecHandle* h = new DecHandle{DEC_MAGIC, sg, slot};
+    return h;
 }
 SKP_int32 AGR_Sate_Decoder_Decode(void* SATEDec_State, SKP_int16* AGR_Sate_PCM, SKP_int16* nSamplesOut, const SKP_uint8* AGR_Sate_Bit,
                                   SKP_int16 nBytes[], SKP_int32 lostflag) {
-    if (!SATEDec_State) return -1;
+    DecHandle* h = (DecHandle*)SATEDec_State;
+    if (!h || h->magic != DEC_MAGIC) return -1;
     if (nBytes[0] <= 0) return -1;
-    solo_b200_dec_batch* b = (solo_b200_dec_batch*)SATEDec_State;
+    solo_b200_dec_batch* b = h->seg->b;
+    const int cap = MAX_PAYLOAD + 8;
     uint8_t tmp[MAX_PAYLOAD + 8];
     memset(tmp, 0, sizeof tmp);
-    int n0 = nBytes[0] > MAX_PAYLOAD + 8 ? MAX_PAYLOAD + 8 : nBytes[0];
+    int n0 = nBytes[0] > cap ? cap : nBytes[0];
     memcpy(tmp, AGR_Sate_Bit, n0);
     int16_t nb[2] = {nBytes[0], nBytes[1]};
     int32_t flag = lostflag, ret = 0;
-    int r = solo_b200_dec_batch_decode_host(b, AGR_Sate_PCM, tmp, MAX_PAYLOAD + 8, nb, &flag, &ret);
-    if (r) { fprintf(stderr, "solo_b200: decode failed: %s\n", g_err); return -1; }
+    {
+        std::lock_guard<std::mutex> lk(h->seg->mu);
+        if (cudaSetDevice(b->device) != cudaSuccess || dec_staging(b, cap)) { fprintf(stderr, "solo_b200: decode failed: %s\n", g_err); return -1; }
+        const size_t s = (size_t)h->slot;
+        cudaStream_t st = b->stream;
+        bool ok = cudaMemcpyAsync(b->d_bits + s * cap, tmp, cap, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(b->d_nbytes + 2 * s, nb, sizeof nb, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(b->d_flags + s, &flag, sizeof flag, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        ok = ok && dec_launch(b, h->slot, 1, b->d_pcm, b->d_bits, cap, b->d_nbytes, b->d_flags, b->d_ret, st) == 0;
+        ok = ok && cudaMemcpyAsync(AGR_Sate_PCM, b->d_pcm + s * b->spp, sizeof(i16) * b->spp, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(&ret, b->d_ret + s, sizeof ret, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
+        if (!ok) { fprintf(stderr, "solo_b200: decode failed: %s\n", g_err[0] ? g_err : cudaGetErrorString(cudaGetLastError())); return -1; }
+    }
     // the reference rewrites the caller's nBytes[] while splitting the payload (AGR_BWE_decode_frame_FLP.c:171-190)
     dec_split_lengths(nb, lostflag, b->hb_bytes);
     nBytes[0] = nb[0];
     nBytes[1] = nb[1];
-    *nSamplesOut = (SKP_int16)((solo_b200_dec_batch*)SATEDec_State)->spp;
+    *nSamplesOut = (SKP_int16)b->spp;
     return ret;
 }
 SKP_int32 AGR_Sate_Decoder_Uninit(void* SATEDec_State) {
-    if (!SATEDec_State) return -1;
-    solo_b200_dec_batch_destroy((solo_b200_dec_batch*)SATEDec_State);
+    DecHandle* h = (DecHandle*)SATEDec_State;
+    if (!h || h->magic != DEC_MAGIC) return -1;
+    {
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        h->seg->used[h->slot] = 0;
+        h->seg->n_used--;
+    }
+    h->magic = 0;
+    delete h;
+    return 0;
+}
+/* arena bookkeeping for tests: segments and slots in use (encoder, decoder) */
+int solo_b200_arena_stats(int out[4]) {
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    int eu = 0, du = 0;
+    for (auto* sg : g_enc_segs) eu += sg->n_used;
+    for (auto* sg : g_dec_segs) du += sg->n_used;
+    if (out) { out[0] = (int)g_enc_segs.size(); out[1] = eu; out[2] = (int)g_dec_segs.size(); out[3] = du; }
     return 0;
 }
 

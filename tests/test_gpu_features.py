@@ -335,3 +335,44 @@ def test_malformed_payloads_do_not_fault_and_match_the_host_build(sb):
             if r == 0:
                 assert np.array_equal(want, pcm[s]), (p, s)
     eb.close(); db.close()
+
+
+def test_ten_thousand_drop_in_handles_share_the_arena(sb):
+    """AGR_Sate_Encoder_Init / Decoder_Init hand out slots of the process-wide arena (segments of 256 streams): 10 000 encoder
+    handles come up in well under a second each thousand, occupy 40 segments (not 10 000 batches / 50 000 CUDA streams), still
+    produce the golden bitstream, and a released slot is reused."""
+    import ctypes as C
+    import time
+    L = sb.lib()
+    L.solo_b200_arena_stats.argtypes = [C.POINTER(C.c_int)]
+    st = (C.c_int * 4)()
+    L.solo_b200_arena_stats(st)
+    seg0, used0 = st[0], st[1]
+    g, clip = load_golden(), load_clip()
+    t0 = time.perf_counter()
+    hs = [sb.SoloEncoder(rate=13600) for _ in range(10000)]
+    dt = time.perf_counter() - t0
+    L.solo_b200_arena_stats(st)
+    assert st[1] - used0 == 10000 and st[0] - seg0 <= 40, list(st)
+    assert dt < 5.0, dt                      # ~0.1 ms per handle including the Python wrapper; round 1 needed ~1 ms and 5 CUDA streams each
+    for k in (0, 255, 256, 5000, 9999):      # slots of different segments, first packets of the clip
+        for p in range(3):
+            b, nb, n = hs[k].encode(clip[p * 640:(p + 1) * 640])
+            assert nb == tuple(g["fix_nbytes"][p]) and b[:n] == bytes(g["fix_bits"][p, :n]), (k, p)
+    for h in hs[:3000]:
+        h.close()
+    L.solo_b200_arena_stats(st)
+    assert st[1] - used0 == 7000
+    again = [sb.SoloEncoder(rate=13600) for _ in range(3000)]      # reuses the released slots: no new segment
+    L.solo_b200_arena_stats(st)
+    assert st[1] - used0 == 10000 and st[0] - seg0 <= 40
+    b, nb, n = again[0].encode(clip[:640])                          # a recycled slot starts from a fresh state
+    assert nb == tuple(g["fix_nbytes"][0]) and b[:n] == bytes(g["fix_bits"][0, :n])
+    for h in hs[3000:] + again:
+        h.close()
+    d = [sb.SoloDecoder() for _ in range(1000)]
+    L.solo_b200_arena_stats(st)
+    assert st[3] >= 1000 and st[2] <= 8
+    for h in d:
+        h.close()
+    print("10000 encoder handles in %.3f s" % dt)
