@@ -1816,8 +1816,8 @@ struct CoopWork {
     EncCtrl c;
     alignas(16) i16 xfw[FRAME];
     i32 vadFlag;
+    i32 vad[2][6];             // per frame: speech activity Q8, four band qualities Q15, tilt Q15 (from the VAD kernel)
     union {
-        i16 vadX[4][FRAME / 2];
         PitchScr pitch;
         ShapeScr shape;
         PrefScr pref;
@@ -1842,7 +1842,11 @@ SB_CFN void c_encode_frame_analysis(EncSilk* st, CoopWork* W, const i16* pIn, in
         EncCtrl* cj = &Wj->c;
         const i16* pj = xoff(pIn, d);
         cj->Seed = sj->frameCounter++ & 3;
-        vad_get_sa_q8_x(&sj->vad, &sj->speech_activity_Q8, cj->input_quality_bands_Q15, &cj->input_tilt_Q15, pj, Wj->u.vadX);
+        // voice activity of this frame: computed ahead of time by the VAD kernel (it depends on nothing but the band signal
+        // and its own state), handed over in W->vad
+        sj->speech_activity_Q8 = Wj->vad[frame_in_packet][0];
+        for (int b = 0; b < 4; b++) cj->input_quality_bands_Q15[b] = Wj->vad[frame_in_packet][1 + b];
+        cj->input_tilt_Q15 = Wj->vad[frame_in_packet][5];
         hp_variable_cutoff(sj, cj, Wj->pIn_HP, pj);
     });
     SB_PARFOR(i, 0, FRAME) x_frame[LA_SHAPE + i] = W->pIn_HP[i];   // LP_variable_cutoff is a copy (transition_frame_no == 0)
@@ -1876,6 +1880,11 @@ SB_CFN void c_encode_frame_analysis(EncSilk* st, CoopWork* W, const i16* pIn, in
 // Stage A for the SILK core of one packet.  st, W: shared memory; W->low already holds the low band; scr: global memory.
 SB_CFN void c_enc_packet_analysis(EncSilk* st, CoopWork* W, EncScratch* scr, const NlsfFastTabs* fast = nullptr) {
     const int nf = st->frames_per_packet;
+    if (SB_LANE < 12) {
+        const int f = SB_LANE / 6, q = SB_LANE - 6 * f;
+        W->vad[f][q] = q == 0 ? scr->vad_sa_Q8[f] : (q == 5 ? scr->vad_tilt_Q15[f] : scr->vad_quality_Q15[f][q - 1]);
+    }
+    SB_SYNC();
     for (int f = 0; f < nf; f++) {
         c_encode_frame_analysis(st, W, W->low + f * FRAME, f, fast);
         const i32* src = reinterpret_cast<const i32*>(&W->c);

@@ -114,6 +114,13 @@ SB_FN void vad_get_sa_q8(VadState* v, i32* pSA_Q8, i32* pQuality_Q15, i32* pTilt
     vad_get_sa_q8_x(v, pSA_Q8, pQuality_Q15, pTilt_Q15, pIn, X);
 }
 
+// Voice activity of every frame of a packet ahead of the rest of the analysis (device: its own thread-per-stream kernel --
+// the detector is three cascaded all-pass filter banks plus scalar bookkeeping, a pure recurrence that depends on nothing but
+// the low-band signal and its own state).  low: nf * FRAME samples.
+SB_FN void vad_packet(VadState* v, const i16* low, int nf, i32* sa_Q8, i32 (*quality_Q15)[4], i32* tilt_Q15) {
+    for (int f = 0; f < nf; f++) vad_get_sa_q8(v, &sa_Q8[f], quality_Q15[f], &tilt_Q15[f], low + f * FRAME);
+}
+
 // ---- SKP_Silk_HP_variable_cutoff_FIX.c:37-118 ---------------------------------------------------------
 SB_FN void hp_variable_cutoff(EncSilk* st, EncCtrl* c, i16* out, const i16* in) {
     if (st->prev_sigtype == 0) {

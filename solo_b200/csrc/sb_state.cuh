@@ -146,6 +146,8 @@ struct EncScratch {
     i32 hb_lsp_idx[2];
     i32 hb_nrg0[2][4];
     i32 dtx_drop;
+    // voice-activity results of the packet's frames, written by the VAD kernel and consumed by the analysis kernel
+    i32 vad_sa_Q8[2], vad_quality_Q15[2][4], vad_tilt_Q15[2];
 };
 
 // Range coder (SKP_Silk_range_coder_state, structs.h:85-92); the byte buffer lives with the caller.

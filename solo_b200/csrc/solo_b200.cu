@@ -127,6 +127,21 @@ __global__ void __launch_bounds__(SB_QMF_SPB * 32) sb_enc_qmf_kernel(EncState* s
     for (int i = lane; i < 63; i += 32) st->qmf_mem[i] = x[spp + 62 - i];          // mem[i] = x[N + M - 2 - i]
 }
 
+// ---- stage A1: voice-activity detector of both frames, one thread per stream (pure recurrence, full lane efficiency) ----
+__global__ void __launch_bounds__(SB_TPB) sb_enc_vad_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ bands, int spp, int n) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    VadState v = states[s].vad;
+    __align__(16) i16 low[2 * FRAME];
+    const int nf = states[s].frames_per_packet;
+    const int4* src = reinterpret_cast<const int4*>(bands + (size_t)s * spp);     // low band = first half of the row
+    int4* dst = reinterpret_cast<int4*>(low);
+    for (int i = 0; i < nf * FRAME / 8; i++) dst[i] = src[i];
+    EncScratch* scr = &scratch[s];
+    vad_packet(&v, low, nf, scr->vad_sa_Q8, scr->vad_quality_Q15, scr->vad_tilt_Q15);
+    states[s].vad = v;
+}
+
 // Encoder after the band split = three kernels per packet wave (stream s, scratch slot s):
 //   A  sb_enc_analysis_kernel : one thread per stream  -- QMF split, VAD .. gain processing of both frames, high-band analysis
 //   B  sb_enc_nsq_kernel      : one WARP per stream    -- MD delayed-decision noise-shaping quantiser, state in shared memory
@@ -449,6 +464,8 @@ static int enc_launch(solo_b200_enc_batch* b, int lo, int n, const i16* d_pcm, u
 #if SB_ANALYSIS_WARP
     i16* bands = b->d_bands + (size_t)lo * b->spp;
     sb_enc_qmf_kernel<<<(n + SB_QMF_SPB - 1) / SB_QMF_SPB, SB_QMF_SPB * 32, 0, st>>>(states, pcm, bands, b->spp, n, pcm_is_local(b->device, pcm));
+    sb_enc_vad_kernel<<<(n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(states, scratch, bands, b->spp, n);
+    count_launch();
     { int e = sb_launch_enc_hb_warp(states, scratch, bands, b->spp, n, st); if (e) return fail("high-band analysis launch", (cudaError_t)e); }
     { int e = sb_launch_enc_analysis_warp(states, scratch, bands, b->spp, n, st); if (e) return fail("analysis launch", (cudaError_t)e); }
     count_launch(); count_launch();

@@ -77,6 +77,7 @@ int hs_enc_encode(void* p, const short* pcm, unsigned char* out, int cap, short*
     const int nf = h->st.frames_per_packet;
     sb::qmf_decomp(pcm, h->w.a.low, h->w.a.high, h->st.qmf_mem, nf * 2 * sb::FRAME);
     for (int i = 0; i < nf * sb::FRAME; i++) cw.low[i] = h->w.a.low[i];
+    sb::vad_packet(&h->st.vad, h->w.a.low, nf, h->w.scr.vad_sa_Q8, h->w.scr.vad_quality_Q15, h->w.scr.vad_tilt_Q15);   // the VAD kernel
     sb::emu::run32([=]() { sb::c_enc_packet_analysis(&h->st, &cw, &h->w.scr); });
     static sb::HbScr hs;
     sb::emu::run32([=]() {
