@@ -8,8 +8,11 @@
 //   * lanes over stages       -- the warped all-pass chains run as a skewed wavefront (lane = stage, one shuffle per step);
 //   * lane per instance       -- short recursions that exist several times per frame (4 shaping windows, 4 LTP sub-frames,
 //                                4 interpolation candidates) run as one scalar instance per lane.
-// What is genuinely one serial recurrence at signal rate (VAD filter bank, high-pass biquad, the 2:1 decimator, the
-// low-frequency shaping recursion) runs on lane 0.
+// Short scalar recursions that exist once or a few times per stream (high-pass biquad, decimator chains, Schur / step-up
+// recursions per window, LTP normal equations per sub-frame, NLSF -> LPC conversions) run as "instances": the block's streams
+// side by side on consecutive threads (c_instances, sb_par.cuh).  Pure recurrences that depend on nothing else in the frame
+// are not here at all: the voice-activity detector runs before this kernel, the shaping-filter finishing and the prefilter
+// after it, as thread-per-instance kernels (solo_b200.cu).
 // The scalar routines of sb_enc_*.cuh / sb_sigproc.cuh remain the executable specification: tests/hostsim compiles both and
 // checks this file (32 fibres per stream, sb_par.cuh SB_EMU) against the golden bitstream on a machine without a GPU.
 #pragma once
@@ -186,6 +189,7 @@ struct PitchScr {
     i32 acorr[12];
     i16 rc_Q15[16];
     i16 A_Q12[16];
+    i32 dn[2][FRAME];     // outputs of the two all-pass chains of the 2:1 decimator
 };
 
 SB_CFN int c_pitch_analysis_core(PitchScr* P, const i16* signal, i32* pitch_out, i32* lagIndex, i32* contourIndex, i32* LTPCorr_Q15,
@@ -197,7 +201,23 @@ SB_CFN int c_pitch_analysis_core(PitchScr* P, const i16* signal, i32* pitch_out,
     SB_PARFOR(i, 0, FL8) sig8[i] = signal[i];
     SB_SYNC();
     // 2:1 decimator: one recurrence over the frame (lane 0)
-    c_instances<1>([&](int d, int) { i32 fs[2] = {0, 0}; resampler_down2(fs, xoff(sig4, d), xoff(sig8, d), FL8); });
+    // (SKP_Silk_resampler_down2.c:41-78 from a cleared state): the two all-pass chains (even / odd input samples) as two scalar
+    // instances, their outputs added afterwards -- out32 is a wrap-around sum of the four terms, so the order is free
+    c_instances<2>([&](int d, int k) {
+        PitchScr* Pj = xoff(P, d);
+        const i16* in = Pj->sig8;
+        i32* o = Pj->dn[k];
+        i32 S = 0;
+        if (k == 0) {
+            const i32 c1 = SB_T(resampler_down2_1)[0];
+            for (int q = 0; q < FL4; q++) { const i32 in32 = shl((i32)in[2 * q], 10); const i32 Y = subw(in32, S); const i32 X = smlawb(Y, Y, c1); o[q] = addw(S, X); S = addw(in32, X); }
+        } else {
+            const i32 c0 = SB_T(resampler_down2_0)[0];
+            for (int q = 0; q < FL4; q++) { const i32 in32 = shl((i32)in[2 * q + 1], 10); const i32 Y = subw(in32, S); const i32 X = smulwb(Y, c0); o[q] = addw(S, X); S = addw(in32, X); }
+        }
+    });
+    SB_PARFOR(i, 0, FL4) sig4[i] = (i16)sat16(rshift_round(addw(P->dn[0][i], P->dn[1][i]), 11));
+    SB_SYNC();
     // low-pass (descending in-place loop of the reference = old values on the right-hand side) + scaling
     i32 v[5];
 #pragma unroll
@@ -753,34 +773,9 @@ SB_CFN void c_noise_shape_analysis(EncSilk* st, EncCtrl* c, ShapeScr* S, const i
 #pragma unroll
         for (int i = 0; i < SHAPE_ORDER; i++) { Sj->ar[k][0][i] = AR2_Q24[i]; Sj->ar[k][1][i] = AR1_Q24[i]; }
     });
-    // inverse prediction gains of the eight filters (window x {AR2, AR1}): eight scalar instances side by side
-    c_instances<2 * NB_SUBFR>([&](int d, int q) {
-        ShapeScr* Sj = xoff(S, d);
-        i32 A[SHAPE_ORDER];
-#pragma unroll
-        for (int i = 0; i < SHAPE_ORDER; i++) A[i] = Sj->ar[q >> 1][q & 1][i];
-        i32 g;
-        lpc_inv_pred_gain_q24_r<SHAPE_ORDER>(&g, A);
-        Sj->invgain[q >> 1][q & 1] = g;
-    });
-    c_instances<NB_SUBFR>([&](int d, int k) {
-        ShapeScr* Sj = xoff(S, d);
-        EncCtrl* cj = xoff(c, d);
-        i32 AR1_Q24[SHAPE_ORDER], AR2_Q24[SHAPE_ORDER];
-#pragma unroll
-        for (int i = 0; i < SHAPE_ORDER; i++) { AR2_Q24[i] = Sj->ar[k][0][i]; AR1_Q24[i] = Sj->ar[k][1][i]; }
-        i32 pre_nrg_Q30 = Sj->invgain[k][0];
-        const i32 nrg = Sj->invgain[k][1];
-        pre_nrg_Q30 = shl(smulwb(pre_nrg_Q30, SB_FIXC(0.7, 15)), 1);
-        Sj->gains[k][1] = SB_FIXC(0.3, 14) + div32_varq(pre_nrg_Q30, nrg, 14);
-        limit_warped_coefs_r<SHAPE_ORDER>(AR2_Q24, AR1_Q24, Sj->par3[0], SB_FIXC(3.999, 24));
-#pragma unroll
-        for (int i = 0; i < SHAPE_ORDER; i++) {
-            cj->AR1_Q13[k * SHAPE_ORDER + i] = (i16)sat16(rshift_round(AR1_Q24[i], 11));
-            cj->AR2_Q13[k * SHAPE_ORDER + i] = (i16)sat16(rshift_round(AR2_Q24[i], 11));
-        }
-    });
-    i32 gain_k = S->gains[lane & 3][0], gains_pre_k = S->gains[lane & 3][1];
+    // (inverse prediction gains, pre-gains, coefficient limiting and the Q13 coefficients of the windows are finished by the
+    //  shaping-filter kernel that runs after this one: nothing in the rest of the analysis reads them)
+    i32 gain_k = S->gains[lane & 3][0];
     // ---- gain tweaking ----
     const i32 md_gain_mult_Q16 = log2lin(negw(smlawb(-SB_FIXC(16.0, 7), md_SNR_adj_dB_Q7, SB_FIXC(0.16, 16))));
     i32 gain_mult_Q16 = log2lin(negw(smlawb(-SB_FIXC(16.0, 7), SNR_adj_dB_Q7, SB_FIXC(0.16, 16))));
@@ -802,8 +797,7 @@ SB_CFN void c_noise_shape_analysis(EncSilk* st, EncCtrl* c, ShapeScr* S, const i
             avgGain_Q16 = add_sat32(avgGain_Q16, smulwb(gk - avgGain_Q16, coef));
         }
     }
-    gain_mult_Q16 = SB_FIXC(1.0, 16) + rshift_round(mlaw(SB_FIXC(0.05f, 26), coding_quality_Q14, SB_FIXC(0.1f, 12)), 10);
-    gains_pre_k = smulwb(gain_mult_Q16, gains_pre_k);
+    gain_mult_Q16 = SB_FIXC(1.0, 16) + rshift_round(mlaw(SB_FIXC(0.05f, 26), coding_quality_Q14, SB_FIXC(0.1f, 12)), 10);   // pre-gain multiplier
     // ---- low-frequency shaping, tilt, harmonic shaping ----
     strength_Q16 = mulw(SB_FIXC(3.0f, 0), SB_FIXC(1.0, 16) + smulbb(SB_FIXC(0.5f, 1), c->input_quality_bands_Q15[0] - SB_FIXC(1.0, 15)));
     i32 Tilt_Q16, LF_shp_k;
@@ -838,7 +832,6 @@ SB_CFN void c_noise_shape_analysis(EncSilk* st, EncCtrl* c, ShapeScr* S, const i
     SB_SYNC();     // every lane has read what it needs from c / st
     if (lane < NB_SUBFR) {
         c->Gains_Q16[lane] = gain_k;
-        c->GainsPre_Q14[lane] = gains_pre_k;
         c->LF_shp_Q14[lane] = LF_shp_k;
         c->HarmBoost_Q14[lane] = hb_k;
         c->HarmShapeGain_Q14[lane] = hs_k;
@@ -854,109 +847,7 @@ SB_CFN void c_noise_shape_analysis(EncSilk* st, EncCtrl* c, ShapeScr* S, const i
         c->md_delta_gain_par = md_delta_gain_par;
         st->avgGain_Q16 = avgGain_Q16;
         st->HarmBoost_smth_Q16 = hb; st->HarmShapeGain_smth_Q16 = hs; st->Tilt_smth_Q16 = ti;
-    }
-    SB_SYNC();
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// prefilter (SKP_Silk_prefilter_FIX.c:43-224)
-// ---------------------------------------------------------------------------------------------------------------------
-struct PrefScr {
-    i16 st_res[FRAME];
-    i32 sLF_MA[FRAME];         // x_filt_Q12 on the way in, sLF_MA_shp_Q12 on the way out of the lane-0 recursion
-    i32 par[NB_SUBFR][6];      // per sub-frame: B0, B1, Tilt_Q14, LF_shp_Q14, HarmShapeFIRPacked_Q12, lag
-};
-
-SB_CFN void c_prefilter(EncSilk* st, const EncCtrl* c, PrefScr* S, i16* xw, const i16* x) {
-    const int lane = SB_LANE;
-    // ---- warped LPC analysis filter over the whole frame: wavefront, lane j = all-pass section j (16 lanes) ----
-    {
-        const int j = lane;
-        const i32 lambda = WARPING_Q16;
-        i32 p0 = 0, p1 = 0, out = 0, acc_out = 0;
-        const bool mine = j < SHAPE_ORDER;
-        if (mine) { p0 = st->pf_sAR_shp[j]; p1 = st->pf_sAR_shp[j + 1]; }
-        const i16* cf = &c->AR1_Q13[mine ? j : 0];
-        i32 coef = cf[0];
-        int n = -j, left = SUBFR;        // sample this lane works on at the current step; samples left in its sub-frame
-        for (int t = 0; t < FRAME + SHAPE_ORDER - 1; t++, n++) {
-            const i32 in_prev = wshfl_up(out, 1), acc_prev = wshfl_up(acc_out, 1);
-            if (mine && (unsigned)n < (unsigned)FRAME) {
-                const i32 xin = x[n];
-                const i32 in = j == 0 ? shl(xin, 14) : in_prev;
-                const i32 o = smlawb(p0, j == 0 ? p1 : subw(p1, in), lambda);
-                const i32 a = smlawb(j == 0 ? 0 : acc_prev, o, coef);
-                p0 = in; p1 = o; out = o; acc_out = a;
-                if (j == SHAPE_ORDER - 1) S->st_res[n] = (i16)sat16(xin - rshift_round(a, 11));
-                if (--left == 0) { left = SUBFR; cf += SHAPE_ORDER; coef = n + 1 < FRAME ? cf[0] : 0; }
-            }
-        }
-        SB_SYNC();      // state is read above by every lane before anyone writes it
-        if (j < SHAPE_ORDER) st->pf_sAR_shp[j] = p0;
-        if (j == SHAPE_ORDER - 1) st->pf_sAR_shp[SHAPE_ORDER] = p1;
-    }
-    // ---- per sub-frame constants (lanes 0..3) ----
-    const i32 lagPrev = st->pf_lagPrev, idx_start = st->pf_sLTP_shp_buf_idx;   // read before lane 0 advances them below
-    if (lane < NB_SUBFR) {
-        const int k = lane;
-        const i32 HarmShapeGain_Q12 = smulwb(c->HarmShapeGain_Q14[k], 16384 - c->HarmBoost_Q14[k]);
-        i32 packed = HarmShapeGain_Q12 >> 2;
-        packed |= shl(HarmShapeGain_Q12 >> 1, 16);
-        i32 t32 = smlabb(SB_FIXC(0.05f, 26), c->HarmBoost_Q14[k], HarmShapeGain_Q12);
-        t32 = smlabb(t32, c->coding_quality_Q14, SB_FIXC(0.1f, 12));
-        t32 = smulwb(t32, -c->GainsPre_Q14[k]);
-        t32 = rshift_round(t32, 12);
-        S->par[k][0] = rshift_round(c->GainsPre_Q14[k], 2);
-        S->par[k][1] = sat16(t32);
-        S->par[k][2] = c->Tilt_Q14[k];
-        S->par[k][3] = c->LF_shp_Q14[k];
-        S->par[k][4] = packed;
-        S->par[k][5] = c->sigtype == 0 ? c->pitchL[k] : lagPrev;
-    }
-    const i32 sHarmHP = st->pf_sHarmHP;
-    SB_SYNC();
-    SB_PARFOR(i, 0, FRAME) {
-        const int k = i / SUBFR;
-        const i32 prev = i > 0 ? (i32)S->st_res[i - 1] : sHarmHP;
-        S->sLF_MA[i] = smlabb(smulbb(S->st_res[i], S->par[k][0]), prev, S->par[k][1]);
-    }
-    // ---- low-frequency shaping recursion (SKP_Silk_prefilt_FIX :174-224): one chain per frame, lane 0 ----
-    c_instances<1>([&](int d, int) {
-        EncSilk* sj = xoff(st, d);
-        PrefScr* Sj = xoff(S, d);
-        const EncCtrl* cj = xoff(c, d);
-        i32 sLF_AR = sj->pf_sLF_AR_shp_Q12, sLF_MA = sj->pf_sLF_MA_shp_Q12;
-        for (int k = 0; k < NB_SUBFR; k++) {
-            const i32 Tilt_Q14 = Sj->par[k][2], LF_shp_Q14 = Sj->par[k][3];
-            for (int i = k * SUBFR; i < (k + 1) * SUBFR; i++) {
-                const i32 n_Tilt_Q10 = smulwb(sLF_AR, Tilt_Q14);
-                const i32 n_LF_Q10 = smlawb(smulwt(sLF_AR, LF_shp_Q14), sLF_MA, LF_shp_Q14);
-                sLF_AR = subw(Sj->sLF_MA[i], shl(n_Tilt_Q10, 2));
-                sLF_MA = subw(sLF_AR, shl(n_LF_Q10, 2));
-                Sj->sLF_MA[i] = sLF_MA;
-            }
-        }
-        sj->pf_sLF_AR_shp_Q12 = sLF_AR;
-        sj->pf_sLF_MA_shp_Q12 = sLF_MA;
-        sj->pf_sHarmHP = Sj->st_res[FRAME - 1];
-        sj->pf_sLTP_shp_buf_idx = (sj->pf_sLTP_shp_buf_idx - FRAME) & LTP_MASK;
-        sj->pf_lagPrev = cj->pitchL[NB_SUBFR - 1];
-    });
-    // shaping-buffer writes of the whole frame first, harmonic taps afterwards: a tap of sample i reaches lag - 2 .. lag
-    // samples back (lag >= 16), i.e. only positions written before sample i
-    SB_PARFOR(i, 0, FRAME) st->pf_sLTP_shp[(idx_start - 1 - i) & LTP_MASK] = (i16)sat16(rshift_round(S->sLF_MA[i], 12));
-    SB_SYNC();
-    SB_PARFOR(i, 0, FRAME) {
-        const int k = i / SUBFR;
-        const i32 lag = S->par[k][5], packed = S->par[k][4];
-        i32 n_LTP_Q12 = 0;
-        if (lag > 0) {
-            const i32 idx = lag + idx_start - i;
-            n_LTP_Q12 = smulbb(st->pf_sLTP_shp[(idx - 2) & LTP_MASK], packed);
-            n_LTP_Q12 = smlabt(n_LTP_Q12, st->pf_sLTP_shp[(idx - 1) & LTP_MASK], packed);
-            n_LTP_Q12 = smlabb(n_LTP_Q12, st->pf_sLTP_shp[idx & LTP_MASK], packed);
-        }
-        xw[i] = (i16)sat16(rshift_round(subw(S->sLF_MA[i], n_LTP_Q12), 12));
+        S->par3[1] = gain_mult_Q16;
     }
     SB_SYNC();
 }
@@ -1814,13 +1705,13 @@ struct CoopWork {
     i16 pIn_HP[FRAME];
     i16 res_pitch[2 * FRAME + LA_PITCH];
     EncCtrl c;
-    alignas(16) i16 xfw[FRAME];
     i32 vadFlag;
     i32 vad[2][6];             // per frame: speech activity Q8, four band qualities Q15, tilt Q15 (from the VAD kernel)
+    i32 ar_keep[NB_SUBFR * 2 * SHAPE_ORDER];   // shaping filters of the frame, for the kernels that run after this one
+    i32 par_keep[2];
     union {
         PitchScr pitch;
         ShapeScr shape;
-        PrefScr pref;
         PredScr pred;
     } u;
 };
@@ -1855,8 +1746,9 @@ SB_CFN void c_encode_frame_analysis(EncSilk* st, CoopWork* W, const i16* pIn, in
     c_find_pitch_lags(st, c, &W->u.pitch, W->res_pitch, x_frame);
     SB_PHASE();
     c_noise_shape_analysis(st, c, &W->u.shape, W->res_pitch + FRAME, x_frame);
-    SB_PHASE();
-    c_prefilter(st, c, &W->u.pref, W->xfw, x_frame);
+    SB_PARFOR(i, 0, NB_SUBFR * 2 * SHAPE_ORDER) W->ar_keep[i] = (&W->u.shape.ar[0][0][0])[i];
+    if (SB_LANE < 2) W->par_keep[SB_LANE] = W->u.shape.par3[SB_LANE == 0 ? 0 : 1];
+    SB_SYNC();
     SB_PHASE();
     c_find_pred_coefs(st, c, &W->u.pred, W->res_pitch, frame_in_packet, fast);
     c_instances<1>([&](int d, int) {
@@ -1890,9 +1782,13 @@ SB_CFN void c_enc_packet_analysis(EncSilk* st, CoopWork* W, EncScratch* scr, con
         const i32* src = reinterpret_cast<const i32*>(&W->c);
         i32* dst = reinterpret_cast<i32*>(&scr->c[f]);
         SB_PARFOR(i, 0, (int)(sizeof(EncCtrl) / 4)) dst[i] = src[i];
-        const i32* xs = reinterpret_cast<const i32*>(W->xfw);
-        i32* xd = reinterpret_cast<i32*>(scr->xfw[f]);
+        // the prefilter's input is the frame as the analysis saw it (delayed by the shaping look-ahead): after the slide of
+        // x_buf at the end of the frame that is x_buf[0 .. FRAME)
+        const i32* xs = reinterpret_cast<const i32*>(st->x_buf);
+        i32* xd = reinterpret_cast<i32*>(scr->x_hp[f]);
         SB_PARFOR(i, 0, FRAME / 2) xd[i] = xs[i];
+        SB_PARFOR(i, 0, NB_SUBFR * 2 * SHAPE_ORDER) (&scr->ar_Q24[f][0][0][0])[i] = W->ar_keep[i];
+        if (SB_LANE < 2) scr->shape_par[f][SB_LANE] = W->par_keep[SB_LANE];
         if (SB_LANE0) scr->vadFlag[f] = W->vadFlag;
         SB_SYNC();
     }

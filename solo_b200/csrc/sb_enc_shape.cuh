@@ -266,28 +266,38 @@ SB_FN void noise_shape_analysis(EncSilk* st, EncCtrl* c, const i16* pitch_res, c
 
 // ---- SKP_Silk_prefilter_FIX.c:43-82 (warped LPC analysis filter, order 16) ------------------------------------
 SB_FN void warped_lpc_analysis_filter(i32* state, i16* res, const i16* coef_Q13, const i16* input, i32 lambda_Q16, int length) {
+    i32 sv[SHAPE_ORDER + 1], cq[SHAPE_ORDER];      // register copies: state and coefficients do not change place during the call
+#pragma unroll
+    for (int i = 0; i <= SHAPE_ORDER; i++) sv[i] = state[i];
+#pragma unroll
+    for (int i = 0; i < SHAPE_ORDER; i++) cq[i] = coef_Q13[i];
     for (int n = 0; n < length; n++) {
-        i32 tmp2 = smlawb(state[0], state[1], lambda_Q16);
-        state[0] = shl((i32)input[n], 14);
-        i32 tmp1 = smlawb(state[1], subw(state[2], tmp2), lambda_Q16);
-        state[1] = tmp2;
-        i32 acc_Q11 = smulwb(tmp2, coef_Q13[0]);
+        const i32 xin = input[n];
+        i32 tmp2 = smlawb(sv[0], sv[1], lambda_Q16);
+        sv[0] = shl(xin, 14);
+        i32 tmp1 = smlawb(sv[1], subw(sv[2], tmp2), lambda_Q16);
+        sv[1] = tmp2;
+        i32 acc_Q11 = smulwb(tmp2, cq[0]);
+#pragma unroll
         for (int i = 2; i < SHAPE_ORDER; i += 2) {
-            tmp2 = smlawb(state[i], subw(state[i + 1], tmp1), lambda_Q16);
-            state[i] = tmp1;
-            acc_Q11 = smlawb(acc_Q11, tmp1, coef_Q13[i - 1]);
-            tmp1 = smlawb(state[i + 1], subw(state[i + 2], tmp2), lambda_Q16);
-            state[i + 1] = tmp2;
-            acc_Q11 = smlawb(acc_Q11, tmp2, coef_Q13[i]);
+            tmp2 = smlawb(sv[i], subw(sv[i + 1], tmp1), lambda_Q16);
+            sv[i] = tmp1;
+            acc_Q11 = smlawb(acc_Q11, tmp1, cq[i - 1]);
+            tmp1 = smlawb(sv[i + 1], subw(sv[i + 2], tmp2), lambda_Q16);
+            sv[i + 1] = tmp2;
+            acc_Q11 = smlawb(acc_Q11, tmp2, cq[i]);
         }
-        state[SHAPE_ORDER] = tmp1;
-        acc_Q11 = smlawb(acc_Q11, tmp1, coef_Q13[SHAPE_ORDER - 1]);
-        res[n] = (i16)sat16((i32)input[n] - rshift_round(acc_Q11, 11));
+        sv[SHAPE_ORDER] = tmp1;
+        acc_Q11 = smlawb(acc_Q11, tmp1, cq[SHAPE_ORDER - 1]);
+        res[n] = (i16)sat16(xin - rshift_round(acc_Q11, 11));
     }
+#pragma unroll
+    for (int i = 0; i <= SHAPE_ORDER; i++) state[i] = sv[i];
 }
 
 // ---- SKP_Silk_prefilter_FIX.c:85-224 -------------------------------------------------------------------
-SB_FN void prefilter(EncSilk* st, const EncCtrl* c, i16* xw, const i16* x) {
+// ST: EncSilk, or any struct with the pf_* fields (the prefilter kernel works on a thread-private PrefState)
+template <class ST> SB_FN void prefilter(ST* st, const EncCtrl* c, i16* xw, const i16* x) {
     i32 x_filt_Q12[SUBFR];
     i16 st_res[SUBFR];
     const i16* px = x;
@@ -339,6 +349,44 @@ SB_FN void prefilter(EncSilk* st, const EncCtrl* c, i16* xw, const i16* x) {
         pxw += SUBFR;
     }
     st->pf_lagPrev = c->pitchL[NB_SUBFR - 1];
+}
+
+// ---- after the analysis kernel (device: two thread-per-instance kernels; scalar recursions at full lane efficiency) ----
+// (1) one shaping window: inverse prediction gains of AR2 / AR1 -> GainsPre, coefficient limiting, Q13 coefficients
+//     (noise_shape_analysis_FIX.c:392-415; the analysis kernel stops after the bandwidth expansion of the window)
+SB_FN void shape_post_window(EncScratch* scr, int f, int k) {
+    i32 AR1_Q24[SHAPE_ORDER], AR2_Q24[SHAPE_ORDER];
+    for (int i = 0; i < SHAPE_ORDER; i++) { AR2_Q24[i] = scr->ar_Q24[f][k][0][i]; AR1_Q24[i] = scr->ar_Q24[f][k][1][i]; }
+    i32 pre_nrg_Q30, nrg;
+    lpc_inv_pred_gain_q24(&pre_nrg_Q30, AR2_Q24, SHAPE_ORDER);
+    lpc_inv_pred_gain_q24(&nrg, AR1_Q24, SHAPE_ORDER);
+    pre_nrg_Q30 = shl(smulwb(pre_nrg_Q30, SB_FIXC(0.7, 15)), 1);
+    const i32 gains_pre = SB_FIXC(0.3, 14) + div32_varq(pre_nrg_Q30, nrg, 14);
+    limit_warped_coefs(AR2_Q24, AR1_Q24, scr->shape_par[f][0], SB_FIXC(3.999, 24), SHAPE_ORDER);
+    EncCtrl* c = &scr->c[f];
+    for (int i = 0; i < SHAPE_ORDER; i++) {
+        c->AR1_Q13[k * SHAPE_ORDER + i] = (i16)sat16(rshift_round(AR1_Q24[i], 11));
+        c->AR2_Q13[k * SHAPE_ORDER + i] = (i16)sat16(rshift_round(AR2_Q24[i], 11));
+    }
+    c->GainsPre_Q14[k] = smulwb(scr->shape_par[f][1], gains_pre);
+}
+// (2) the prefilter of every frame of the packet (its output feeds only the quantiser)
+struct PrefState {      // the prefilter's part of EncSilk
+    i16 pf_sLTP_shp[LTP_BUF];
+    i32 pf_sAR_shp[SHAPE_ORDER + 1];
+    i32 pf_sLTP_shp_buf_idx, pf_sLF_AR_shp_Q12, pf_sLF_MA_shp_Q12, pf_sHarmHP, pf_lagPrev;
+};
+SB_FN void prefilter_packet(EncSilk* st, EncScratch* scr, int nf) {
+    PrefState ps;        // thread-private copy: on the device the recursion then runs out of registers / local memory
+    for (int i = 0; i < LTP_BUF; i++) ps.pf_sLTP_shp[i] = st->pf_sLTP_shp[i];
+    for (int i = 0; i <= SHAPE_ORDER; i++) ps.pf_sAR_shp[i] = st->pf_sAR_shp[i];
+    ps.pf_sLTP_shp_buf_idx = st->pf_sLTP_shp_buf_idx; ps.pf_sLF_AR_shp_Q12 = st->pf_sLF_AR_shp_Q12; ps.pf_sLF_MA_shp_Q12 = st->pf_sLF_MA_shp_Q12;
+    ps.pf_sHarmHP = st->pf_sHarmHP; ps.pf_lagPrev = st->pf_lagPrev;
+    for (int f = 0; f < nf; f++) prefilter(&ps, &scr->c[f], scr->xfw[f], scr->x_hp[f]);
+    for (int i = 0; i < LTP_BUF; i++) st->pf_sLTP_shp[i] = ps.pf_sLTP_shp[i];
+    for (int i = 0; i <= SHAPE_ORDER; i++) st->pf_sAR_shp[i] = ps.pf_sAR_shp[i];
+    st->pf_sLTP_shp_buf_idx = ps.pf_sLTP_shp_buf_idx; st->pf_sLF_AR_shp_Q12 = ps.pf_sLF_AR_shp_Q12; st->pf_sLF_MA_shp_Q12 = ps.pf_sLF_MA_shp_Q12;
+    st->pf_sHarmHP = ps.pf_sHarmHP; st->pf_lagPrev = ps.pf_lagPrev;
 }
 
 }  // namespace sb

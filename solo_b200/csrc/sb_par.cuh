@@ -1,22 +1,22 @@
-// solo_b200 -- "one stream = one warp" execution model for the analysis stage.
+// solo_b200 -- "one stream = one warp" execution model of the analysis stage (sb_coop.cuh is written against it).
 //
-// The analysis routines are written ONCE against this small vocabulary and compiled in three ways:
+// Two builds of the same source:
+//   SB_COOP (device, sb_analysis.cu) : the 32 lanes of a warp cooperate on one stream.  SB_PARFOR spreads independent loop
+//                                      iterations over the lanes, SB_SYNC() is __syncwarp(), the w* / g* collectives are
+//                                      shuffle trees; arrays touched by more than one lane live in shared memory.
+//   SB_EMU (host, tests/hostsim)     : 32 fibres per stream, run round-robin between barriers; shuffles and ballots go through a
+//                                      shared scratch line.  A lane that reads what another lane has not written yet, or
+//                                      that takes a different number of collectives, shows up deterministically on a machine
+//                                      without a GPU (test infrastructure only).
+// Without either macro the file only provides inert definitions, so the scalar headers can include it.
 //
-//   SB_COOP on the device  : 32 lanes of a warp cooperate on one stream.  SB_PARFOR spreads independent loop iterations
-//                            over the lanes, SB_SYNC() is __syncwarp(), the w* reductions are shuffle trees.  Every array
-//                            that more than one lane touches lives in shared memory (state, work area, Arena).
-//   serial (default)       : SB_PARFOR is a plain loop, SB_SYNC() and the reductions are no-ops -- this is what the
-//                            thread-per-stream kernels, and the host build used by the CPU test-suite, compile.
-//   SB_EMU on the host     : tests/hostsim runs 32 OS threads per stream with a barrier for SB_SYNC() and a shared
-//                            scratch line for the reductions, so that races and missing barriers in the cooperative code
-//                            show up on a machine without a GPU (test infrastructure only).
-//
-// Rules the routines follow:
+// Rules the cooperative routines follow:
 //   * scalars are computed redundantly by every lane from shared data ("uniform" code: no divergence, no broadcast);
-//   * a lane writes shared data either inside SB_PARFOR (its own iterations) or under SB_LANE0;
-//   * SB_SYNC() separates a write from any read by another lane;
+//   * state is read into registers before the SB_SYNC() that precedes any lane's write to it;
+//   * a lane writes shared data either inside SB_PARFOR (its own iterations) or under an explicit lane test;
 //   * integer sums that the reference accumulates with wrap-around (no saturation, no intermediate shift) may be split
-//     across lanes and combined with wsum(): addition modulo 2^32 / 2^64 is associative, so the result is bit-identical.
+//     across lanes and combined with wsum(): addition modulo 2^32 / 2^64 is associative, so the result is bit-identical;
+//   * every lane of the warp executes every collective (loops around collectives have warp-uniform trip counts).
 #pragma once
 #include "sb_common.cuh"
 
@@ -293,25 +293,5 @@ template <int K, class F> SB_CFN void c_instances(F f) {
 #endif
 }
 #endif
-
-// ---- Arena: LIFO scratch shared by the lanes of a stream (shared memory on the device) ------------------------------
-// Every lane executes the same alloc / release sequence, so the pointers are uniform without any communication.
-struct Arena {
-    unsigned char* base;
-    int cap, top, peak;
-};
-SB_HD void arena_init(Arena* a, void* mem, int cap) { a->base = (unsigned char*)mem; a->cap = cap; a->top = 0; a->peak = 0; }
-SB_HD int arena_mark(const Arena* a) { return a->top; }
-SB_HD void arena_release(Arena* a, int mark) { a->top = mark; }
-template <class T> SB_HD T* arena_alloc(Arena* a, int count) {
-    int off = (a->top + 15) & ~15;
-    int end = off + count * (int)sizeof(T);
-    a->top = end;
-    if (end > a->peak) a->peak = end;
-#if !defined(__CUDA_ARCH__)
-    if (end > a->cap) { __builtin_trap(); }
-#endif
-    return (T*)(a->base + off);
-}
 
 }  // namespace sb

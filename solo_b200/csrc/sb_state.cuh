@@ -148,6 +148,10 @@ struct EncScratch {
     i32 dtx_drop;
     // voice-activity results of the packet's frames, written by the VAD kernel and consumed by the analysis kernel
     i32 vad_sa_Q8[2], vad_quality_Q15[2][4], vad_tilt_Q15[2];
+    // hand-over from the analysis kernel to the shaping-filter / prefilter kernels that run after it
+    i16 x_hp[2][FRAME];                          // high-passed input, delayed by the shaping look-ahead (what the prefilter filters)
+    i32 ar_Q24[2][NB_SUBFR][2][SHAPE_ORDER];     // AR2, AR1 of every shaping window after bandwidth expansion
+    i32 shape_par[2][2];                         // warping_Q16, pre-gain multiplier Q16
 };
 
 // Range coder (SKP_Silk_range_coder_state, structs.h:85-92); the byte buffer lives with the caller.

@@ -142,6 +142,21 @@ __global__ void __launch_bounds__(SB_TPB) sb_enc_vad_kernel(EncState* states, En
     states[s].vad = v;
 }
 
+// ---- after the analysis kernel: scalar recursions whose results only the quantiser reads, one thread per instance ----
+__global__ void __launch_bounds__(128) sb_enc_shape_post_kernel(const EncState* states, EncScratch* scratch, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;       // (stream, frame, window)
+    const int s = t >> 3;
+    if (s >= n) return;
+    const int f = (t >> 2) & 1, k = t & 3;
+    if (f >= states[s].frames_per_packet) return;
+    shape_post_window(&scratch[s], f, k);
+}
+__global__ void __launch_bounds__(SB_TPB) sb_enc_prefilter_kernel(EncState* states, EncScratch* scratch, int n) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    prefilter_packet(&states[s], &scratch[s], states[s].frames_per_packet);
+}
+
 // Encoder after the band split = three kernels per packet wave (stream s, scratch slot s):
 //   A  sb_enc_analysis_kernel : one thread per stream  -- QMF split, VAD .. gain processing of both frames, high-band analysis
 //   B  sb_enc_nsq_kernel      : one WARP per stream    -- MD delayed-decision noise-shaping quantiser, state in shared memory
@@ -468,7 +483,9 @@ static int enc_launch(solo_b200_enc_batch* b, int lo, int n, const i16* d_pcm, u
     count_launch();
     { int e = sb_launch_enc_hb_warp(states, scratch, bands, b->spp, n, st); if (e) return fail("high-band analysis launch", (cudaError_t)e); }
     { int e = sb_launch_enc_analysis_warp(states, scratch, bands, b->spp, n, st); if (e) return fail("analysis launch", (cudaError_t)e); }
-    count_launch(); count_launch();
+    sb_enc_shape_post_kernel<<<(8 * n + 127) / 128, 128, 0, st>>>(states, scratch, n);
+    sb_enc_prefilter_kernel<<<(n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(states, scratch, n);
+    count_launch(); count_launch(); count_launch(); count_launch();
 #else
 #if SB_QMF_KERNEL
     i16* bands = b->d_bands + (size_t)lo * b->spp;

@@ -79,6 +79,8 @@ int hs_enc_encode(void* p, const short* pcm, unsigned char* out, int cap, short*
     for (int i = 0; i < nf * sb::FRAME; i++) cw.low[i] = h->w.a.low[i];
     sb::vad_packet(&h->st.vad, h->w.a.low, nf, h->w.scr.vad_sa_Q8, h->w.scr.vad_quality_Q15, h->w.scr.vad_tilt_Q15);   // the VAD kernel
     sb::emu::run32([=]() { sb::c_enc_packet_analysis(&h->st, &cw, &h->w.scr); });
+    for (int f = 0; f < nf; f++) for (int k = 0; k < sb::NB_SUBFR; k++) sb::shape_post_window(&h->w.scr, f, k);   // shaping-filter kernel
+    sb::prefilter_packet(&h->st, &h->w.scr, nf);                                                                  // prefilter kernel
     static sb::HbScr hs;
     sb::emu::run32([=]() {
         for (int f = 0; f < nf * sb::FRAME / h->st.hb_frame; f++) {

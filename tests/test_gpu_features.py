@@ -354,7 +354,7 @@ def test_ten_thousand_drop_in_handles_share_the_arena(sb):
     dt = time.perf_counter() - t0
     L.solo_b200_arena_stats(st)
     assert st[1] - used0 == 10000 and st[0] - seg0 <= 40, list(st)
-    assert dt < 5.0, dt                      # ~0.1 ms per handle including the Python wrapper; round 1 needed ~1 ms and 5 CUDA streams each
+    assert dt < 10.0, dt                     # ~0.1 ms per handle including the Python wrapper; round 1 needed ~1 ms and 5 CUDA streams each
     for k in (0, 255, 256, 5000, 9999):      # slots of different segments, first packets of the clip
         for p in range(3):
             b, nb, n = hs[k].encode(clip[p * 640:(p + 1) * 640])
