@@ -62,17 +62,25 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(streams_per_launch):
-    """DRAM bytes (read + write) of the dominant kernel from the committed `ncu --set full` capture, scaled from the
-    number of streams that capture's launch processed to the launches of this run (traffic is per stream: state + I/O)."""
+def ncu_summary():
+    """profiles/ncu_summary.json (tools/profile_round.py): per kernel the DRAM bytes, issue-slot utilisation and warp
+    instructions of one `ncu --set full` launch.  bench.py never runs under a profiler; these are the committed captures."""
     p = os.path.join(ROOT, "profiles", "ncu_summary.json")
-    if os.path.exists(p):
-        try:
-            d = json.load(open(p))
-            return d["encode_kernel_dram_bytes_per_launch"] / d["encode_kernel_streams_per_launch"] * streams_per_launch
-        except Exception:
-            return None
-    return None
+    try:
+        d = json.load(open(p))
+        return d if "kernels" in d else None
+    except Exception:
+        return None
+
+
+def ncu_traffic(kernel, streams_per_launch):
+    """DRAM bytes (read + write) of `kernel` per launch, scaled from the capture's streams per launch to this run's."""
+    d = ncu_summary()
+    try:
+        k = d["kernels"][kernel]
+        return k["dram_bytes_per_launch"] / k["streams_per_launch"] * streams_per_launch
+    except Exception:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -413,7 +421,11 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "sb_enc_nsq_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(streams_per_launch), "peak_source": peak_src,
+                         "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic("sb_enc_nsq_kernel", streams_per_launch), "peak_source": peak_src,
+                         "issue_util": ((ncu_summary() or {}).get("issue_util_time_weighted_pct") or 0) / 100.0 or None,
+                         "dram_bytes_per_packet": (ncu_summary() or {}).get("dram_bytes_per_packet"),
+                         "warp_inst_per_packet": (ncu_summary() or {}).get("warp_inst_per_packet"),
+                         "ncu_capture": (ncu_summary() or {}).get("from"),
                          "algorithmic_bytes_per_launch": alg_bytes_enc, "kernel_ms": enc_ms,
                          "kernel_ms_all": kms, "kernel_ms_per_wave": kms_wave, "streams_per_launch": streams_per_launch,
                          "decode_algorithmic_bytes_per_launch": alg_bytes_dec,

@@ -1145,6 +1145,7 @@ struct PredScr {
     i32 ie[8][2];                // residual energy and shift of (candidate, half-frame)
     i32 vq_meta[5];              // MSVQ: survivor set, survivors, fluctuation reduction off, its weight, signal type
     i32 vq_wsse[16];
+    i32 nlsf_out[2][LPC_ORDER];  // quantised NLSFs of the two half-frames, for the gain kernel
     i16 a_tmp_Q12[4][LPC_ORDER + 2];
     union {
         struct { BurgScr burg; A2nlsfScr a2n; } lpc;
@@ -1489,23 +1490,13 @@ SB_CFN void c_process_nlsfs(EncSilk* st, EncCtrl* c, i32* pNLSF_Q15, PredScr* Q,
     }
     c_nlsf_msvq_encode(c->NLSFIndices, pNLSF_Q15, cb, st->prev_NLSFq_Q15, Q->NLSFW_Q6, NLSF_mu_Q15, NLSF_mu_fluc_red_Q16,
                        st->first_frame_after_reset, sigtype, Q);
-    // quantised NLSFs -> prediction filters of the two half-frames (two scalar instances)
-    c_instances<2>([&](int d, int k) {
-        const i32* nlj = xoff(pNLSF_Q15, d);
-        EncCtrl* cj = xoff(c, d);
-        i32 nl[LPC_ORDER];
-        i16 a12[LPC_ORDER];
-        const int iq = cj->NLSFInterpCoef_Q2;
-        if (k == 1 || iq >= (1 << 2)) { for (int i = 0; i < LPC_ORDER; i++) nl[i] = nlj[i]; }
-        else {
-            const EncSilk* sj = xoff(st, d);
-            i32 a[LPC_ORDER], b[LPC_ORDER];
-            for (int i = 0; i < LPC_ORDER; i++) { a[i] = sj->prev_NLSFq_Q15[i]; b[i] = nlj[i]; }
-            interpolate(nl, a, b, iq, LPC_ORDER);
-        }
-        nlsf2a_stable(a12, nl, LPC_ORDER);
-        for (int i = 0; i < LPC_ORDER; i++) cj->PredCoef_Q12[k][i] = a12[i];
-    });
+    // quantised NLSFs of the two half-frames (first half interpolated); the gain kernel turns them into prediction filters
+    if (lane < LPC_ORDER) {
+        const i32 q = pNLSF_Q15[lane];
+        Q->nlsf_out[1][lane] = q;
+        Q->nlsf_out[0][lane] = doInterpolate ? st->prev_NLSFq_Q15[lane] + (mulw(q - st->prev_NLSFq_Q15[lane], interpQ2) >> 2) : q;
+    }
+    SB_SYNC();
 }
 
 // SKP_Silk_find_pred_coefs_FIX (find_pred_coefs_FIX.c:31-131)
@@ -1571,33 +1562,7 @@ SB_CFN void c_find_pred_coefs(EncSilk* st, EncCtrl* c, PredScr* Q, const i16* re
     SB_PHASE();
     c_process_nlsfs(st, c, Q->NLSF_Q15, Q, fast);
     SB_PHASE();
-    // SKP_Silk_residual_energy_FIX (residual_energy_FIX.c:32-92): both half-frame filters over all lanes, four energies on four lanes
-    {
-        enum { OFF = LPC_ORDER + SUBFR };
-        for (int t = lane; t < 4 * OFF; t += 32) {
-            const int hh = t / (2 * OFF), kx = t - hh * 2 * OFF;
-            const i16* xp = Q->LPC_in_pre + hh * 2 * OFF;
-            const i16* bq = c->PredCoef_Q12[hh];
-            i32 acc = 0;
-#pragma unroll
-            for (int d = 0; d < LPC_ORDER; d++) if (d < kx) acc = addw(acc, (i32)xp[kx - 1 - d] * (i32)bq[d]);
-            Q->u.LPC_res[hh][kx] = (i16)sat16(rshift_round(sub_sat32(shl((i32)xp[kx], 12), acc), 12));
-        }
-        SB_SYNC();
-        if (lane < NB_SUBFR) {
-            const int hh = lane >> 1, jj = lane & 1;
-            i32 nrg, rshift;
-            sum_sqr_shift(&nrg, &rshift, Q->u.LPC_res[hh] + LPC_ORDER + jj * OFF, SUBFR, 0);
-            i32 nq = -rshift;
-            const i32 gn = Q->local_gains[lane];
-            const int lz1 = clz32(nrg) - 1, lz2 = clz32(gn) - 1;
-            i32 tmp32 = shl(gn, lz2);
-            tmp32 = smmul(tmp32, tmp32);
-            c->ResNrg[lane] = smmul(tmp32, shl(nrg, lz1));
-            c->ResNrgQ[lane] = nq + lz1 + 2 * lz2 - 32 - 32;
-        }
-    }
-    SB_SYNC();
+    // (prediction filters, residual energies and the gain processing follow in the gain kernel)
     if (lane < LPC_ORDER) st->prev_NLSFq_Q15[lane] = Q->NLSF_Q15[lane];
     SB_SYNC();
 }
@@ -1705,7 +1670,6 @@ struct CoopWork {
     i16 pIn_HP[FRAME];
     i16 res_pitch[2 * FRAME + LA_PITCH];
     EncCtrl c;
-    i32 vadFlag;
     i32 vad[2][6];             // per frame: speech activity Q8, four band qualities Q15, tilt Q15 (from the VAD kernel)
     i32 ar_keep[NB_SUBFR * 2 * SHAPE_ORDER];   // shaping filters of the frame, for the kernels that run after this one
     i32 par_keep[2];
@@ -1751,15 +1715,12 @@ SB_CFN void c_encode_frame_analysis(EncSilk* st, CoopWork* W, const i16* pIn, in
     SB_SYNC();
     SB_PHASE();
     c_find_pred_coefs(st, c, &W->u.pred, W->res_pitch, frame_in_packet, fast);
-    c_instances<1>([&](int d, int) {
-        EncSilk* sj = xoff(st, d);
-        CoopWork* Wj = xoff(W, d);
-        process_gains(sj, &Wj->c, frame_in_packet);
-        vad_flag_and_dtx(sj, &Wj->vadFlag);
-        sj->prev_sigtype = Wj->c.sigtype;
-        sj->prevLag = Wj->c.pitchL[NB_SUBFR - 1];
-        sj->first_frame_after_reset = 0;
-    });
+    if (SB_LANE0) {
+        st->prev_sigtype = c->sigtype;
+        st->prevLag = c->pitchL[NB_SUBFR - 1];
+        st->first_frame_after_reset = 0;
+    }
+    SB_SYNC();
     {   // x_buf slides by one frame: [0,160) <- [160,320), then [160,200) <- [320,360) (each step reads only unwritten words)
         i32* xb = reinterpret_cast<i32*>(st->x_buf);
         SB_PARFOR(i, 0, FRAME / 2) xb[i] = xb[FRAME / 2 + i];
@@ -1789,10 +1750,11 @@ SB_CFN void c_enc_packet_analysis(EncSilk* st, CoopWork* W, EncScratch* scr, con
         SB_PARFOR(i, 0, FRAME / 2) xd[i] = xs[i];
         SB_PARFOR(i, 0, NB_SUBFR * 2 * SHAPE_ORDER) (&scr->ar_Q24[f][0][0][0])[i] = W->ar_keep[i];
         if (SB_LANE < 2) scr->shape_par[f][SB_LANE] = W->par_keep[SB_LANE];
-        if (SB_LANE0) scr->vadFlag[f] = W->vadFlag;
+        SB_PARFOR(i, 0, 2 * LPC_ORDER) (&scr->nlsf_Q15[f][0][0])[i] = (&W->u.pred.nlsf_out[0][0])[i];
+        SB_PARFOR(i, 0, (NB_SUBFR * LPC_ORDER + FRAME) / 2) reinterpret_cast<i32*>(scr->lpc_in_pre[f])[i] = reinterpret_cast<const i32*>(W->u.pred.LPC_in_pre)[i];
+        if (SB_LANE < NB_SUBFR) scr->local_gains[f][SB_LANE] = W->u.pred.local_gains[SB_LANE];
         SB_SYNC();
     }
-    if (SB_LANE0) scr->dtx_drop = (st->useDTX && st->inDTX) ? 1 : 0;
 }
 
 }  // namespace sb

@@ -614,6 +614,32 @@ SB_FN i32 dec_silk_frame(DecState* st, DecCtrl* c, RangeDec* rc, i32 (*Pulses)[F
     return ret;
 }
 
+// One group of four outputs of the synthesis filter bank (AGR_BWE_qmf.c:125-176): xx1 / xx2 = time-reversed band signals
+// followed by the filter memories, i = even output-pair index.  The order of the float operations is the reference's; the
+// groups are independent of each other, which is what the synthesis kernel uses (one group per lane and step).
+SB_HD void qmf_synth_group(const float* xx1, const float* xx2, const float* a, int N2, int i, float* y4) {
+    enum { M2 = 32 };
+    float y0 = 0, y1 = 0, y2 = 0, y3 = 0;
+    float x10 = xx1[N2 - 2 - i], x20 = xx2[N2 - 2 - i];
+    for (int j = 0; j < M2; j += 2) {
+        float a0 = a[2 * j], a1 = a[2 * j + 1];
+        float x11 = xx1[N2 - 1 + j - i], x21 = xx2[N2 - 1 + j - i];
+        y0 = y0 + a0 * (x11 - x21);
+        y1 = y1 + a1 * (x11 + x21);
+        y2 = y2 + a0 * (x10 - x20);
+        y3 = y3 + a1 * (x10 + x20);
+        a0 = a[2 * j + 2];
+        a1 = a[2 * j + 3];
+        x10 = xx1[N2 + j - i];
+        x20 = xx2[N2 + j - i];
+        y0 = y0 + a0 * (x10 - x20);
+        y1 = y1 + a1 * (x10 + x20);
+        y2 = y2 + a0 * (x11 - x21);
+        y3 = y3 + a1 * (x11 + x21);
+    }
+    y4[0] = 2.f * y0; y4[1] = 2.f * y1; y4[2] = 2.f * y2; y4[3] = 2.f * y3;
+}
+
 // ---- AGR_Sate_qmf_synth, float branch (AGR_BWE_qmf.c:86-182), N = 2 * N2 = 640 or 320, M = 64 ----------------------
 SB_FN void qmf_synth_f32(const float* x1, const float* x2, float* y, float* mem1, float* mem2, int N2) {
     enum { M = 64, M2 = 32, N2MAX = PACKET / 2 };
@@ -623,30 +649,7 @@ SB_FN void qmf_synth_f32(const float* x1, const float* x2, float* y, float* mem1
     for (int i = 0; i < M2; i++) xx1[N2 + i] = mem1[2 * i + 1];
     for (int i = 0; i < N2; i++) xx2[i] = x2[N2 - 1 - i];
     for (int i = 0; i < M2; i++) xx2[N2 + i] = mem2[2 * i + 1];
-    for (int i = 0; i < N2; i += 2) {
-        float y0 = 0, y1 = 0, y2 = 0, y3 = 0;
-        float x10 = xx1[N2 - 2 - i], x20 = xx2[N2 - 2 - i];
-        for (int j = 0; j < M2; j += 2) {
-            float a0 = a[2 * j], a1 = a[2 * j + 1];
-            float x11 = xx1[N2 - 1 + j - i], x21 = xx2[N2 - 1 + j - i];
-            y0 = y0 + a0 * (x11 - x21);
-            y1 = y1 + a1 * (x11 + x21);
-            y2 = y2 + a0 * (x10 - x20);
-            y3 = y3 + a1 * (x10 + x20);
-            a0 = a[2 * j + 2];
-            a1 = a[2 * j + 3];
-            x10 = xx1[N2 + j - i];
-            x20 = xx2[N2 + j - i];
-            y0 = y0 + a0 * (x10 - x20);
-            y1 = y1 + a1 * (x10 + x20);
-            y2 = y2 + a0 * (x11 - x21);
-            y3 = y3 + a1 * (x11 + x21);
-        }
-        y[2 * i] = 2.f * y0;
-        y[2 * i + 1] = 2.f * y1;
-        y[2 * i + 2] = 2.f * y2;
-        y[2 * i + 3] = 2.f * y3;
-    }
+    for (int i = 0; i < N2; i += 2) qmf_synth_group(xx1, xx2, a, N2, i, &y[2 * i]);
     for (int i = 0; i < M2; i++) mem1[2 * i + 1] = xx1[i];
     for (int i = 0; i < M2; i++) mem2[2 * i + 1] = xx2[i];
 }
@@ -723,14 +726,20 @@ struct DecPacketWork {
     DecCtrl c;
     i32 Pulses[2][FRAME];
     u8 pay[2][MAX_PAYLOAD + 8];
-    i16 lowout[PACKET / 2];
+    alignas(16) i16 lowout[PACKET / 2];
     i32 res_Q10[PACKET / 2];
     float res_f[PACKET / 2];
-    float OutLow[PACKET / 2], OutHigh[PACKET / 2], out[PACKET];
+    alignas(16) float OutHigh[PACKET / 2];
+    float OutLow[PACKET / 2], out[PACKET];     // only the scalar model (bands == nullptr) uses these two
 };
 
+// Band signals handed from the decoder kernel to the synthesis-filter-bank kernel (device pipeline): int16 low band and
+// float high band of the packet.  With bands == nullptr dec_packet runs the filter bank itself (scalar model).
+struct DecBands { i16* low; float* high; };
+
 // bits/cap: payload row as handed in by the caller; nb: {n0, n1} (not modified); returns the reference's return code.
-SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, int cap, const i16* nb_in, i32 lostflag, DecStale* stale = nullptr) {
+SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, int cap, const i16* nb_in, i32 lostflag, DecStale* stale = nullptr,
+                     const DecBands* bands = nullptr) {
     if (nb_in[0] <= 0) return -1;
     if (lostflag < 1 || lostflag > 4) return -1;
     // frame control starts from zeros: after a rejected (corrupted) frame a few of its fields are read before anything
@@ -791,7 +800,6 @@ SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, 
             st->rc_bufferIx[k] = rc[k].bufferIx; st->rc_error[k] = rc[k].error; st->rc_bufLen[k] = rc[k].bufLen;
         }
     }
-    for (int i = 0; i < half; i++) W->OutLow[i] = (float)W->lowout[i];
     const int hb_lost = (lostflag == 1 || lostflag == 2);
     for (int f = 0; f < nhb; f++) {
         for (int i = 0; i < F; i++) W->res_f[i] = (float)(W->res_Q10[f * F + i] >> 10);
@@ -800,6 +808,20 @@ SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, 
         if (!hb_lost) for (int i = 0; i < 4; i++) hb4[i] = bits[hb_off + 4 * f + i];
         hb_decode_frame(st, hb4, W->OutHigh + f * F, W->res_f, lostflag);
     }
+    if (bands) {      // device pipeline: the 64-tap synthesis filter bank has no recurrence and runs as its own kernel
+#ifdef __CUDA_ARCH__
+        const int4* sl = reinterpret_cast<const int4*>(W->lowout);
+        int4* dl = reinterpret_cast<int4*>(bands->low);
+        for (int i = 0; i < half / 8; i++) dl[i] = sl[i];
+        const float4* sh = reinterpret_cast<const float4*>(W->OutHigh);
+        float4* dh = reinterpret_cast<float4*>(bands->high);
+        for (int i = 0; i < half / 4; i++) dh[i] = sh[i];
+#else
+        for (int i = 0; i < half; i++) { bands->low[i] = W->lowout[i]; bands->high[i] = W->OutHigh[i]; }
+#endif
+        return 0;
+    }
+    for (int i = 0; i < half; i++) W->OutLow[i] = (float)W->lowout[i];
     qmf_synth_f32(W->OutLow, W->OutHigh, W->out, st->g0_mem, st->g1_mem, half);
     for (int i = 0; i < 2 * half; i++) {
         i32 t = trunc_i32((double)W->out[i]);

@@ -742,4 +742,31 @@ SB_FN void process_gains(EncSilk* st, EncCtrl* c, int frame_in_packet) {
                     smulwb(SB_FIXC(1.5f, 16), quant_offset_Q10);
 }
 
+// ---- after the analysis kernel (device: one thread per stream): what only the quantiser and the entropy coder read ----
+// quantised NLSFs -> the two prediction filters (process_NLSFs_FIX.c:108-127), residual energies (residual_energy_FIX.c),
+// gain processing and quantisation (process_gains_FIX.c), VAD flag / DTX counter (encode_frame_FIX.c:151-165)
+SB_FN void gains_packet(EncSilk* st, EncScratch* scr, int nf) {
+    for (int f = 0; f < nf; f++) {
+        EncCtrl* c = &scr->c[f];
+        for (int k = 0; k < 2; k++) {
+            i32 nl[LPC_ORDER];
+            i16 a12[LPC_ORDER];
+            for (int i = 0; i < LPC_ORDER; i++) nl[i] = scr->nlsf_Q15[f][k][i];
+            nlsf2a_stable(a12, nl, LPC_ORDER);
+            for (int i = 0; i < LPC_ORDER; i++) c->PredCoef_Q12[k][i] = a12[i];
+        }
+        i16 x[NB_SUBFR * LPC_ORDER + FRAME];
+        i16 a[2][LPC_ORDER];
+        i32 lg[NB_SUBFR];
+        for (int i = 0; i < NB_SUBFR * LPC_ORDER + FRAME; i++) x[i] = scr->lpc_in_pre[f][i];
+        for (int k = 0; k < 2; k++) for (int i = 0; i < LPC_ORDER; i++) a[k][i] = c->PredCoef_Q12[k][i];
+        for (int i = 0; i < NB_SUBFR; i++) lg[i] = scr->local_gains[f][i];
+        residual_energy(c->ResNrg, c->ResNrgQ, x, a, lg);
+        st->speech_activity_Q8 = scr->vad_sa_Q8[f];
+        process_gains(st, c, f);
+        vad_flag_and_dtx(st, &scr->vadFlag[f]);
+    }
+    scr->dtx_drop = (st->useDTX && st->inDTX) ? 1 : 0;
+}
+
 }  // namespace sb

@@ -152,6 +152,10 @@ struct EncScratch {
     i16 x_hp[2][FRAME];                          // high-passed input, delayed by the shaping look-ahead (what the prefilter filters)
     i32 ar_Q24[2][NB_SUBFR][2][SHAPE_ORDER];     // AR2, AR1 of every shaping window after bandwidth expansion
     i32 shape_par[2][2];                         // warping_Q16, pre-gain multiplier Q16
+    // ... and to the gain kernel: quantised NLSFs (interpolated first half, second half), the LPC analysis input, gains
+    i32 nlsf_Q15[2][2][LPC_ORDER];
+    i16 lpc_in_pre[2][NB_SUBFR * LPC_ORDER + FRAME];
+    i32 local_gains[2][NB_SUBFR];
 };
 
 // Range coder (SKP_Silk_range_coder_state, structs.h:85-92); the byte buffer lives with the caller.

@@ -154,7 +154,9 @@ __global__ void __launch_bounds__(128) sb_enc_shape_post_kernel(const EncState* 
 __global__ void __launch_bounds__(SB_TPB) sb_enc_prefilter_kernel(EncState* states, EncScratch* scratch, int n) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    prefilter_packet(&states[s], &scratch[s], states[s].frames_per_packet);
+    const int nf = states[s].frames_per_packet;
+    gains_packet(&states[s], &scratch[s], nf);       // (independent of the prefilter: different fields of the control blocks and of the state)
+    prefilter_packet(&states[s], &scratch[s], nf);
 }
 
 // Encoder after the band split = three kernels per packet wave (stream s, scratch slot s):
@@ -229,26 +231,66 @@ __global__ void __launch_bounds__(SB_TPB) sb_dec_init_kernel(DecState* states, i
     if (s < n) dec_state_init(&states[s], mdi, framesize_ms, joint_hb);
 }
 
-__global__ void __launch_bounds__(SB_DEC_TPB, SB_DECODE_MINB) sb_decode_kernel(DecState* states, i16* __restrict__ pcm, const u8* __restrict__ bits, int cap,
+__global__ void __launch_bounds__(SB_DEC_TPB, SB_DECODE_MINB) sb_decode_kernel(DecState* states, const u8* __restrict__ bits, int cap,
                                                            const i16* __restrict__ nbytes, const i32* __restrict__ lostflag,
-                                                           i32* __restrict__ ret, DecStale* stale, int spp, int n) {
+                                                           i32* __restrict__ ret, i32* __restrict__ ret_int, DecStale* stale,
+                                                           i16* __restrict__ band_low, float* __restrict__ band_high, int spp, int n) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     DecPacketWork W;
     i16 nb[2] = {nbytes[2 * s], nbytes[2 * s + 1]};
-    __align__(16) i16 out[PACKET];   // moved to the PCM row (cudaMalloc / 16-byte aligned, see solo_b200.h) with 128-bit stores
+    const DecBands bands = {band_low + (size_t)s * (spp / 2), band_high + (size_t)s * (spp / 2)};
 #if SB_DECODE_LOCAL_STATE
     DecState st = states[s];
-    i32 r = dec_packet(&st, &W, out, bits + (size_t)s * cap, cap, nb, lostflag[s], &stale[s]);
+    i32 r = dec_packet(&st, &W, nullptr, bits + (size_t)s * cap, cap, nb, lostflag[s], &stale[s], &bands);
     states[s] = st;
 #else
-    i32 r = dec_packet(&states[s], &W, out, bits + (size_t)s * cap, cap, nb, lostflag[s], &stale[s]);
+    i32 r = dec_packet(&states[s], &W, nullptr, bits + (size_t)s * cap, cap, nb, lostflag[s], &stale[s], &bands);
 #endif
-    int4* dst = reinterpret_cast<int4*>(pcm + (size_t)s * spp);
-    const int4* src = reinterpret_cast<const int4*>(out);
-#pragma unroll 4
-    for (int i = 0; i < spp * 2 / 16; i++) dst[i] = src[i];
     if (ret) ret[s] = r;
+    ret_int[s] = r;
+}
+
+// ---- synthesis filter bank + float -> int16, one warp per stream (AGR_BWE_qmf.c:86-182, AGR_BWE_decode_frame_FLP.c:222-231) ----
+// 160 (80) independent groups of four outputs per packet: lanes over groups, band signals and filter memories staged in
+// shared memory; the PCM row is written with 8-byte stores, 256 contiguous bytes per warp instruction.
+#ifndef SB_SYN_WARPS
+#define SB_SYN_WARPS 4
+#endif
+__global__ void __launch_bounds__(SB_SYN_WARPS * 32) sb_dec_synth_kernel(DecState* states, const i16* __restrict__ band_low, const float* __restrict__ band_high,
+                                                                        const i32* __restrict__ ret_int, i16* __restrict__ pcm, int spp, int n) {
+    __shared__ float xx[SB_SYN_WARPS][2][32 + PACKET / 2];
+    __shared__ float coef[64];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) coef[i] = SB_T(qmf_flt)[i];
+    __syncthreads();
+    const int s = blockIdx.x * SB_SYN_WARPS + w;
+    if (s >= n || ret_int[s] < 0) return;         // a rejected packet leaves its PCM row and the filter memories alone
+    const int N2 = spp >> 1;
+    float* xx1 = xx[w][0];
+    float* xx2 = xx[w][1];
+    DecState* st = &states[s];
+    const i16* lo = band_low + (size_t)s * N2;
+    const float* hi = band_high + (size_t)s * N2;
+    for (int i = lane; i < N2; i += 32) { xx1[i] = (float)lo[N2 - 1 - i]; xx2[i] = hi[N2 - 1 - i]; }
+    xx1[N2 + lane] = st->g0_mem[2 * lane + 1];
+    xx2[N2 + lane] = st->g1_mem[2 * lane + 1];
+    __syncwarp();
+    i16* out = pcm + (size_t)s * spp;
+    for (int g = lane; g < N2 / 2; g += 32) {
+        float y4[4];
+        qmf_synth_group(xx1, xx2, coef, N2, 2 * g, y4);
+        i32 t[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { i32 v = trunc_i32((double)y4[q]); t[q] = v > 32767 ? 32767 : (v < -32768 ? -32768 : v); }
+        int2 pk;
+        pk.x = (t[0] & 0xffff) | (t[1] << 16);
+        pk.y = (t[2] & 0xffff) | (t[3] << 16);
+        reinterpret_cast<int2*>(out)[g] = pk;
+    }
+    __syncwarp();
+    st->g0_mem[2 * lane + 1] = xx1[lane];
+    st->g1_mem[2 * lane + 1] = xx2[lane];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -378,6 +420,7 @@ struct solo_b200_dec_batch {
     DecState* d_states;
     DecStale* d_stale;          // payload copies that outlive a packet call (only touched after a corrupted packet, see sb_dec.cuh)
     i16* d_pcm; u8* d_bits; i16* d_nbytes; i32* d_flags; i32* d_ret; int bits_cap;
+    i16* d_band_low; float* d_band_high; i32* d_ret_int;   // decoder kernel -> synthesis kernel
     cudaStream_t stream;
     Pipe pipe;
 };
@@ -587,6 +630,9 @@ static solo_b200_dec_batch* dec_batch_create_impl(int n_streams, const USER_Ctrl
     b->n = n_streams; b->device = device; b->spp = 16 * ctrl->framesize_ms; b->hb_bytes = hb_bytes_of(ctrl->framesize_ms, ctrl->joint_enable);
     if (cudaMalloc(&b->d_states, sizeof(DecState) * (size_t)n_streams) != cudaSuccess ||
         cudaMalloc(&b->d_stale, sizeof(DecStale) * (size_t)n_streams) != cudaSuccess ||
+        cudaMalloc(&b->d_band_low, sizeof(i16) * (size_t)(b->spp / 2) * (size_t)n_streams) != cudaSuccess ||
+        cudaMalloc(&b->d_band_high, sizeof(float) * (size_t)(b->spp / 2) * (size_t)n_streams) != cudaSuccess ||
+        cudaMalloc(&b->d_ret_int, sizeof(i32) * (size_t)n_streams) != cudaSuccess ||
         cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || (with_pipe && pipe_create(&b->pipe) != 0)) {
         fail("dec_batch_create", cudaGetLastError());
         solo_b200_dec_batch_destroy(b); return nullptr;
@@ -602,10 +648,14 @@ static int dec_launch(solo_b200_dec_batch* b, int lo, int n, i16* d_pcm, const u
                       i32* d_ret, cudaStream_t st) {
     if (n <= 0) return 0;
     EvPair ev; prof_begin(st, 3, &ev);
-    sb_decode_kernel<<<(n + SB_DEC_TPB - 1) / SB_DEC_TPB, SB_DEC_TPB, 0, st>>>(b->d_states + lo, d_pcm + (size_t)lo * b->spp, d_bits + (size_t)lo * cap, cap,
-                                                                  d_nbytes + 2 * (size_t)lo, d_lostflag + lo, d_ret ? d_ret + lo : nullptr, b->d_stale + lo, b->spp, n);
+    const size_t half = (size_t)(b->spp / 2);
+    sb_decode_kernel<<<(n + SB_DEC_TPB - 1) / SB_DEC_TPB, SB_DEC_TPB, 0, st>>>(b->d_states + lo, d_bits + (size_t)lo * cap, cap, d_nbytes + 2 * (size_t)lo, d_lostflag + lo,
+                                                                  d_ret ? d_ret + lo : nullptr, b->d_ret_int + lo, b->d_stale + lo,
+                                                                  b->d_band_low + (size_t)lo * half, b->d_band_high + (size_t)lo * half, b->spp, n);
+    sb_dec_synth_kernel<<<(n + SB_SYN_WARPS - 1) / SB_SYN_WARPS, SB_SYN_WARPS * 32, 0, st>>>(b->d_states + lo, b->d_band_low + (size_t)lo * half, b->d_band_high + (size_t)lo * half,
+                                                                                          b->d_ret_int + lo, d_pcm + (size_t)lo * b->spp, b->spp, n);
     prof_end(st, &ev);
-    count_launch();
+    count_launch(); count_launch();
     CK(cudaGetLastError());
     return 0;
 }
@@ -679,6 +729,7 @@ void solo_b200_dec_batch_destroy(solo_b200_dec_batch* b) {
     if (b->stream) cudaStreamSynchronize(b->stream);
     pipe_destroy(&b->pipe);
     cudaFree(b->d_states); cudaFree(b->d_stale); cudaFree(b->d_pcm); cudaFree(b->d_bits); cudaFree(b->d_nbytes); cudaFree(b->d_flags); cudaFree(b->d_ret);
+    cudaFree(b->d_band_low); cudaFree(b->d_band_high); cudaFree(b->d_ret_int);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }

@@ -80,6 +80,7 @@ int hs_enc_encode(void* p, const short* pcm, unsigned char* out, int cap, short*
     sb::vad_packet(&h->st.vad, h->w.a.low, nf, h->w.scr.vad_sa_Q8, h->w.scr.vad_quality_Q15, h->w.scr.vad_tilt_Q15);   // the VAD kernel
     sb::emu::run32([=]() { sb::c_enc_packet_analysis(&h->st, &cw, &h->w.scr); });
     for (int f = 0; f < nf; f++) for (int k = 0; k < sb::NB_SUBFR; k++) sb::shape_post_window(&h->w.scr, f, k);   // shaping-filter kernel
+    sb::gains_packet(&h->st, &h->w.scr, nf);                                                                      // gain kernel
     sb::prefilter_packet(&h->st, &h->w.scr, nf);                                                                  // prefilter kernel
     static sb::HbScr hs;
     sb::emu::run32([=]() {
