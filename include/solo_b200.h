@@ -100,9 +100,9 @@ long long solo_b200_kernel_launches(void);
    of 4: total ms and launch count since the last read for {encoder analysis, encoder NSQ, encoder finish, decode}. */
 void solo_b200_profile_enable(int on);
 int solo_b200_profile_read(double ms_total[4], long long launches[4]);
-/* A packet wave is processed as `chunks` groups of streams on internal CUDA streams so that copies overlap kernels and one
-   group's kernels fill the SMs another group's tail leaves idle (default 2, env SOLO_B200_CHUNKS; 1 = one launch per
-   kernel on the caller's stream).  Results do not depend on it. */
+/* A packet wave can be processed as `chunks` groups of streams on internal CUDA streams so that the copies of one group
+   overlap the kernels of another.  Default (0, or env SOLO_B200_CHUNKS unset): 2 for the *_host entry points, 1 (one launch
+   per kernel on the caller's stream) for the *_device entry points.  Results do not depend on it. */
 void solo_b200_set_chunks(int chunks);
 const char *solo_b200_last_error(void);
 

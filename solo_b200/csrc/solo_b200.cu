@@ -363,15 +363,18 @@ struct Pipe {
     cudaEvent_t fork, join[SB_PIPE_STREAMS];
     bool ok;
 };
-static int g_chunks = -1;   // -1: SOLO_B200_CHUNKS or the default below
-static int pipe_chunks(int n) {
+static int g_chunks = -1;   // -1: SOLO_B200_CHUNKS or the defaults below
+// Default: the host entry points cut a wave in two (the copies of one chunk hide behind the kernels of the other); the device
+// entry points launch every kernel once for the whole batch (the thread-per-stream kernels need all the streams they can get
+// to fill 148 SMs, and the warp-per-stream kernels fill the GPU on their own: measured 25.9 vs 26.3 ms per 65 536-stream wave).
+static int pipe_chunks(int n, bool host_copies) {
     if (g_chunks < 0) {
         const char* e = getenv("SOLO_B200_CHUNKS");
-        g_chunks = e ? atoi(e) : 2;
-        if (g_chunks < 1) g_chunks = 1;
+        g_chunks = e ? atoi(e) : 0;
+        if (g_chunks < 0) g_chunks = 0;
         if (g_chunks > 64) g_chunks = 64;
     }
-    int c = g_chunks;
+    int c = g_chunks ? g_chunks : (host_copies ? 2 : 1);
     while (c > 1 && n / c < 2048) c--;   // small batches: fewer, larger chunks
     return c;
 }
@@ -456,7 +459,7 @@ const char* solo_b200_last_error(void) { return g_err; }
 long long solo_b200_kernel_launches(void) { std::lock_guard<std::mutex> lk(g_mu); return g_launches; }
 int solo_b200_enc_state_bytes(void) { return (int)sizeof(EncState); }
 int solo_b200_dec_state_bytes(void) { return (int)sizeof(DecState); }
-void solo_b200_set_chunks(int chunks) { g_chunks = chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks); }
+void solo_b200_set_chunks(int chunks) { g_chunks = chunks < 0 ? 0 : (chunks > 64 ? 64 : chunks); }   // 0: the defaults
 void solo_b200_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_profile = on;
@@ -555,7 +558,7 @@ int solo_b200_enc_batch_encode_device(solo_b200_enc_batch* b, const int16_t* d_p
     if (!b || !d_pcm || !d_bits || !d_nbytes || cap < 16) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
     CK(cudaSetDevice(b->device));
     cudaStream_t user = (cudaStream_t)cuda_stream;
-    const int C = pipe_chunks(b->n);
+    const int C = pipe_chunks(b->n, false);
     if (C == 1) return enc_launch(b, 0, b->n, d_pcm, d_bits, cap, d_nbytes, user);
     // fork from the caller's stream onto the internal ones, join back: the caller sees ordinary stream semantics
     CK(cudaEventRecord(b->pipe.fork, user));
@@ -591,7 +594,7 @@ int solo_b200_enc_batch_encode_host(solo_b200_enc_batch* b, const int16_t* pcm, 
     CK(cudaSetDevice(b->device));
     int r = enc_staging(b, cap);
     if (r) return r;
-    const int C = pipe_chunks(b->n);
+    const int C = pipe_chunks(b->n, true);
     const int S = C < SB_PIPE_STREAMS ? C : SB_PIPE_STREAMS;
     for (int c = 0; c < C; c++) {   // per chunk: H2D, encoder kernels, D2H -- chunks alternate over the internal streams
         int lo, hi;
@@ -665,7 +668,7 @@ int solo_b200_dec_batch_decode_device(solo_b200_dec_batch* b, int16_t* d_pcm, co
     if (!b || !d_pcm || !d_bits || !d_nbytes || !d_lostflag || cap < 16) { snprintf(g_err, sizeof g_err, "bad argument"); return -1; }
     CK(cudaSetDevice(b->device));
     cudaStream_t user = (cudaStream_t)cuda_stream;
-    const int C = pipe_chunks(b->n);
+    const int C = pipe_chunks(b->n, false);
     if (C == 1) return dec_launch(b, 0, b->n, d_pcm, d_bits, cap, d_nbytes, d_lostflag, d_ret, user);
     CK(cudaEventRecord(b->pipe.fork, user));
     const int S = C < SB_PIPE_STREAMS ? C : SB_PIPE_STREAMS;
@@ -703,7 +706,7 @@ int solo_b200_dec_batch_decode_host(solo_b200_dec_batch* b, int16_t* pcm, const 
     CK(cudaSetDevice(b->device));
     int r = dec_staging(b, cap);
     if (r) return r;
-    const int C = pipe_chunks(b->n);
+    const int C = pipe_chunks(b->n, true);
     const int S = C < SB_PIPE_STREAMS ? C : SB_PIPE_STREAMS;
     for (int c = 0; c < C; c++) {
         int lo, hi;

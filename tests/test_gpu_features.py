@@ -45,7 +45,7 @@ def test_results_do_not_depend_on_the_number_of_pipeline_chunks(sb):
             for a, b in zip(ref, got):
                 for u, v in zip(a, b):
                     assert np.array_equal(u, v), chunks
-    sb.set_chunks(2)
+    sb.set_chunks(0)           # back to the defaults
 
 
 @pytest.mark.parametrize("N", [1, 2, 3, 63, 65])
