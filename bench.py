@@ -180,7 +180,7 @@ def bench_reference(args, rank):
     for i in range(args.warmup + args.steps):
         res = run_cpu_baseline(cores, spt, pk)
         if res is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (run make -C oracle in the build container)"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref not built (run make -C oracle in the build container)"})
             return
         if i >= args.warmup:
             vals.append(res["packets_per_s"])
@@ -197,7 +197,59 @@ def bench_reference(args, rank):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.time() - t0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+def measure_root_ingest(args, dist, solo_b200, torch, rank, world, local_rank, dev, N, K, W, T, d_pcm, d_flags, d_ret, d_out, d_nb, stream, value):
+    """configs[3] as BASELINE words it: one ingest point.  Rank 0 owns the PCM of ALL streams and receives all payloads / decoded
+    PCM in its HBM; the other ranks map those buffers (CUDA IPC, solo_b200/shard.py) and hand their rows to the same *_device
+    entry points: the band-split kernel pulls PCM over NVLink / NVSwitch, the entropy-coding and synthesis kernels push their rows
+    back -- scatter and gather are fused into the kernels that consume / produce the data, no NCCL transfer step, no staging copy."""
+    from solo_b200.shard import share_from_root
+    lo = rank * N
+    if rank == 0:
+        r_pcm = torch.empty((T, world * N, 640), dtype=torch.int16, device=dev)
+        r_bits = torch.zeros((world * N, CAP), dtype=torch.uint8, device=dev)
+        r_nb = torch.zeros((world * N, 2), dtype=torch.int16, device=dev)
+        r_out = torch.zeros((world * N, 640), dtype=torch.int16, device=dev)
+    else:
+        r_pcm = r_bits = r_nb = r_out = None
+    r_pcm, r_bits, r_nb, r_out = (share_from_root(t_) for t_ in (r_pcm, r_bits, r_nb, r_out))
+    r_pcm[:, lo:lo + N].copy_(d_pcm)                 # setup (untimed): every rank deposits its input rows at the root
+    torch.cuda.synchronize()
+    dist.barrier()
+    enc_r = solo_b200.EncoderBatch(N, rate=RATE, device=local_rank)
+    dec_r = solo_b200.DecoderBatch(N, device=local_rank)
+    pb, pn, po = r_bits[lo:lo + N].data_ptr(), r_nb[lo:lo + N].data_ptr(), r_out[lo:lo + N].data_ptr()
+
+    def step_root(t):
+        enc_r.encode_device(r_pcm[t, lo:lo + N].data_ptr(), pb, CAP, pn, stream)
+        dec_r.decode_device(po, pb, CAP, pn, d_flags.data_ptr(), d_ret.data_ptr(), stream)
+
+    for t in range(W):
+        step_root(t)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0r, e1r = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0r.record()
+    for t in range(W, T):
+        step_root(t)
+    e1r.record()
+    torch.cuda.synchronize()
+    t_ = torch.tensor([e0r.elapsed_time(e1r)], device=dev)
+    dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+    root_ms = float(t_.item())
+    dist.barrier()
+    same = bool(torch.equal(r_out[lo:lo + N], d_out)) and bool(torch.equal(r_nb[lo:lo + N], d_nb))   # same streams, same packets
+    root = {"value": world * N * K / (root_ms / 1e3), "unit": UNIT, "ms_per_step": root_ms / K,
+            "vs_rank_ingest": (world * N * K / (root_ms / 1e3)) / value,
+            "nvlink_bytes_per_step": (world - 1) * N * (1280 + 2 * (CAP + 4) + 1280),
+            "identical_to_rank_ingest": same,
+            "how": "rank 0 holds PCM in / payloads + PCM out of all %d streams; peers read / write them inside the codec kernels over NVLink (CUDA IPC mapping), max over ranks" % (world * N)}
+    enc_r.close(); dec_r.close()
+    del r_pcm, r_bits, r_nb, r_out, pb, pn, po
+    dist.barrier()
+    return root
 
 
 def bind_to_gpu_numa(index):
@@ -219,7 +271,20 @@ def bind_to_gpu_numa(index):
     return "not bound"
 
 
+def emit(line):
+    """The one JSON line goes to the process's original stdout; everything else that libraries print to file descriptor 1
+    (NCCL's version banner, for instance) was redirected to stderr at start-up."""
+    OUT.write(json.dumps(line) + "\n")
+    OUT.flush()
+
+
+OUT = sys.stdout
+
+
 def main():
+    global OUT
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -227,6 +292,7 @@ def main():
     ap.add_argument("--impl", default="solo_b200", choices=["solo_b200", "reference"])
     ap.add_argument("--streams", type=int, default=65536, help="streams per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-root-ingest", action="store_true", help="skip the single-ingest-point measurement (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "solo_b200" else args.warmup
 
@@ -312,50 +378,11 @@ def main():
     # over NVLink / NVSwitch, the entropy-coding and decoder kernels push their rows back -- scatter and gather are fused into
     # the kernels that consume / produce the data, no NCCL transfer step and no staging copy.
     root = None
-    if dist:
-        from solo_b200.shard import share_from_root
-        lo = rank * N
-        if rank == 0:
-            r_pcm = torch.empty((T, world * N, 640), dtype=torch.int16, device=dev)
-            r_bits = torch.zeros((world * N, CAP), dtype=torch.uint8, device=dev)
-            r_nb = torch.zeros((world * N, 2), dtype=torch.int16, device=dev)
-            r_out = torch.zeros((world * N, 640), dtype=torch.int16, device=dev)
-        else:
-            r_pcm = r_bits = r_nb = r_out = None
-        r_pcm, r_bits, r_nb, r_out = (share_from_root(t_) for t_ in (r_pcm, r_bits, r_nb, r_out))
-        r_pcm[:, lo:lo + N].copy_(d_pcm)                 # setup (untimed): every rank deposits its input rows at the root
-        torch.cuda.synchronize()
-        dist.barrier()
-        enc_r = solo_b200.EncoderBatch(N, rate=RATE, device=local_rank)
-        dec_r = solo_b200.DecoderBatch(N, device=local_rank)
-        pb, pn, po = r_bits[lo:lo + N].data_ptr(), r_nb[lo:lo + N].data_ptr(), r_out[lo:lo + N].data_ptr()
-
-        def step_root(t):
-            enc_r.encode_device(r_pcm[t, lo:lo + N].data_ptr(), pb, CAP, pn, stream)
-            dec_r.decode_device(po, pb, CAP, pn, d_flags.data_ptr(), d_ret.data_ptr(), stream)
-
-        for t in range(W):
-            step_root(t)
-        torch.cuda.synchronize()
-        dist.barrier()
-        e0r, e1r = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0r.record()
-        for t in range(W, T):
-            step_root(t)
-        e1r.record()
-        torch.cuda.synchronize()
-        t_ = torch.tensor([e0r.elapsed_time(e1r)], device=dev)
-        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-        root_ms = float(t_.item())
-        dist.barrier()
-        same = bool(torch.equal(r_out[lo:lo + N], d_out)) and bool(torch.equal(r_nb[lo:lo + N], d_nb))   # same streams, same packets
-        root = {"value": world * N * K / (root_ms / 1e3), "unit": UNIT, "ms_per_step": root_ms / K,
-                "vs_rank_ingest": (world * N * K / (root_ms / 1e3)) / value,
-                "nvlink_bytes_per_step": (world - 1) * N * (1280 + 2 * (CAP + 4) + 1280),
-                "identical_to_rank_ingest": same,
-                "how": "rank 0 holds PCM in / payloads + PCM out of all %d streams; peers read / write them inside the codec kernels over NVLink (CUDA IPC mapping), max over ranks" % (world * N)}
-        enc_r.close(); dec_r.close()
-        del r_pcm, r_bits, r_nb, r_out, pb, pn, po
+    if dist and not args.no_root_ingest:
+        try:
+            root = measure_root_ingest(args, dist, solo_b200, torch, rank, world, local_rank, dev, N, K, W, T, d_pcm, d_flags, d_ret, d_out, d_nb, stream, value)
+        except Exception as ex:      # the per-rank numbers above stand on their own
+            root = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
         dist.barrier()
 
     # ---------------- end-to-end through the host entry points (`e2e`) ----------------
@@ -444,7 +471,7 @@ def main():
                                         "sample": "%d pinned threads (one per usable core) x %d streams x %d packets, same speech-replay input, FIX encode + FLP decode" % (cores, spt, pk)}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "oracle/_ref missing"}
-        print(json.dumps(line))
+        emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
