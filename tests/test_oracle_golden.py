@@ -78,3 +78,21 @@ def test_loss_process_matches_fixture():
     g = load_golden()
     assert loss_flags(len(g["loss50_flags"]), 50, seed=1) == [int(v) for v in g["loss50_flags"]]
     assert set(loss_flags(400, 0)) == {4} and set(loss_flags(400, 100)) == {1}
+
+
+def test_flp_encoder_leg_of_config0(ref):
+    """BASELINE configs[0] runs the FLP tree's own CLI: FLP encode -> FLP decode of the reference clip.  The product's
+    bitstream target is the FIX encoder, but the oracle build is pinned on this leg too: the FLP encoder's .bit file has the
+    md5 SURVEY.md 7.2 recorded for the reference CLI (it moves under FMA contraction, which is why oracle/Makefile builds with
+    -ffp-contract=off), and the FLP decoder decodes it without error."""
+    clip = load_clip()
+    e = ref.RefEncoder("flp", rate=13600)
+    pk = [e.encode(clip[i * 640:(i + 1) * 640]) for i in range(len(clip) // 640)]
+    e.close()
+    bf = bitfile(pk)
+    assert len(bf) == 16545 and hashlib.md5(bf).hexdigest() == "26da320f33e8d8f9f0043df37765533c"
+    d = ref.RefDecoder("flp")
+    for b, nb, n in pk:
+        x, r = d.decode(b, nb, 4)
+        assert r == 0 and x.shape == (640,)
+    d.close()
