@@ -205,14 +205,16 @@ SB_CFN int c_pitch_analysis_core(PitchScr* P, const i16* signal, i32* pitch_out,
     // instances, their outputs added afterwards -- out32 is a wrap-around sum of the four terms, so the order is free
     c_instances<2>([&](int d, int k) {
         PitchScr* Pj = xoff(P, d);
-        const i16* in = Pj->sig8;
-        i32* o = Pj->dn[k];
+        const i16* __restrict__ in = Pj->sig8;
+        i32* __restrict__ o = Pj->dn[k];
         i32 S = 0;
         if (k == 0) {
             const i32 c1 = SB_T(resampler_down2_1)[0];
+#pragma unroll 8
             for (int q = 0; q < FL4; q++) { const i32 in32 = shl((i32)in[2 * q], 10); const i32 Y = subw(in32, S); const i32 X = smlawb(Y, Y, c1); o[q] = addw(S, X); S = addw(in32, X); }
         } else {
             const i32 c0 = SB_T(resampler_down2_0)[0];
+#pragma unroll 8
             for (int q = 0; q < FL4; q++) { const i32 in32 = shl((i32)in[2 * q + 1], 10); const i32 Y = subw(in32, S); const i32 X = smulwb(Y, c0); o[q] = addw(S, X); S = addw(in32, X); }
         }
     });

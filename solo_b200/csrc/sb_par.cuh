@@ -276,8 +276,15 @@ SB_HD void sb_mark_end(int) {}
 #endif
 #if SB_COOP_ACTIVE
 SB_CFN int sb_slot_bytes();      // stride of the per-stream slots (defined with the slot layout)
-template <class T> SB_HD T* xoff(T* p, int d) { return reinterpret_cast<T*>(reinterpret_cast<char*>(p) + d); }
-template <class T> SB_HD const T* xoff(const T* p, int d) { return reinterpret_cast<const T*>(reinterpret_cast<const char*>(p) + d); }
+// (the slots live in shared memory; telling the compiler so keeps the accesses of the instance code on the shared-memory
+//  path instead of generic loads / stores)
+#if defined(__CUDA_ARCH__) && !defined(SB_NO_SHARED_HINT)
+#define SB_ASSUME_SHARED(q) __builtin_assume(__isShared(q))
+#else
+#define SB_ASSUME_SHARED(q) ((void)0)
+#endif
+template <class T> SB_HD T* xoff(T* p, int d) { T* q = reinterpret_cast<T*>(reinterpret_cast<char*>(p) + d); SB_ASSUME_SHARED(q); return q; }
+template <class T> SB_HD const T* xoff(const T* p, int d) { const T* q = reinterpret_cast<const T*>(reinterpret_cast<const char*>(p) + d); SB_ASSUME_SHARED(q); return q; }
 template <int K, class F> SB_CFN void c_instances(F f) {
 #if SB_XPOSE_ACTIVE
     __syncthreads();

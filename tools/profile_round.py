@@ -125,8 +125,7 @@ for line in sass.splitlines():
     m = re.search(r"Function : (\S+)", line)
     if m:
         d = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-        fn = short(d)
-        fn = re.sub(r".*::", "", fn) if "::" in fn else fn
+        fn = short(d.replace("(anonymous namespace)::", ""))
         cnt[fn] = collections.Counter()
         continue
     m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
