@@ -51,8 +51,10 @@ def test_split_then_merge_is_what_the_reference_receiver_feeds_its_decoder(sb):
 
 def test_dtx_row_and_bad_lengths(sb):
     assert sb.split_packet(b"\0" * 8, (0, 0)) == (b"", b"")
+    p1, p2 = sb.split_packet(bytes(range(20)), (20, 4))   # 20 ms packets / joint mode 1: description 2 may be just the 4 high-band bytes
+    assert p1 == bytes(range(16)) and p2 == bytes(range(16, 20))
     with pytest.raises(sb.SoloError):
-        sb.split_packet(b"\0" * 20, (20, 4))        # description 2 always carries the 8 high-band bytes
+        sb.split_packet(b"\0" * 20, (20, 3))        # description 2 always carries the high-band bytes (at least 4)
     with pytest.raises(sb.SoloError):
         sb.split_packet(b"\0" * 20, (20, 30))
     with pytest.raises(sb.SoloError):
