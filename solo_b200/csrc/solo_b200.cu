@@ -155,8 +155,10 @@ __global__ void __launch_bounds__(SB_TPB) sb_enc_prefilter_kernel(EncState* stat
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int nf = states[s].frames_per_packet;
-    gains_packet(&states[s], &scratch[s], nf);       // (independent of the prefilter: different fields of the control blocks and of the state)
-    prefilter_packet(&states[s], &scratch[s], nf);
+    // two independent recursions per stream, one thread each (blockIdx.y): gain processing and the prefilter touch different
+    // fields of the control blocks and of the state, so the two halves of the grid run side by side
+    if (blockIdx.y == 0) prefilter_packet(&states[s], &scratch[s], nf);
+    else gains_packet(&states[s], &scratch[s], nf);
 }
 
 // Encoder after the band split = three kernels per packet wave (stream s, scratch slot s):
@@ -530,7 +532,7 @@ static int enc_launch(solo_b200_enc_batch* b, int lo, int n, const i16* d_pcm, u
     { int e = sb_launch_enc_hb_warp(states, scratch, bands, b->spp, n, st); if (e) return fail("high-band analysis launch", (cudaError_t)e); }
     { int e = sb_launch_enc_analysis_warp(states, scratch, bands, b->spp, n, st); if (e) return fail("analysis launch", (cudaError_t)e); }
     sb_enc_shape_post_kernel<<<(8 * n + 127) / 128, 128, 0, st>>>(states, scratch, n);
-    sb_enc_prefilter_kernel<<<(n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(states, scratch, n);
+    sb_enc_prefilter_kernel<<<dim3((n + SB_TPB - 1) / SB_TPB, 2), SB_TPB, 0, st>>>(states, scratch, n);
     count_launch(); count_launch(); count_launch(); count_launch();
 #else
 #if SB_QMF_KERNEL
