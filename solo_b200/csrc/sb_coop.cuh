@@ -416,6 +416,7 @@ SB_CFN int c_pitch_analysis_core(PitchScr* P, const i16* signal, i32* pitch_out,
     }
     i32 best = key, who = lane;
     wargmax(best, who);        // first of equal maxima, as the ascending scan with a strict comparison keeps it
+    SB_SYNC();                 // every lane has read the previous correlation (ltpcorr_prev) before lane 0 replaces it
     if (best == SB_I32_MIN) {  // uniform
         if (lane < 4) pitch_out[lane] = 0;
         if (lane == 0) { *LTPCorr_Q15 = 0; *lagIndex = 0; *contourIndex = 0; }
