@@ -5,9 +5,11 @@
 //   * a warp serves two streams, one per 16-lane group (SB_NSQ_GW); lane L < 12 of a group owns one (quantiser qz = L >> 2,
 //     delayed-decision state s = L & 3) recurrence: its 16-stage warped all-pass chain, its 10 newest short-term-prediction
 //     taps and its scalars sit in registers;
-//   * the decision history (4 x 32 x 4 words per quantiser + excitation + pulses) and the three long buffers (160-entry
-//     rings) sit in shared memory, 12.2 KB per stream; a survivor replacing another state is ~40 warp shuffles (registers +
-//     a 64-bit path word) instead of the reference's 1.5 KB memcpy;
+//   * the decision history (per quantiser 3 x 32 x 4 words + output samples + pulses; centre excitation) and the two long
+//     32-bit buffers (160-entry rings) sit in shared memory, 9.8 KB per stream, so that 11 one-warp blocks fit an SM (the
+//     kernel's speed follows the resident warps almost linearly); the output ring xq -- written once per sample, read
+//     only by the rewhitening of voiced frames -- stays in the global state; a survivor replacing another state is ~40
+//     warp shuffles (registers + a 64-bit path word) instead of the reference's 1.5 KB memcpy;
 //   * the joint rate-distortion argmin, worst/best replacement and winner emission run on shuffles; the sample loop is
 //     executed by both groups in lock step with full-warp collectives and warp-uniform trip counts, everything around it
 //     (rewhitening, flushes, rescaling) names its own group so the two streams may diverge there.
@@ -20,21 +22,23 @@ namespace sb {
 
 // Row paddings keep the three quantisers' rows in different shared-memory banks (the 12 lanes address
 // [qz][same index][state]); the pad words are never read.
-// The three long buffers are 160-entry rings: logical index j of the reference's 2*frame_length arrays (old frame
-// [0,160), frame being written [160,320)) lives at j mod 160.  Nothing older than lag + 2 <= 146 samples behind the write
-// position is ever read, so the ring holds exactly the persistent state on entry and on exit.
+// The long buffers (sLTP_Q16, sLTP_shp_Q10 here, xq in NsqState) are 160-entry rings: logical index j of the reference's
+// 2*frame_length arrays (old frame [0,160), frame being written [160,320)) lives at j mod 160.  Nothing older than
+// lag + 2 <= 146 samples behind the write position is ever read, so the ring holds exactly the persistent state on entry and on exit.
 struct NsqSmem {
     i32 sLTP_Q16[3][FRAME + 1];
     i32 sLTP_shp_Q10[3][FRAME + 2];
-    i16 xq[3][FRAME + 2];
     i32 tabRand[3][DD_DELAY + 1][N_DD];
-    i32 tabXq[3][DD_DELAY + 1][N_DD];
     i32 tabPred[3][DD_DELAY + 1][N_DD];
     i32 tabShape[3][DD_DELAY + 1][N_DD];
-    i32 tabExc[DD_DELAY][N_DD];
-    i8 tabQ[3][DD_DELAY + 1][N_DD];
-    i32 Gain_Q16[DD_DELAY];
+    i16 tabXq[3][DD_DELAY + 1][N_DD];      // output sample as it will be emitted (gain of its own sub-frame already applied)
+    i16 tabExc[DD_DELAY][N_DD];            // centre excitation >> 10
+    i8 tabQ[2][DD_DELAY + 1][N_DD];        // pulses of the two descriptions (the centre's are never emitted)
+#ifdef SB_NSQ_PAD
+    i32 pad_[SB_NSQ_PAD];     // occupancy experiments only
+#endif
 };
+static_assert(((2 * sizeof(NsqSmem) + 255) / 256 * 256 + 1024) * 11 <= 233472, "two streams per one-warp block, eleven blocks per SM (228 KB, 1 KB reserved per block)");
 
 // Lane group = the SB_NSQ_GW lanes that work on one stream (16: two streams per warp, 32: one).  Every collective below
 // names its own group (mask gm, width SB_NSQ_GW), so the two halves of a warp may diverge freely.
@@ -60,14 +64,14 @@ struct NsqCand { i32 Q_Q0, Q_Q10, RD, Rd_ind, xq_Q14, LF_AR, shp, exc16, exc; };
 
 // flush `n` delayed samples of the winner of quantiser qz to the outputs, samples spread over the group's lanes (n <= 32)
 __device__ __forceinline__ void nsqw_flush(NsqSmem& S, int gl, int qz_, u64 wpath, int smpl_buf_idx, int n, int sig_off, int shp_idx,
-                                           int ltp_idx, i8* q, i16* r16, int write_pred) {
+                                           int ltp_idx, i8* q, i16* r16, i16* xq, int write_pred) {
     for (int lane = gl; lane < n; lane += SB_NSQ_GW) {
         const int last = (smpl_buf_idx + n - 1 - lane) & DD_MASK;
         const int sl = (int)((wpath >> (2 * last)) & 3);
         const int o = sig_off + lane - n;
-        if (q) q[o] = S.tabQ[qz_][last][sl];
-        if (r16) r16[o] = (i16)(S.tabExc[last][sl] >> 10);
-        S.xq[qz_][o] = (i16)sat16(rshift_round(smulww(S.tabXq[qz_][last][sl], S.Gain_Q16[last]), 10));
+        if (q) q[o] = S.tabQ[qz_ - 1][last][sl];
+        if (r16) r16[o] = S.tabExc[last][sl];
+        xq[o] = S.tabXq[qz_][last][sl];
         S.sLTP_shp_Q10[qz_][cix(shp_idx - n + lane)] = S.tabShape[qz_][last][sl];
         if (write_pred) S.sLTP_Q16[qz_][cix(ltp_idx - n + lane)] = S.tabPred[qz_][last][sl];
     }
@@ -83,6 +87,7 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
     const int qz = act ? (gl >> 2) : 2;
     const int s = gl & 3;
     i8* const Qout = qz == 0 ? (i8*)0 : (qz == 1 ? q_md0 : q_md1);
+    i16* const xq_out = ns3[qz].xq;     // output ring of this lane's quantiser (global state)
 
     const int sigtype = c->sigtype;
     const i32 offset_Q10 = SB_T(quant_offsets_q10)[sigtype * 2 + c->QuantOffsetType];
@@ -101,16 +106,15 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
     // ---- load persistent state into shared memory / registers ----
     for (int qq = 0; qq < 3; qq++) {
         const NsqState* ns = &ns3[qq];
-        for (int i = gl; i < FRAME; i += SB_NSQ_GW) { S.xq[qq][i] = ns->xq[i]; S.sLTP_shp_Q10[qq][i] = ns->sLTP_shp_Q10[i]; S.sLTP_Q16[qq][i] = 0; }
-        if (gl < 2) { S.sLTP_shp_Q10[qq][FRAME + gl] = 0; S.xq[qq][FRAME + gl] = 0; }
+        for (int i = gl; i < FRAME; i += SB_NSQ_GW) { S.sLTP_shp_Q10[qq][i] = ns->sLTP_shp_Q10[i]; S.sLTP_Q16[qq][i] = 0; }
+        if (gl < 2) S.sLTP_shp_Q10[qq][FRAME + gl] = 0;
         if (gl == 0) S.sLTP_Q16[qq][FRAME] = 0;
         for (int i = gl; i < DD_DELAY * N_DD; i += SB_NSQ_GW) {
             (&S.tabRand[qq][0][0])[i] = 0; (&S.tabXq[qq][0][0])[i] = 0; (&S.tabPred[qq][0][0])[i] = 0; (&S.tabShape[qq][0][0])[i] = 0;
-            (&S.tabQ[qq][0][0])[i] = 0;
+            if (qq) (&S.tabQ[qq - 1][0][0])[i] = 0;
             if (qq == 0) (&S.tabExc[0][0])[i] = 0;
         }
     }
-    for (int i = gl; i < DD_DELAY; i += SB_NSQ_GW) S.Gain_Q16[i] = 0;
     __syncwarp(gm);
     if (gl < N_DD) for (int qq = 0; qq < 3; qq++) S.tabShape[qq][0][gl] = ns3[qq].sLTP_shp_Q10[FRAME - 1];
     NsqLane L;
@@ -167,7 +171,7 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                     for (int qq = 0; qq < 3; qq++) {
                         u64 wpath = shfl64(gm, L.path, qq * 4 + Winner);
                         nsqw_flush(S, gl, qq, wpath, smpl_buf_idx, decisionDelay, sig_off, shp_idx, ltp_idx,
-                                   qq == 0 ? (i8*)0 : (qq == 1 ? q_md0 : q_md1), qq == 0 ? r16 : (i16*)0, 0);
+                                   qq == 0 ? (i8*)0 : (qq == 1 ? q_md0 : q_md1), qq == 0 ? r16 : (i16*)0, ns3[qq].xq, 0);
                     }
                     __syncwarp(gm);
                 }
@@ -178,7 +182,7 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                 const int lagk = c->pitchL[k];
                 const int n0 = FRAME - lagk - LTP_ORDER / 2;
                 for (int qq = 0; qq < 3; qq++) {
-                    const i16* in = S.xq[qq];
+                    const i16* in = ns3[qq].xq;   // this warp's own emissions of the frame so far, ordered by the barriers around them
                     for (int n = n0 + gl; n < FRAME; n += SB_NSQ_GW) {
                         const int j = k * SUBFR + n;   // logical position in [old frame | this frame]
                         i32 pred = 0;
@@ -461,9 +465,9 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                 if ((subfr > 0 || i >= decisionDelay) && act && s == Winner) {
                     const int sl = (int)((L.path >> (2 * last_smple_idx)) & 3);
                     const int o = sig_off + i - decisionDelay;
-                    if (Qout) Qout[o] = S.tabQ[qz][last_smple_idx][sl];
-                    if (qz == 0) r16[o] = (i16)(S.tabExc[last_smple_idx][sl] >> 10);
-                    S.xq[qz][o] = (i16)sat16(rshift_round(smulww(S.tabXq[qz][last_smple_idx][sl], S.Gain_Q16[last_smple_idx]), 10));
+                    if (Qout) Qout[o] = S.tabQ[qz - 1][last_smple_idx][sl];
+                    if (qz == 0) r16[o] = S.tabExc[last_smple_idx][sl];
+                    xq_out[o] = S.tabXq[qz][last_smple_idx][sl];
                     S.sLTP_shp_Q10[qz][cix(shp_idx - decisionDelay)] = S.tabShape[qz][last_smple_idx][sl];
                     S.sLTP_Q16[qz][cix(ltp_idx - decisionDelay)] = S.tabPred[qz][last_smple_idx][sl];
                 }
@@ -480,15 +484,14 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                 L.Seed = addw(L.Seed, c0.Q_Q0);
                 L.RD = c0.RD;
                 if (act) {
-                    S.tabXq[qz][smpl_buf_idx][s] = c0.xq_Q14 >> 4;
-                    S.tabQ[qz][smpl_buf_idx][s] = (i8)c0.Q_Q0;
+                    S.tabXq[qz][smpl_buf_idx][s] = (i16)sat16(rshift_round(smulww(c0.xq_Q14 >> 4, Gain_Q16), 10));
+                    if (qz) S.tabQ[qz - 1][smpl_buf_idx][s] = (i8)c0.Q_Q0;
                     S.tabPred[qz][smpl_buf_idx][s] = c0.exc16;
                     S.tabShape[qz][smpl_buf_idx][s] = c0.shp;
                     S.tabRand[qz][smpl_buf_idx][s] = L.Seed;
-                    if (qz == 0) S.tabExc[smpl_buf_idx][s] = c0.exc;
+                    if (qz == 0) S.tabExc[smpl_buf_idx][s] = (i16)(c0.exc >> 10);
                 }
                 L.path = (L.path & ~((u64)3 << (2 * smpl_buf_idx))) | ((u64)s << (2 * smpl_buf_idx));
-                if (gl == 0) S.Gain_Q16[smpl_buf_idx] = Gain_Q16;
             }
             __syncwarp();
         }
@@ -507,7 +510,7 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
         for (int qq = 0; qq < 3; qq++) {
             u64 wpath = shfl64(gm, L.path, qq * 4 + Winner);
             nsqw_flush(S, gl, qq, wpath, smpl_buf_idx, decisionDelay, FRAME, shp_idx, ltp_idx,
-                       qq == 0 ? (i8*)0 : (qq == 1 ? q_md0 : q_md1), qq == 0 ? r16 : (i16*)0, 1);
+                       qq == 0 ? (i8*)0 : (qq == 1 ? q_md0 : q_md1), qq == 0 ? r16 : (i16*)0, ns3[qq].xq, 1);
         }
         __syncwarp(gm);
         if (act && s == Winner) {
@@ -522,7 +525,7 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
         }
         for (int qq = 0; qq < 3; qq++) {
             NsqState* ns = &ns3[qq];
-            for (int i = gl; i < FRAME; i += SB_NSQ_GW) { ns->xq[i] = S.xq[qq][i]; ns->sLTP_shp_Q10[i] = S.sLTP_shp_Q10[qq][i]; }
+            for (int i = gl; i < FRAME; i += SB_NSQ_GW) ns->sLTP_shp_Q10[i] = S.sLTP_shp_Q10[qq][i];
         }
         __syncwarp(gm);
     }

@@ -194,10 +194,10 @@ __global__ void __launch_bounds__(SB_ANA_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_
 #endif
 
 #ifndef SB_NSQ_WARPS
-#define SB_NSQ_WARPS 1      // one warp = two streams = 2 x 12.2 KB of shared memory; 9 blocks (18 streams) per SM
+#define SB_NSQ_WARPS 1      // one warp = two streams = 2 x 9.8 KB of shared memory; 11 blocks (22 streams) per SM
 #endif
 #ifndef SB_NSQ_MINB
-#define SB_NSQ_MINB 10     // 168 registers: 9 one-warp blocks per SM
+#define SB_NSQ_MINB 11     // <= 186 registers per thread
 #endif
 #define SB_NSQ_SPB (SB_NSQ_WARPS * (32 / SB_NSQ_GW))   // streams per block
 __global__ void __launch_bounds__(SB_NSQ_WARPS * 32, SB_NSQ_MINB) sb_enc_nsq_kernel(EncState* states, EncScratch* scratch, int n) {
