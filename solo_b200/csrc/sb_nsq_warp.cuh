@@ -5,11 +5,12 @@
 //   * a warp serves two streams, one per 16-lane group (SB_NSQ_GW); lane L < 12 of a group owns one (quantiser qz = L >> 2,
 //     delayed-decision state s = L & 3) recurrence: its 16-stage warped all-pass chain, its 10 newest short-term-prediction
 //     taps and its scalars sit in registers;
-//   * the decision history (per quantiser 3 x 32 x 4 words + output samples + pulses; centre excitation) and the two long
-//     32-bit buffers (160-entry rings) sit in shared memory, 9.8 KB per stream, so that 11 one-warp blocks fit an SM (the
-//     kernel's speed follows the resident warps almost linearly); the output ring xq -- written once per sample, read
-//     only by the rewhitening of voiced frames -- stays in the global state; a survivor replacing another state is ~40
-//     warp shuffles (registers + a 64-bit path word) instead of the reference's 1.5 KB memcpy;
+//   * the decision history (per quantiser 2 x 32 x 4 words + output samples + pulses; centre excitation) and the two long
+//     32-bit buffers (160-entry rings) sit in shared memory, 8.2 KB per stream, so that 12 one-warp blocks fit an SM (the
+//     kernel's time is ~ a + b / resident warps; 168 registers allow no more than 12).  What is touched once per sample
+//     with slack stays in global memory: the output ring xq (read back only by the rewhitening of voiced frames) and the
+//     random-generator history (loaded at the top of a sample, used at its end).  A survivor replacing another state is
+//     ~40 warp shuffles (registers + a 64-bit path word) instead of the reference's 1.5 KB memcpy;
 //   * the joint rate-distortion argmin, worst/best replacement and winner emission run on shuffles; the sample loop is
 //     executed by both groups in lock step with full-warp collectives and warp-uniform trip counts, everything around it
 //     (rewhitening, flushes, rescaling) names its own group so the two streams may diverge there.
@@ -28,7 +29,6 @@ namespace sb {
 struct NsqSmem {
     i32 sLTP_Q16[3][FRAME + 1];
     i32 sLTP_shp_Q10[3][FRAME + 2];
-    i32 tabRand[3][DD_DELAY + 1][N_DD];
     i32 tabPred[3][DD_DELAY + 1][N_DD];
     i32 tabShape[3][DD_DELAY + 1][N_DD];
     i16 tabXq[3][DD_DELAY + 1][N_DD];      // output sample as it will be emitted (gain of its own sub-frame already applied)
@@ -38,7 +38,7 @@ struct NsqSmem {
     i32 pad_[SB_NSQ_PAD];     // occupancy experiments only
 #endif
 };
-static_assert(((2 * sizeof(NsqSmem) + 255) / 256 * 256 + 1024) * 11 <= 233472, "two streams per one-warp block, eleven blocks per SM (228 KB, 1 KB reserved per block)");
+static_assert(((2 * sizeof(NsqSmem) + 255) / 256 * 256 + 1024) * 12 <= 233472, "two streams per one-warp block, twelve blocks per SM (228 KB, 1 KB reserved per block)");
 
 // Lane group = the SB_NSQ_GW lanes that work on one stream (16: two streams per warp, 32: one).  Every collective below
 // names its own group (mask gm, width SB_NSQ_GW), so the two halves of a warp may diverge freely.
@@ -79,7 +79,7 @@ __device__ __forceinline__ void nsqw_flush(NsqSmem& S, int gl, int qz_, u64 wpat
 
 // One 20 ms frame.  st: persistent quantiser states (global); c: frame control from the analysis stage (global, Seed is
 // updated); x: prefiltered input; outputs: pulses of the two descriptions, (int16)(centre excitation >> 10).
-__device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i16* __restrict__ x, i8* q_md0, i8* q_md1, i16* r16) {
+__device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i16* __restrict__ x, i8* q_md0, i8* q_md1, i16* r16, i32* rand_g) {
     const int gl = threadIdx.x & (SB_NSQ_GW - 1);                 // gl inside the group
     const int gsh = (threadIdx.x & 31) & ~(SB_NSQ_GW - 1);         // first warp gl of the group
     const unsigned gm = SB_NSQ_GW == 32 ? 0xffffffffu : (0xffffu << gsh);
@@ -110,7 +110,7 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
         if (gl < 2) S.sLTP_shp_Q10[qq][FRAME + gl] = 0;
         if (gl == 0) S.sLTP_Q16[qq][FRAME] = 0;
         for (int i = gl; i < DD_DELAY * N_DD; i += SB_NSQ_GW) {
-            (&S.tabRand[qq][0][0])[i] = 0; (&S.tabXq[qq][0][0])[i] = 0; (&S.tabPred[qq][0][0])[i] = 0; (&S.tabShape[qq][0][0])[i] = 0;
+            rand_g[qq * (DD_DELAY * N_DD) + i] = 0; (&S.tabXq[qq][0][0])[i] = 0; (&S.tabPred[qq][0][0])[i] = 0; (&S.tabShape[qq][0][0])[i] = 0;
             if (qq) (&S.tabQ[qq - 1][0][0])[i] = 0;
             if (qq == 0) (&S.tabExc[0][0])[i] = 0;
         }
@@ -246,6 +246,10 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
         __syncwarp();
 
         for (int i = 0; i < SUBFR; i++) {
+            // random-generator state of the sample that leaves the decision window, along this lane's path: fetched from the
+            // global history now, needed only at the winner selection some 400 instructions later
+            const int last_pre = (smpl_buf_idx - 1 + decisionDelay) & DD_MASK;
+            const i32 rs = rand_g[(qz * DD_DELAY + last_pre) * N_DD + (int)((L.path >> (2 * last_pre)) & 3)];
             // ---- long-term prediction / harmonic shaping of this gl's quantiser ----
             i32 LTP_pred_Q14 = 0, n_LTP_Q14 = 0;
             if (sigtype == 0) {
@@ -403,7 +407,6 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                 int W0 = 0; i32 RDmin = j0[0];
 #pragma unroll
                 for (int m = 1; m < 4; m++) { const bool t = j0[m] < RDmin; RDmin = t ? j0[m] : RDmin; W0 = t ? m : W0; }
-                const i32 rs = S.tabRand[qz][last_smple_idx][(int)((L.path >> (2 * last_smple_idx)) & 3)];
                 const i32 wrs = shfl(fm, rs, qz * 4 + W0);
                 const unsigned bal = (__ballot_sync(fm, act && rs != wrs) >> gsh) & 0xffffu;
                 const unsigned mstate = (bal | (bal >> 4) | (bal >> 8)) & 0xF;
@@ -488,7 +491,7 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
                     if (qz) S.tabQ[qz - 1][smpl_buf_idx][s] = (i8)c0.Q_Q0;
                     S.tabPred[qz][smpl_buf_idx][s] = c0.exc16;
                     S.tabShape[qz][smpl_buf_idx][s] = c0.shp;
-                    S.tabRand[qz][smpl_buf_idx][s] = L.Seed;
+                    rand_g[(qz * DD_DELAY + smpl_buf_idx) * N_DD + s] = L.Seed;
                     if (qz == 0) S.tabExc[smpl_buf_idx][s] = (i16)(c0.exc >> 10);
                 }
                 L.path = (L.path & ~((u64)3 << (2 * smpl_buf_idx))) | ((u64)s << (2 * smpl_buf_idx));

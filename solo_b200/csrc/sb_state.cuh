@@ -156,6 +156,8 @@ struct EncScratch {
     i32 nlsf_Q15[2][2][LPC_ORDER];
     i16 lpc_in_pre[2][NB_SUBFR * LPC_ORDER + FRAME];
     i32 local_gains[2][NB_SUBFR];
+    // quantiser kernel: random-generator states of the delayed-decision window, [quantiser][position][state]
+    i32 nsq_rand[3][DD_DELAY][N_DD];
 };
 
 // Range coder (SKP_Silk_range_coder_state, structs.h:85-92); the byte buffer lives with the caller.

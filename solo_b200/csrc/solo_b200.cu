@@ -194,10 +194,10 @@ __global__ void __launch_bounds__(SB_ANA_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_
 #endif
 
 #ifndef SB_NSQ_WARPS
-#define SB_NSQ_WARPS 1      // one warp = two streams = 2 x 9.8 KB of shared memory; 11 blocks (22 streams) per SM
+#define SB_NSQ_WARPS 1      // one warp = two streams = 2 x 8.2 KB of shared memory; 12 blocks (24 streams) per SM
 #endif
 #ifndef SB_NSQ_MINB
-#define SB_NSQ_MINB 11     // <= 186 registers per thread
+#define SB_NSQ_MINB 12     // <= 170 registers per thread
 #endif
 #define SB_NSQ_SPB (SB_NSQ_WARPS * (32 / SB_NSQ_GW))   // streams per block
 __global__ void __launch_bounds__(SB_NSQ_WARPS * 32, SB_NSQ_MINB) sb_enc_nsq_kernel(EncState* states, EncScratch* scratch, int n) {
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(SB_NSQ_WARPS * 32, SB_NSQ_MINB) sb_enc_nsq_ker
     EncScratch* scr = &scratch[s];
     const int nf = states[s].frames_per_packet;
     for (int f = 0; f < nf; f++)
-        nsq_del_dec_warp(*S, states[s].nsq, &scr->c[f], scr->xfw[f], scr->q_md[f][0], scr->q_md[f][1], scr->r16[f]);
+        nsq_del_dec_warp(*S, states[s].nsq, &scr->c[f], scr->xfw[f], scr->q_md[f][0], scr->q_md[f][1], scr->r16[f], &scr->nsq_rand[0][0][0]);
 }
 
 __global__ void __launch_bounds__(SB_TPB, SB_FINISH_MINB) sb_enc_finish_kernel(EncState* states, const EncScratch* scratch, u8* __restrict__ bits, int cap,
