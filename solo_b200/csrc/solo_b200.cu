@@ -1,11 +1,16 @@
 // solo_b200 -- sm_100a kernels and the C ABI of libsolo_b200.so.
 //
-// One packet wave = five kernels:
-//   A0 sb_enc_qmf_kernel       warp per stream     QMF band split, PCM row fetched by TMA (cp.async.bulk)
-//   A  sb_enc_analysis_kernel  thread per stream   VAD .. gain processing of both 20 ms frames, high-band analysis
-//   B  sb_enc_nsq_kernel       two streams / warp  MD delayed-decision noise-shaping quantiser, history in shared memory
-//   C  sb_enc_finish_kernel    thread per stream   range coding of both descriptions, high-band gains, payload assembly
-//   D  sb_decode_kernel        thread per stream   the whole decoder incl. concealment, high band and QMF synthesis
+// One packet wave of the encoder = eight launches, of the decoder = two:
+//   sb_enc_qmf_kernel            warp per stream       QMF band split, PCM rows fetched by the TMA engine (cp.async.bulk)
+//   sb_enc_vad_kernel            thread per stream     voice-activity detection of both frames (pure recurrences)
+//   sb_enc_hb_warp_kernel        warp per stream       high-band LPC / LSP analysis            (sb_analysis.cu, sb_coop.cuh)
+//   sb_enc_analysis_warp_kernel  warp per stream       pitch, noise shaping, LTP / LPC / NLSF analysis, state in shared memory
+//   sb_enc_shape_post_kernel     thread per window     shaping-filter post-processing (inverse gains, coefficient limiting)
+//   sb_enc_prefilter_kernel      thread per stream     prefilter recurrence | gain processing (grid.y)
+//   sb_enc_nsq_kernel            two streams per warp  MD delayed-decision noise-shaping quantiser, history in shared memory
+//   sb_enc_finish_kernel         2 threads per stream  range coding of one description each, high-band gains, payload assembly
+//   sb_decode_kernel             thread per stream     range decoding, synthesis, concealment, comfort noise, high band
+//   sb_dec_synth_kernel          warp per stream       QMF synthesis filter bank + float -> int16
 // Persistent per-stream state lives in device arrays (EncState / DecState) that never leave the GPU between packets;
 // a wave is processed as a few chunks of streams on internal CUDA streams (Pipe).  The host code below is the C ABI:
 // the batched entry points of include/solo_b200.h and the reference's six functions of include/AGR_JC1_SDK_API.h.
@@ -27,32 +32,15 @@ using namespace sb;
 // kernels
 // ---------------------------------------------------------------------------------------------------
 #define SB_TPB 64
-#ifndef SB_ANA_TPB
-#define SB_ANA_TPB 64        // threads per block of the analysis kernel
-#endif
 #ifndef SB_DEC_TPB
 #define SB_DEC_TPB 64
-#endif
-#ifndef SB_ANALYSIS_LOCAL_STATE
-#define SB_ANALYSIS_LOCAL_STATE 1   // stage the per-stream state in local memory for the duration of a packet (thread-per-stream kernels)
 #endif
 #ifndef SB_DECODE_LOCAL_STATE
 #define SB_DECODE_LOCAL_STATE 0
 #endif
-#ifndef SB_ANA_SMEM_TABS
-#define SB_ANA_SMEM_TABS 1    // NLSF codebooks of kernel A in shared memory (5.2 KB per block)
-#endif
-#ifndef SB_QMF_KERNEL
-#define SB_QMF_KERNEL 1       // band split as its own warp-per-stream kernel with a TMA-fetched PCM tile (0: inside kernel A)
-#endif
-#ifndef SB_ANALYSIS_WARP
-#define SB_ANALYSIS_WARP 1   // 1: stage A = the warp-per-stream kernels of sb_analysis.cu; 0: the thread-per-stream kernel below
-#endif
+// the warp-per-stream analysis kernels live in sb_analysis.cu
 extern "C" int sb_launch_enc_analysis_warp(void* states, void* scratch, const void* bands, int spp, int n, void* stream);
 extern "C" int sb_launch_enc_hb_warp(void* states, void* scratch, const void* bands, int spp, int n, void* stream);
-#ifndef SB_ANALYSIS_MINB
-#define SB_ANALYSIS_MINB 4   // min resident blocks per SM of the analysis kernel (register cap = 65536 / (64 * MINB) = 255)
-#endif
 #ifndef SB_FINISH_MINB
 #define SB_FINISH_MINB 8     // 128 registers: every stream of a chunk resident (0.92 -> 0.65 ms per wave)
 #endif
@@ -161,38 +149,6 @@ __global__ void __launch_bounds__(SB_TPB) sb_enc_prefilter_kernel(EncState* stat
     else gains_packet(&states[s], &scratch[s], nf);
 }
 
-// Encoder after the band split = three kernels per packet wave (stream s, scratch slot s):
-//   A  sb_enc_analysis_kernel : one thread per stream  -- QMF split, VAD .. gain processing of both frames, high-band analysis
-//   B  sb_enc_nsq_kernel      : one WARP per stream    -- MD delayed-decision noise-shaping quantiser, state in shared memory
-//   C  sb_enc_finish_kernel   : one thread per stream  -- range coding of both descriptions, high-band gains, payload assembly
-#if !SB_ANALYSIS_WARP
-__global__ void __launch_bounds__(SB_ANA_TPB, SB_ANALYSIS_MINB) sb_enc_analysis_kernel(EncState* states, EncScratch* scratch, const i16* __restrict__ pcm, const i16* __restrict__ bands, int spp, int n) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-#if SB_ANA_SMEM_TABS
-    __shared__ NlsfFastTabs s_nlsf;
-    nlsf_fast_tabs_fill(&s_nlsf, threadIdx.x, blockDim.x);
-    __syncthreads();
-#endif
-    if (s >= n) return;
-    EncAnalysisWork W;
-#if SB_ANA_SMEM_TABS
-    W.nlsf_fast = &s_nlsf;
-#else
-    W.nlsf_fast = nullptr;
-#endif
-    const i16* x = pcm + (size_t)s * spp;      // row of spp = 640 (40 ms) or 320 (20 ms) samples, read once, with 128-bit loads, by the QMF split
-#if SB_ANALYSIS_LOCAL_STATE
-    // analysis state staged in local memory: same-offset words of the 32 streams of a warp share cache lines there
-    EncCore st = static_cast<const EncCore&>(states[s]);
-    enc_packet_analysis(&st, &W, x, &scratch[s], bands ? bands + (size_t)s * spp : nullptr);
-    static_cast<EncCore&>(states[s]) = st;
-#else
-    enc_packet_analysis(&states[s], &W, x, &scratch[s], bands ? bands + (size_t)s * spp : nullptr);
-#endif
-}
-
-#endif
-
 #ifndef SB_NSQ_WARPS
 #define SB_NSQ_WARPS 1      // one warp = two streams = 2 x 8.2 KB of shared memory; 12 blocks (24 streams) per SM
 #endif
@@ -217,15 +173,49 @@ __global__ void __launch_bounds__(SB_NSQ_WARPS * 32, SB_NSQ_MINB) sb_enc_nsq_ker
         nsq_del_dec_warp(*S, states[s].nsq, &scr->c[f], scr->xfw[f], scr->q_md[f][0], scr->q_md[f][1], scr->r16[f], &scr->nsq_rand[0][0][0]);
 }
 
+// Entropy coding and payload assembly, TWO threads per stream: thread k range-codes description k of both frames (the two
+// coders share nothing but read-only frame parameters) and packs high-band frame k; the pair exchanges lengths and status
+// by shuffle and writes the row [MD1 | MD2 | HB].  Same result as the one-thread model enc_packet_finish() (sb_enc.cuh).
 __global__ void __launch_bounds__(SB_TPB, SB_FINISH_MINB) sb_enc_finish_kernel(EncState* states, const EncScratch* scratch, u8* __restrict__ bits, int cap,
                                                                i16* __restrict__ nbytes, int n) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = t >> 1, k = t & 1;
+    const unsigned m = __ballot_sync(0xffffffffu, s < n);     // whole pairs
     if (s >= n) return;
+    EncCore* st = &states[s];
+    const EncScratch* scr = &scratch[s];
+    u8* out = bits + (size_t)s * cap;
     u8 rcbuf[MAX_PAYLOAD];
-    i16 nb[2];
-    enc_packet_finish(&states[s], &scratch[s], rcbuf, bits + (size_t)s * cap, cap, nb);
-    nbytes[2 * s] = nb[0];
-    nbytes[2 * s + 1] = nb[1];
+    const int nf = st->frames_per_packet, nhb = nf * FRAME / st->hb_frame, hb_bytes = 4 * nhb;
+    RangeEnc rc;
+    rc_enc_init(&rc, rcbuf, MAX_PAYLOAD);
+    for (int f = 0; f < nf; f++) {
+        encode_parameters(&rc, st, &scr->c[f], k, f, scr->vadFlag[f], scr->q_md[f][k]);
+        // frame terminator: MORE_FRAMES (1) while frames follow in this packet, LAST_FRAME (0) after the last one
+        rc_encode(&rc, f < nf - 1 ? 1 : 0, SB_T(frame_term_cdf));
+    }
+    int nb_k;
+    rc_get_length(&rc, &nb_k);
+    const int ok_k = rc.error ? 0 : 1;
+    const int nb_o = __shfl_xor_sync(m, nb_k, 1), ok_o = __shfl_xor_sync(m, ok_k, 1);
+    const int nb0 = k ? nb_o : nb_k, nb1 = k ? nb_k : nb_o, ok0 = k ? ok_o : ok_k, ok1 = k ? ok_k : ok_o;
+    const int ok = ok0 && ok1 && nb0 + nb1 <= MAX_PAYLOAD;        // pnBytesOut[0] >= nMDBytes (encode_frame_FIX.c:245)
+    const int dtx = scr->dtx_drop;
+    if (k == 0 ? ok0 : ok) {
+        rc_enc_wrap_up(&rc);
+        const int off = k ? nb0 : 0;
+        for (int i = 0; i < nb_k; i++) if (off + i < cap) out[off + i] = rcbuf[i];
+    }
+    u8 hb[4];
+    const int my_hb = k < nhb;
+    if (my_hb) hb_pack_frame(scr->hb_lsp_idx[k], scr->hb_nrg0[k], &scr->r16[0][0] + k * st->hb_frame, hb, st->hb_frame >> 2);
+    __syncwarp(m);      // a rejected or dropped packet's high-band bytes land on top of description 1's
+    const int lb = (ok && !dtx) ? nb0 + nb1 : 0;
+    if (my_hb) for (int i = 0; i < 4; i++) if (lb + 4 * k + i < cap) out[lb + 4 * k + i] = hb[i];
+    if (k == 0) {
+        nbytes[2 * s] = lb ? (i16)(lb + hb_bytes) : 0;
+        nbytes[2 * s + 1] = lb ? (i16)(nb1 + hb_bytes) : 0;
+    }
 }
 
 __global__ void __launch_bounds__(SB_TPB) sb_dec_init_kernel(DecState* states, int n, int mdi, int framesize_ms, int joint_hb) {
@@ -524,34 +514,22 @@ static int enc_launch(solo_b200_enc_batch* b, int lo, int n, const i16* d_pcm, u
     const i16* pcm = d_pcm + (size_t)lo * b->spp;
     EvPair ev;
     prof_begin(st, 0, &ev);
-#if SB_ANALYSIS_WARP
     i16* bands = b->d_bands + (size_t)lo * b->spp;
     sb_enc_qmf_kernel<<<(n + SB_QMF_SPB - 1) / SB_QMF_SPB, SB_QMF_SPB * 32, 0, st>>>(states, pcm, bands, b->spp, n, pcm_is_local(b->device, pcm));
     sb_enc_vad_kernel<<<(n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(states, scratch, bands, b->spp, n);
-    count_launch();
     { int e = sb_launch_enc_hb_warp(states, scratch, bands, b->spp, n, st); if (e) return fail("high-band analysis launch", (cudaError_t)e); }
     { int e = sb_launch_enc_analysis_warp(states, scratch, bands, b->spp, n, st); if (e) return fail("analysis launch", (cudaError_t)e); }
     sb_enc_shape_post_kernel<<<(8 * n + 127) / 128, 128, 0, st>>>(states, scratch, n);
     sb_enc_prefilter_kernel<<<dim3((n + SB_TPB - 1) / SB_TPB, 2), SB_TPB, 0, st>>>(states, scratch, n);
-    count_launch(); count_launch(); count_launch(); count_launch();
-#else
-#if SB_QMF_KERNEL
-    i16* bands = b->d_bands + (size_t)lo * b->spp;
-    sb_enc_qmf_kernel<<<(n + SB_QMF_SPB - 1) / SB_QMF_SPB, SB_QMF_SPB * 32, 0, st>>>(states, pcm, bands, b->spp, n, pcm_is_local(b->device, pcm));
-    count_launch();
-#else
-    const i16* bands = nullptr;
-#endif
-    sb_enc_analysis_kernel<<<(n + SB_ANA_TPB - 1) / SB_ANA_TPB, SB_ANA_TPB, 0, st>>>(states, scratch, pcm, bands, b->spp, n);
-#endif
+    for (int i = 0; i < 6; i++) count_launch();
     prof_end(st, &ev);
     prof_begin(st, 1, &ev);
     sb_enc_nsq_kernel<<<(n + SB_NSQ_SPB - 1) / SB_NSQ_SPB, SB_NSQ_WARPS * 32, SB_NSQ_SPB * sizeof(NsqSmem), st>>>(states, scratch, n);
     prof_end(st, &ev);
     prof_begin(st, 2, &ev);
-    sb_enc_finish_kernel<<<(n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(states, scratch, d_bits + (size_t)lo * cap, cap, d_nbytes + 2 * (size_t)lo, n);
+    sb_enc_finish_kernel<<<(2 * n + SB_TPB - 1) / SB_TPB, SB_TPB, 0, st>>>(states, scratch, d_bits + (size_t)lo * cap, cap, d_nbytes + 2 * (size_t)lo, n);
     prof_end(st, &ev);
-    count_launch(); count_launch(); count_launch();
+    count_launch(); count_launch();
     CK(cudaGetLastError());
     return 0;
 }
