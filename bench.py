@@ -207,16 +207,32 @@ def measure_root_ingest(args, dist, solo_b200, torch, rank, world, local_rank, d
     back -- scatter and gather are fused into the kernels that consume / produce the data, no NCCL transfer step, no staging copy."""
     from solo_b200.shard import share_from_root
     lo = rank * N
+
+    def agree(ok):      # every rank takes part, so that a failure on one rank ends the measurement on all of them together
+        f = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        return bool(f.item())
+
+    err = None
+    r_pcm = r_bits = r_nb = r_out = None
     if rank == 0:
-        r_pcm = torch.empty((T, world * N, 640), dtype=torch.int16, device=dev)
-        r_bits = torch.zeros((world * N, CAP), dtype=torch.uint8, device=dev)
-        r_nb = torch.zeros((world * N, 2), dtype=torch.int16, device=dev)
-        r_out = torch.zeros((world * N, 640), dtype=torch.int16, device=dev)
-    else:
-        r_pcm = r_bits = r_nb = r_out = None
-    r_pcm, r_bits, r_nb, r_out = (share_from_root(t_) for t_ in (r_pcm, r_bits, r_nb, r_out))
-    r_pcm[:, lo:lo + N].copy_(d_pcm)                 # setup (untimed): every rank deposits its input rows at the root
-    torch.cuda.synchronize()
+        try:
+            r_pcm = torch.empty((T, world * N, 640), dtype=torch.int16, device=dev)
+            r_bits = torch.zeros((world * N, CAP), dtype=torch.uint8, device=dev)
+            r_nb = torch.zeros((world * N, 2), dtype=torch.int16, device=dev)
+            r_out = torch.zeros((world * N, 640), dtype=torch.int16, device=dev)
+        except Exception as ex:
+            err = ex
+    if not agree(err is None):
+        return {"error": "root buffers: %s" % (str(err)[:160] if err else "failed on rank 0")}
+    try:
+        r_pcm, r_bits, r_nb, r_out = (share_from_root(t_) for t_ in (r_pcm, r_bits, r_nb, r_out))
+        r_pcm[:, lo:lo + N].copy_(d_pcm)             # setup (untimed): every rank deposits its input rows at the root
+        torch.cuda.synchronize()
+    except Exception as ex:
+        err = ex
+    if not agree(err is None):
+        return {"error": "peer mapping: %s" % (str(err)[:160] if err else "failed on another rank")}
     dist.barrier()
     enc_r = solo_b200.EncoderBatch(N, rate=RATE, device=local_rank)
     dec_r = solo_b200.DecoderBatch(N, device=local_rank)
