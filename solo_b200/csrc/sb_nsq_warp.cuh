@@ -16,8 +16,16 @@
 //     (rewhitening, flushes, rescaling) names its own group so the two streams may diverge there.
 // Lanes 12..15 of a group execute the same instruction stream on clamped indices and never store.
 #pragma once
-#ifdef __CUDACC__
+// (tests/hostsim compiles this file for the host under SB_EMU: 32 fibres play the lanes, the warp intrinsics are shims)
+#if defined(__CUDACC__) || defined(SB_EMU)
 #include "sb_nsq.cuh"
+#ifdef __CUDACC__
+#define SB_NSQ_DEV __device__ __forceinline__
+#define SB_NSQ_KFN __device__
+#else
+#define SB_NSQ_DEV inline
+#define SB_NSQ_KFN inline
+#endif
 
 namespace sb {
 
@@ -45,9 +53,9 @@ static_assert(((2 * sizeof(NsqSmem) + 255) / 256 * 256 + 1024) * 12 <= 233472, "
 #ifndef SB_NSQ_GW
 #define SB_NSQ_GW 16
 #endif
-__device__ __forceinline__ int cix(int j) { return j >= FRAME ? j - FRAME : j; }   // ring index, 0 <= j <= 2*FRAME
-__device__ __forceinline__ i32 shfl(unsigned gm, i32 v, int src) { return __shfl_sync(gm, v, src, SB_NSQ_GW); }
-__device__ __forceinline__ u64 shfl64(unsigned gm, u64 v, int src) {
+SB_NSQ_DEV int cix(int j) { return j >= FRAME ? j - FRAME : j; }   // ring index, 0 <= j <= 2*FRAME
+SB_NSQ_DEV i32 shfl(unsigned gm, i32 v, int src) { return __shfl_sync(gm, v, src, SB_NSQ_GW); }
+SB_NSQ_DEV u64 shfl64(unsigned gm, u64 v, int src) {
     u32 lo = __shfl_sync(gm, (u32)v, src, SB_NSQ_GW), hi = __shfl_sync(gm, (u32)(v >> 32), src, SB_NSQ_GW);
     return ((u64)hi << 32) | lo;
 }
@@ -59,11 +67,11 @@ struct NsqLane {            // registers of one (quantiser, state) recurrence
     u64 path;
 };
 // acc + (x * c16) >> 16 with the coefficient already moved to the high half-word (one IMAD.HI, no shift in the loop)
-__device__ __forceinline__ i32 mlahi(i32 acc, i32 x, i32 c_hi) { return addw(acc, __mulhi(x, c_hi)); }
+SB_NSQ_DEV i32 mlahi(i32 acc, i32 x, i32 c_hi) { return addw(acc, __mulhi(x, c_hi)); }
 struct NsqCand { i32 Q_Q0, Q_Q10, RD, Rd_ind, xq_Q14, LF_AR, shp, exc16, exc; };
 
 // flush `n` delayed samples of the winner of quantiser qz to the outputs, samples spread over the group's lanes (n <= 32)
-__device__ __forceinline__ void nsqw_flush(NsqSmem& S, int gl, int qz_, u64 wpath, int smpl_buf_idx, int n, int sig_off, int shp_idx,
+SB_NSQ_DEV void nsqw_flush(NsqSmem& S, int gl, int qz_, u64 wpath, int smpl_buf_idx, int n, int sig_off, int shp_idx,
                                            int ltp_idx, i8* q, i16* r16, i16* xq, int write_pred) {
     for (int lane = gl; lane < n; lane += SB_NSQ_GW) {
         const int last = (smpl_buf_idx + n - 1 - lane) & DD_MASK;
@@ -79,7 +87,7 @@ __device__ __forceinline__ void nsqw_flush(NsqSmem& S, int gl, int qz_, u64 wpat
 
 // One 20 ms frame.  st: persistent quantiser states (global); c: frame control from the analysis stage (global, Seed is
 // updated); x: prefiltered input; outputs: pulses of the two descriptions, (int16)(centre excitation >> 10).
-__device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i16* __restrict__ x, i8* q_md0, i8* q_md1, i16* r16, i32* rand_g) {
+SB_NSQ_KFN void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i16* __restrict__ x, i8* q_md0, i8* q_md1, i16* r16, i32* rand_g) {
     const int gl = threadIdx.x & (SB_NSQ_GW - 1);                 // gl inside the group
     const int gsh = (threadIdx.x & 31) & ~(SB_NSQ_GW - 1);         // first warp gl of the group
     const unsigned gm = SB_NSQ_GW == 32 ? 0xffffffffu : (0xffffu << gsh);
@@ -535,4 +543,4 @@ __device__ void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
 }
 
 }  // namespace sb
-#endif  // __CUDACC__
+#endif  // __CUDACC__ || SB_EMU

@@ -56,6 +56,28 @@ static void run32(const std::function<void()>& f) {
 #include "../../solo_b200/csrc/sb_dec.cuh"
 #ifdef SB_EMU
 #include "../../solo_b200/csrc/sb_coop.cuh"
+// ---- the quantiser kernel's device code (sb_nsq_warp.cuh) under the same 32-fibre emulation: one stream per "warp"
+//      (SB_NSQ_GW = 32), the CUDA warp intrinsics it uses as shims over the emulation's exchange buffer ----
+namespace {
+struct EmuThreadIdx { struct X { operator int() const { return sb::emu::lane; } } x; } threadIdx;
+template <class T> inline T __shfl_sync(unsigned, T v, int src, int w = 32) {
+    return (T)sb::wshfl64((sb::i64)v, (sb::emu::lane & ~(w - 1)) | (src & (w - 1)));
+}
+template <class T> inline T __shfl_down_sync(unsigned, T v, int d, int w = 32) {
+    const int l = sb::emu::lane;
+    return (T)sb::wshfl64((sb::i64)v, ((l & (w - 1)) + d < w) ? l + d : l);
+}
+inline unsigned __ballot_sync(unsigned, bool p) { return sb::wballot(p); }
+inline bool __any_sync(unsigned, bool p) { return sb::wballot(p) != 0; }
+inline int __reduce_max_sync(unsigned, int v) { return sb::wmax(v); }
+inline void __syncwarp(unsigned = 0xffffffffu) { sb::emu::barrier(); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __mulhi(int a, int b) { return (int)(((long long)a * (long long)b) >> 32); }
+}
+#define SB_NSQ_GW 32
+#include "../../solo_b200/csrc/sb_nsq_warp.cuh"
+static int g_emu_nsq = 0;
+extern "C" void hs_set_emu_nsq(int on) { g_emu_nsq = on; }
 #endif
 #include <stdlib.h>
 
@@ -89,6 +111,14 @@ int hs_enc_encode(void* p, const short* pcm, unsigned char* out, int cap, short*
             else sb::c_hb_analyse_frame<2 * sb::HB_FRAME>(&h->st, &hs, h->w.a.high + f * h->st.hb_frame, &h->w.scr.hb_lsp_idx[f], h->w.scr.hb_nrg0[f]);
         }
     });
+    if (g_emu_nsq) {      // the quantiser kernel: same device code, one stream per emulated warp
+        static sb::NsqSmem S;
+        for (int f = 0; f < nf; f++) {
+            sb::EncScratch* scr = &h->w.scr;
+            sb::emu::run32([=]() { sb::nsq_del_dec_warp(S, h->st.nsq, &scr->c[f], scr->xfw[f], scr->q_md[f][0], scr->q_md[f][1], scr->r16[f], &scr->nsq_rand[0][0][0]); });
+        }
+        return sb::enc_packet_finish(&h->st, &h->w.scr, h->w.rcbuf, out, cap, nb);
+    }
     return sb::enc_packet_quantise_and_code(&h->st, &h->w, out, cap, nb);
 #else
     return sb::enc_packet(&h->st, &h->w, pcm, out, cap, nb);

@@ -32,13 +32,18 @@ def lib(emu=None):
         L.hs_dec_create.argtypes = [C.c_int]
         L.hs_dec_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.hs_dec_destroy.argtypes = [C.c_void_p]
+        if emu:
+            L.hs_set_emu_nsq.argtypes = [C.c_int]
         _libs[emu] = L
     return _libs[emu]
 
 
 class SimEncoder:
-    def __init__(self, rate=13600, dtx=0, use_md_index=0, cap=1024, emu=None, framesize_ms=40, joint_hb=0):
+    def __init__(self, rate=13600, dtx=0, use_md_index=0, cap=1024, emu=None, framesize_ms=40, joint_hb=0, emu_nsq=False):
+        """emu_nsq (emu build only): the quantiser stage runs the device kernel's code (sb_nsq_warp.cuh) on emulated lanes too."""
         self.L = lib(emu)
+        self.emu_nsq = bool(emu_nsq)
+        assert not self.emu_nsq or self.L.hs_is_emu() == 1
         self.h = self.L.hs_enc_create3(rate, dtx, use_md_index, framesize_ms, joint_hb)
         self.samples = 16 * framesize_ms
         self.cap = cap
@@ -48,6 +53,8 @@ class SimEncoder:
     def encode(self, pcm640):
         x = np.ascontiguousarray(pcm640, np.int16)
         assert x.size == self.samples
+        if self.L.hs_is_emu() == 1:
+            self.L.hs_set_emu_nsq(1 if self.emu_nsq else 0)
         n = self.L.hs_enc_encode(self.h, x.ctypes.data, self.out.ctypes.data, self.cap, self.nb.ctypes.data)
         return bytes(self.out[:max(n, 0)]), (int(self.nb[0]), int(self.nb[1])), n
 

@@ -276,6 +276,32 @@ def test_cooperative_analysis_under_32_lane_emulation(sim):
         e0.close(); e1.close()
 
 
+def test_quantiser_kernel_code_under_32_lane_emulation(sim):
+    """The device code of the quantiser kernel (sb_nsq_warp.cuh: lane = (quantiser, decision state), shuffles for the joint
+    rate-distortion decisions, 64-bit path words, history tables, output ring and random-generator history outside the
+    shared-memory block) compiled for the host and run on 32 emulated lanes per stream behind the emulated analysis stage:
+    golden bitstream on the first 48 packets of the clip (both signal types, rewhitening, decision-window resets), and the
+    scalar model on the other input classes / modes / rates.  The GPU tests check the same code two streams per warp."""
+    g = load_golden()
+    clip = load_clip()
+    e = sim.SimEncoder(rate=13600, emu=True, emu_nsq=True)
+    for p in range(48):
+        b, nb, n = e.encode(clip[p * 640:(p + 1) * 640])
+        assert nb == tuple(g["fix_nbytes"][p]) and b[:n] == bytes(g["fix_bits"][p, :n]), p
+    e.close()
+    cases = [(name, x, dict(kw)) for name, x, kw in synth_inputs(clip) if name not in ("rate15600", "rate_default", "shift2", "dtx")]
+    cases += [("20ms", clip[320 * 30:], dict(framesize_ms=20)), ("joint1", clip[640 * 15:], dict(joint_hb=1))]
+    for name, x, kw in cases:
+        if "mdi" in kw:
+            kw["use_md_index"] = kw.pop("mdi")
+        e0, e1 = sim.SimEncoder(emu=False, **kw), sim.SimEncoder(emu=True, emu_nsq=True, **kw)
+        spp = e0.samples
+        first = 12 if name.startswith("rate") or name in ("clip4x", "mdi") else 0     # start inside the speech
+        for p in range(first, first + 6):
+            assert e0.encode(x[p * spp:(p + 1) * spp]) == e1.encode(x[p * spp:(p + 1) * spp]), (name, p)
+        e0.close(); e1.close()
+
+
 def test_fast_reciprocal_division_is_exact():
     """div_q29 (sb_common.cuh): (INT32_MAX >> 2) / d through a float reciprocal + one correction equals C integer division for
     every divisor the approximate-division helpers can produce (16384 <= |d| <= 32768) -- same float operations as the device."""
