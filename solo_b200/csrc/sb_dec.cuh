@@ -655,8 +655,9 @@ SB_FN void qmf_synth_f32(const float* x1, const float* x2, float* y, float* mem1
 }
 
 // ---- AGR_Bwe_decode_frame_FLP (AGR_BWE_decode_frame_FLP.c:41-130): one 20 ms high-band frame ------------------------
-// res_f: float copy of (residue >> 10) for this frame; hb4: the 4 coded bytes (ignored on loss).
-template <int SF> SB_FN void hb_decode_frame_t(DecState* st, const u8* hb4, float* OutHigh, const float* res_f, int lostflag) {
+// hb4: the 4 coded bytes (ignored on loss); res_Q10: low-band excitation of the frame (Q10), nullptr = all zero -- the
+// reference works on a float copy of (res >> 10), converted here where it is used.
+template <int SF> SB_FN void hb_decode_frame_t(DecState* st, const u8* hb4, float* OutHigh, const i32* res_Q10, int lostflag) {
     // SF = sub-frame length: 40, or 80 with joint_mode 1
     float QHB_LSP[HB_ORDER], QGain[4], HB_PredCoef[HB_ORDER], HB_LPCRes[2 * SUBFR];
     float sLPC[16 + 2 * SUBFR];
@@ -687,7 +688,10 @@ template <int SF> SB_FN void hb_decode_frame_t(DecState* st, const u8* hb4, floa
     for (int i = 0; i < 16; i++) sLPC[i] = st->hb_sLPC[i];
     float* p_out = OutHigh;
     for (int s = 0; s < 4; s++) {
-        for (int i = 0; i < SF; i++) HB_LPCRes[i] = (float)(-0.7 * (double)QGain[s] * (double)res_f[s * SF + i]);
+        for (int i = 0; i < SF; i++) {
+            const float res_f = res_Q10 ? (float)(res_Q10[s * SF + i] >> 10) : 0.0f;
+            HB_LPCRes[i] = (float)(-0.7 * (double)QGain[s] * (double)res_f);
+        }
         // AGR_Sate_LPC_synthesizer (AGR_BWE_LPC_synthesizer.c:29-52)
         for (int i = 0; i < SF; i++) {
             float LPC_pred = 0.0f;
@@ -706,9 +710,9 @@ template <int SF> SB_FN void hb_decode_frame_t(DecState* st, const u8* hb4, floa
     st->hb_first = 0;
 }
 
-SB_FN void hb_decode_frame(DecState* st, const u8* hb4, float* OutHigh, const float* res_f, int lostflag) {
-    if (st->hb_frame == HB_FRAME) hb_decode_frame_t<SUBFR>(st, hb4, OutHigh, res_f, lostflag);
-    else hb_decode_frame_t<2 * SUBFR>(st, hb4, OutHigh, res_f, lostflag);
+SB_FN void hb_decode_frame(DecState* st, const u8* hb4, float* OutHigh, const i32* res_Q10, int lostflag) {
+    if (st->hb_frame == HB_FRAME) hb_decode_frame_t<SUBFR>(st, hb4, OutHigh, res_Q10, lostflag);
+    else hb_decode_frame_t<2 * SUBFR>(st, hb4, OutHigh, res_Q10, lostflag);
 }
 
 // A payload outliving its packet.  The reference keeps the range decoders (with their own copy of the payload) in the
@@ -728,7 +732,6 @@ struct DecPacketWork {
     u8 pay[2][MAX_PAYLOAD + 8];
     alignas(16) i16 lowout[PACKET / 2];
     i32 res_Q10[PACKET / 2];
-    float res_f[PACKET / 2];
     alignas(16) float OutHigh[PACKET / 2];
     float OutLow[PACKET / 2], out[PACKET];     // only the scalar model (bands == nullptr) uses these two
 };
@@ -802,11 +805,12 @@ SB_FN i32 dec_packet(DecState* st, DecPacketWork* W, i16* vout, const u8* bits, 
     }
     const int hb_lost = (lostflag == 1 || lostflag == 2);
     for (int f = 0; f < nhb; f++) {
-        for (int i = 0; i < F; i++) W->res_f[i] = (float)(W->res_Q10[f * F + i] >> 10);
-        if (hb_lost) for (int i = 0; i < half; i++) W->res_Q10[i] = 0;  // App. A Q12: the memset wipes the rest of the packet
+        // App. A Q12: with the high band lost, the reference's memset after the first high-band frame wipes the excitation
+        // of the rest of the packet -- later frames are synthesised from zeros
+        const i32* res = (hb_lost && f > 0) ? nullptr : W->res_Q10 + f * F;
         u8 hb4[4] = {0, 0, 0, 0};
         if (!hb_lost) for (int i = 0; i < 4; i++) hb4[i] = bits[hb_off + 4 * f + i];
-        hb_decode_frame(st, hb4, W->OutHigh + f * F, W->res_f, lostflag);
+        hb_decode_frame(st, hb4, W->OutHigh + f * F, res, lostflag);
     }
     if (bands) {      // device pipeline: the 64-tap synthesis filter bank has no recurrence and runs as its own kernel
 #ifdef __CUDA_ARCH__
