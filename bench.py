@@ -454,7 +454,7 @@ def main():
             "data": "synthetic (speech-replay of the codec's 16 kHz test clip, SURVEY 8(d)(i); fresh codec state)",
             "config": {"workload": "configs[2]: batch=65536 streams/GPU full encode+decode round trip (lostflag 4), 13.6 kb/s",
                        "arithmetic": "int32/int16 fixed point (encoder, SILK decoder), f32 (decoder high band + QMF synthesis)",
-                       "streams_per_gpu": N, "streams_total": world * N, "pipeline_chunks": os.environ.get("SOLO_B200_CHUNKS", "default: 1 (device entry points), 2 (host entry points)"), "payload_cap": CAP, "mean_payload_bytes": mean_payload,
+                       "streams_per_gpu": N, "streams_total": world * N, "pipeline_chunks": os.environ.get("SOLO_B200_CHUNKS", "default: 1 (device entry points), 3 (host entry points)"), "payload_cap": CAP, "mean_payload_bytes": mean_payload,
                        "l2": "no flush: every step reads a new 84 MB PCM wave and ~0.9 GB of per-stream state (> 126 MB L2)",
                        "parallelism": "streams sharded contiguously across GPUs, no collective on the data path",
                        "host_binding": numa},

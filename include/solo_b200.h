@@ -101,7 +101,7 @@ long long solo_b200_kernel_launches(void);
 void solo_b200_profile_enable(int on);
 int solo_b200_profile_read(double ms_total[4], long long launches[4]);
 /* A packet wave can be processed as `chunks` groups of streams on internal CUDA streams so that the copies of one group
-   overlap the kernels of another.  Default (0, or env SOLO_B200_CHUNKS unset): 2 for the *_host entry points, 1 (one launch
+   overlap the kernels of another.  Default (0, or env SOLO_B200_CHUNKS unset): 3 for the *_host entry points, 1 (one launch
    per kernel on the caller's stream) for the *_device entry points.  Results do not depend on it. */
 void solo_b200_set_chunks(int chunks);
 const char *solo_b200_last_error(void);

@@ -356,9 +356,9 @@ struct Pipe {
     bool ok;
 };
 static int g_chunks = -1;   // -1: SOLO_B200_CHUNKS or the defaults below
-// Default: the host entry points cut a wave in two (the copies of one chunk hide behind the kernels of the other); the device
-// entry points launch every kernel once for the whole batch (the thread-per-stream kernels need all the streams they can get
-// to fill 148 SMs, and the warp-per-stream kernels fill the GPU on their own: measured 25.9 vs 26.3 ms per 65 536-stream wave).
+// Default: the host entry points cut a wave in three (the copies of one chunk hide behind the kernels of its neighbours:
+// 26.8 ms per 65 536-stream wave end to end, against 27.2 with two chunks, 27.0 with four, 28.0 with six); the device entry
+// points launch every kernel once for the whole batch.
 static int pipe_chunks(int n, bool host_copies) {
     if (g_chunks < 0) {
         const char* e = getenv("SOLO_B200_CHUNKS");
@@ -366,7 +366,7 @@ static int pipe_chunks(int n, bool host_copies) {
         if (g_chunks < 0) g_chunks = 0;
         if (g_chunks > 64) g_chunks = 64;
     }
-    int c = g_chunks ? g_chunks : (host_copies ? 2 : 1);
+    int c = g_chunks ? g_chunks : (host_copies ? 3 : 1);
     while (c > 1 && n / c < 2048) c--;   // small batches: fewer, larger chunks
     return c;
 }
