@@ -347,8 +347,8 @@ def main():
     host_pcm = torch.from_numpy(speech_replay(clip, sids, T)).pin_memory()      # [T, N, 640] int16
     d_pcm = host_pcm.to(dev, non_blocking=True)
     # Encoder wave then decoder wave on one CUDA stream.  (Running the two batch objects on separate streams so that
-    # decode(t) overlaps encode(t+1) was measured and is slower: all four kernels are latency-bound at a fixed number of
-    # resident warps and slow each other down when co-resident -- DESIGN.md section 6.)
+    # decode(t) overlaps encode(t+1) gains nothing -- tools/overlap_check.py, 25.6 vs 25.8 ms: a later grid's blocks are only
+    # placed once the earlier grid has none left, so the kernels overlap at their tails -- DESIGN.md section 6.)
     d_bits = torch.zeros((N, CAP), dtype=torch.uint8, device=dev)
     d_nb = torch.zeros((N, 2), dtype=torch.int16, device=dev)
     d_flags = torch.full((N,), 4, dtype=torch.int32, device=dev)
