@@ -10,7 +10,10 @@ SRC = os.path.join(HERE, "hostsim.cpp")
 
 
 def build(force=False, emu=False):
-    """emu=True: the cooperative (32 threads per stream) build of the analysis stage, libsb_hostsim_emu.so."""
+    """emu=True: the cooperative (32 threads per stream) build of the analysis stage, libsb_hostsim_emu.so;
+    emu="gw16": the same with the quantiser code in its two-lane-groups-per-warp packing, libsb_hostsim_emu16.so."""
+    if emu == "gw16":
+        return _build(os.path.join(OUT_DIR, "libsb_hostsim_emu16.so"), ["-DSB_EMU", "-DSB_EMU_GW16"], force)
     if emu:
         return _build(os.path.join(OUT_DIR, "libsb_hostsim_emu.so"), ["-DSB_EMU"], force)
     return _build(OUT, [], force)

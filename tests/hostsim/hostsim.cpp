@@ -74,7 +74,11 @@ inline void __syncwarp(unsigned = 0xffffffffu) { sb::emu::barrier(); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __mulhi(int a, int b) { return (int)(((long long)a * (long long)b) >> 32); }
 }
+#ifdef SB_EMU_GW16
+#define SB_NSQ_GW 16     // the kernel's packing: two lane groups per warp; here the second group shadows the first one's stream
+#else                    // (what the kernel does with the last stream of an odd batch), so both take the same path
 #define SB_NSQ_GW 32
+#endif
 #include "../../solo_b200/csrc/sb_nsq_warp.cuh"
 static int g_emu_nsq = 0;
 extern "C" void hs_set_emu_nsq(int on) { g_emu_nsq = on; }
@@ -112,10 +116,10 @@ int hs_enc_encode(void* p, const short* pcm, unsigned char* out, int cap, short*
         }
     });
     if (g_emu_nsq) {      // the quantiser kernel: same device code, one stream per emulated warp
-        static sb::NsqSmem S;
+        static sb::NsqSmem S[2];
         for (int f = 0; f < nf; f++) {
             sb::EncScratch* scr = &h->w.scr;
-            sb::emu::run32([=]() { sb::nsq_del_dec_warp(S, h->st.nsq, &scr->c[f], scr->xfw[f], scr->q_md[f][0], scr->q_md[f][1], scr->r16[f], &scr->nsq_rand[0][0][0]); });
+            sb::emu::run32([=]() { sb::nsq_del_dec_warp(S[sb::emu::lane / SB_NSQ_GW], h->st.nsq, &scr->c[f], scr->xfw[f], scr->q_md[f][0], scr->q_md[f][1], scr->r16[f], &scr->nsq_rand[0][0][0]); });
         }
         return sb::enc_packet_finish(&h->st, &h->w.scr, h->w.rcbuf, out, cap, nb);
     }

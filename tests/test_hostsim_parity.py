@@ -281,7 +281,8 @@ def test_quantiser_kernel_code_under_32_lane_emulation(sim):
     rate-distortion decisions, 64-bit path words, history tables, output ring and random-generator history outside the
     shared-memory block) compiled for the host and run on 32 emulated lanes per stream behind the emulated analysis stage:
     golden bitstream on the first 48 packets of the clip (both signal types, rewhitening, decision-window resets), and the
-    scalar model on the other input classes / modes / rates.  The GPU tests check the same code two streams per warp."""
+    scalar model on the other input classes / modes / rates; then the kernel's two-streams-per-warp packing (two lane groups,
+    the second shadowing the first one's stream) on the golden bitstream again.  The GPU tests run two different streams per warp."""
     g = load_golden()
     clip = load_clip()
     e = sim.SimEncoder(rate=13600, emu=True, emu_nsq=True)
@@ -300,6 +301,13 @@ def test_quantiser_kernel_code_under_32_lane_emulation(sim):
         for p in range(first, first + 6):
             assert e0.encode(x[p * spp:(p + 1) * spp]) == e1.encode(x[p * spp:(p + 1) * spp]), (name, p)
         e0.close(); e1.close()
+    # the kernel's packing -- two 16-lane groups per warp, group masks, segmented shuffles, ballot halves -- with the second
+    # group shadowing the first one's stream, which is what the kernel does with the last stream of an odd batch
+    e = sim.SimEncoder(rate=13600, emu="gw16", emu_nsq=True)
+    for p in range(32):
+        b, nb, n = e.encode(clip[p * 640:(p + 1) * 640])
+        assert nb == tuple(g["fix_nbytes"][p]) and b[:n] == bytes(g["fix_bits"][p, :n]), ("gw16", p)
+    e.close()
 
 
 def test_fast_reciprocal_division_is_exact():
