@@ -50,6 +50,58 @@ static void run32(const std::function<void()>& f) {
         if (nbar[i] != nbar[0]) { fprintf(stderr, "emu: lane %d took %ld barriers, lane 0 took %ld (divergent collective)\n", i, nbar[i], nbar[0]); abort(); }
     lane = 0;
 }
+
+// ---- a second scheduler for code whose collectives name a lane mask (the quantiser kernel: two 16-lane groups that may take
+//      different paths between the full-warp sections).  barrier_mask(m) really waits: a lane spins (yielding round-robin to
+//      the other lanes) until every lane of m has arrived at a barrier with the same mask.  Lanes finish at different times. ----
+static bool done_[32];
+static struct MaskBar { unsigned mask, arrived; unsigned long phase; } mbar[8];
+static int n_mbar;
+static long spins;
+static void yield_next() {
+    const int me = lane;
+    for (int k = 1; k <= 32; k++) {
+        const int nx = (me + k) & 31;
+        if (!done_[nx]) { if (nx == me) return; lane = nx; swapcontext(&ctx[me], &ctx[nx]); lane = me; return; }
+    }
+}
+void barrier_mask(unsigned m) {
+    const int me = lane;
+    MaskBar* e = nullptr;
+    for (int i = 0; i < n_mbar; i++) if (mbar[i].mask == m) e = &mbar[i];
+    if (!e) { if (n_mbar == 8) { fprintf(stderr, "emu: too many distinct lane masks\n"); abort(); } e = &mbar[n_mbar++]; e->mask = m; e->arrived = 0; e->phase = 0; }
+    if (!((m >> me) & 1)) { fprintf(stderr, "emu: lane %d at a barrier whose mask %08x does not name it\n", me, m); abort(); }
+    const unsigned long my_phase = e->phase;
+    e->arrived |= 1u << me;
+    if (e->arrived == m) { e->arrived = 0; e->phase++; spins = 0; }
+    while (e->phase == my_phase) {
+        if (++spins > 100000000L) { fprintf(stderr, "emu: deadlock -- lanes %08x of mask %08x never arrived (divergent collective)\n", m & ~e->arrived, m); abort(); }
+        yield_next();
+    }
+}
+static void entry_m() {
+    body();
+    const int me = lane;
+    done_[me] = true;
+    for (int k = 1; k < 32; k++) { const int nx = (me + k) & 31; if (!done_[nx]) { lane = nx; setcontext(&ctx[nx]); } }
+    setcontext(&main_ctx);
+}
+static void run32m(const std::function<void()>& f) {
+    body = f;
+    n_mbar = 0; spins = 0;
+    for (int i = 0; i < 32; i++) {
+        if (!stacks[i]) stacks[i] = (char*)malloc(1 << 20);
+        getcontext(&ctx[i]);
+        ctx[i].uc_stack.ss_sp = stacks[i];
+        ctx[i].uc_stack.ss_size = 1 << 20;
+        ctx[i].uc_link = &main_ctx;
+        makecontext(&ctx[i], (void (*)())entry_m, 0);
+        done_[i] = false;
+    }
+    lane = 0;
+    swapcontext(&main_ctx, &ctx[0]);
+    lane = 0;
+}
 } }
 #endif
 #include "../../solo_b200/csrc/sb_enc.cuh"
@@ -60,17 +112,37 @@ static void run32(const std::function<void()>& f) {
 //      (SB_NSQ_GW = 32), the CUDA warp intrinsics it uses as shims over the emulation's exchange buffer ----
 namespace {
 struct EmuThreadIdx { struct X { operator int() const { return sb::emu::lane; } } x; } threadIdx;
-template <class T> inline T __shfl_sync(unsigned, T v, int src, int w = 32) {
-    return (T)sb::wshfl64((sb::i64)v, (sb::emu::lane & ~(w - 1)) | (src & (w - 1)));
+static long long xbuf[32];     // exchange line of the shims (one slot per lane)
+template <class T> inline T emu_xchg(unsigned m, T v, int src) {
+    xbuf[sb::emu::lane] = (long long)v;
+    sb::emu::barrier_mask(m);
+    const T r = (T)xbuf[src & 31];
+    sb::emu::barrier_mask(m);
+    return r;
 }
-template <class T> inline T __shfl_down_sync(unsigned, T v, int d, int w = 32) {
+template <class T> inline T __shfl_sync(unsigned m, T v, int src, int w = 32) { return emu_xchg<T>(m, v, (sb::emu::lane & ~(w - 1)) | (src & (w - 1))); }
+template <class T> inline T __shfl_down_sync(unsigned m, T v, int d, int w = 32) {
     const int l = sb::emu::lane;
-    return (T)sb::wshfl64((sb::i64)v, ((l & (w - 1)) + d < w) ? l + d : l);
+    return emu_xchg<T>(m, v, ((l & (w - 1)) + d < w) ? l + d : l);
 }
-inline unsigned __ballot_sync(unsigned, bool p) { return sb::wballot(p); }
-inline bool __any_sync(unsigned, bool p) { return sb::wballot(p) != 0; }
-inline int __reduce_max_sync(unsigned, int v) { return sb::wmax(v); }
-inline void __syncwarp(unsigned = 0xffffffffu) { sb::emu::barrier(); }
+inline unsigned __ballot_sync(unsigned m, bool p) {
+    xbuf[sb::emu::lane] = p ? 1 : 0;
+    sb::emu::barrier_mask(m);
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) if ((m >> i) & 1) r |= (unsigned)xbuf[i] << i;
+    sb::emu::barrier_mask(m);
+    return r;
+}
+inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
+inline int __reduce_max_sync(unsigned m, int v) {
+    xbuf[sb::emu::lane] = v;
+    sb::emu::barrier_mask(m);
+    int r = v;
+    for (int i = 0; i < 32; i++) if (((m >> i) & 1) && (int)xbuf[i] > r) r = (int)xbuf[i];
+    sb::emu::barrier_mask(m);
+    return r;
+}
+inline void __syncwarp(unsigned m = 0xffffffffu) { sb::emu::barrier_mask(m); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __mulhi(int a, int b) { return (int)(((long long)a * (long long)b) >> 32); }
 }
@@ -95,10 +167,10 @@ void* hs_enc_create3(int rate, int dtx, int mdi, int framesize_ms, int joint_hb)
 }
 void* hs_enc_create2(int rate, int dtx, int mdi, int framesize_ms) { return hs_enc_create3(rate, dtx, mdi, framesize_ms, 0); }
 void* hs_enc_create(int rate, int dtx, int mdi) { return hs_enc_create2(rate, dtx, mdi, 40); }
-int hs_enc_encode(void* p, const short* pcm, unsigned char* out, int cap, short* nb) {
-    HsEnc* h = (HsEnc*)p;
 #ifdef SB_EMU
-    // device pipeline: band split (kernel A0), core analysis (kernel A, cooperative), high-band analysis
+// the device pipeline up to the quantiser: band split (kernel A0), VAD, core analysis (cooperative), the thread-per-stream
+// kernels behind it, high-band analysis (cooperative)
+static void emu_front(HsEnc* h, const short* pcm) {
     static sb::CoopWork cw;
     const int nf = h->st.frames_per_packet;
     sb::qmf_decomp(pcm, h->w.a.low, h->w.a.high, h->st.qmf_mem, nf * 2 * sb::FRAME);
@@ -115,17 +187,49 @@ int hs_enc_encode(void* p, const short* pcm, unsigned char* out, int cap, short*
             else sb::c_hb_analyse_frame<2 * sb::HB_FRAME>(&h->st, &hs, h->w.a.high + f * h->st.hb_frame, &h->w.scr.hb_lsp_idx[f], h->w.scr.hb_nrg0[f]);
         }
     });
-    if (g_emu_nsq) {      // the quantiser kernel: same device code, one stream per emulated warp
-        static sb::NsqSmem S[2];
-        for (int f = 0; f < nf; f++) {
+}
+// the quantiser kernel's code for one warp: lane group g works on stream hh[g] (one group with SB_NSQ_GW = 32)
+static void emu_nsq(HsEnc* const* hh) {
+    static sb::NsqSmem S[2];
+    const int nf = hh[0]->st.frames_per_packet;
+    for (int f = 0; f < nf; f++)
+        sb::emu::run32m([=]() {
+            const int g = sb::emu::lane / SB_NSQ_GW;
+            HsEnc* h = hh[g];
             sb::EncScratch* scr = &h->w.scr;
-            sb::emu::run32([=]() { sb::nsq_del_dec_warp(S[sb::emu::lane / SB_NSQ_GW], h->st.nsq, &scr->c[f], scr->xfw[f], scr->q_md[f][0], scr->q_md[f][1], scr->r16[f], &scr->nsq_rand[0][0][0]); });
-        }
+            sb::nsq_del_dec_warp(S[g], h->st.nsq, &scr->c[f], scr->xfw[f], scr->q_md[f][0], scr->q_md[f][1], scr->r16[f], &scr->nsq_rand[0][0][0]);
+        });
+}
+#endif
+int hs_enc_encode(void* p, const short* pcm, unsigned char* out, int cap, short* nb) {
+    HsEnc* h = (HsEnc*)p;
+#ifdef SB_EMU
+    emu_front(h, pcm);
+    if (g_emu_nsq) {      // second lane group (SB_NSQ_GW = 16): shadows the same stream, as the kernel does for an odd batch
+        HsEnc* hh[2] = {h, h};
+        emu_nsq(hh);
         return sb::enc_packet_finish(&h->st, &h->w.scr, h->w.rcbuf, out, cap, nb);
     }
     return sb::enc_packet_quantise_and_code(&h->st, &h->w, out, cap, nb);
 #else
     return sb::enc_packet(&h->st, &h->w, pcm, out, cap, nb);
+#endif
+}
+// two DIFFERENT streams through one emulated quantiser warp (SB_NSQ_GW = 16 build): the lane groups take their own paths
+// between the full-warp sample loops.  Both encoders must have the same packet length.  ret[g] = bytes of stream g.
+int hs_enc_encode_pair(void* pa, void* pb, const short* pcm_a, const short* pcm_b, unsigned char* out_a, unsigned char* out_b, int cap,
+                       short* nb_a, short* nb_b, int* ret) {
+#if defined(SB_EMU) && defined(SB_EMU_GW16)
+    HsEnc* hh[2] = {(HsEnc*)pa, (HsEnc*)pb};
+    if (hh[0]->st.frames_per_packet != hh[1]->st.frames_per_packet) return -1;
+    emu_front(hh[0], pcm_a);
+    emu_front(hh[1], pcm_b);
+    emu_nsq(hh);
+    ret[0] = sb::enc_packet_finish(&hh[0]->st, &hh[0]->w.scr, hh[0]->w.rcbuf, out_a, cap, nb_a);
+    ret[1] = sb::enc_packet_finish(&hh[1]->st, &hh[1]->w.scr, hh[1]->w.rcbuf, out_b, cap, nb_b);
+    return 0;
+#else
+    return -1;
 #endif
 }
 void hs_enc_destroy(void* p) { free(p); }

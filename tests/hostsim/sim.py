@@ -34,6 +34,7 @@ def lib(emu=None):
         L.hs_dec_destroy.argtypes = [C.c_void_p]
         if emu:
             L.hs_set_emu_nsq.argtypes = [C.c_int]
+            L.hs_enc_encode_pair.argtypes = [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 3
         _libs[emu] = L
     return _libs[emu]
 
@@ -62,6 +63,17 @@ class SimEncoder:
         if self.h:
             self.L.hs_enc_destroy(self.h)
             self.h = None
+
+
+def encode_pair(ea, eb, pcm_a, pcm_b):
+    """Two encoders of the emu="gw16" build through ONE emulated quantiser warp (a lane group each).  Returns the two
+    (payload, (n0, n1), n) results."""
+    xa, xb = np.ascontiguousarray(pcm_a, np.int16), np.ascontiguousarray(pcm_b, np.int16)
+    ret = np.zeros(2, np.int32)
+    r = ea.L.hs_enc_encode_pair(ea.h, eb.h, xa.ctypes.data, xb.ctypes.data, ea.out.ctypes.data, eb.out.ctypes.data, ea.cap,
+                                ea.nb.ctypes.data, eb.nb.ctypes.data, ret.ctypes.data)
+    assert r == 0
+    return tuple((bytes(e.out[:max(int(n), 0)]), (int(e.nb[0]), int(e.nb[1])), int(n)) for e, n in ((ea, ret[0]), (eb, ret[1])))
 
 
 class SimDecoder:

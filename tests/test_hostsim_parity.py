@@ -281,8 +281,8 @@ def test_quantiser_kernel_code_under_32_lane_emulation(sim):
     rate-distortion decisions, 64-bit path words, history tables, output ring and random-generator history outside the
     shared-memory block) compiled for the host and run on 32 emulated lanes per stream behind the emulated analysis stage:
     golden bitstream on the first 48 packets of the clip (both signal types, rewhitening, decision-window resets), and the
-    scalar model on the other input classes / modes / rates; then the kernel's two-streams-per-warp packing (two lane groups,
-    the second shadowing the first one's stream) on the golden bitstream again.  The GPU tests run two different streams per warp."""
+    scalar model on the other input classes / modes / rates; then the kernel's two-streams-per-warp packing: the second lane group
+    shadowing the first one's stream, and two different streams (speech beside noise / silence / a sine / other speech)."""
     g = load_golden()
     clip = load_clip()
     e = sim.SimEncoder(rate=13600, emu=True, emu_nsq=True)
@@ -301,13 +301,31 @@ def test_quantiser_kernel_code_under_32_lane_emulation(sim):
         for p in range(first, first + 6):
             assert e0.encode(x[p * spp:(p + 1) * spp]) == e1.encode(x[p * spp:(p + 1) * spp]), (name, p)
         e0.close(); e1.close()
-    # the kernel's packing -- two 16-lane groups per warp, group masks, segmented shuffles, ballot halves -- with the second
-    # group shadowing the first one's stream, which is what the kernel does with the last stream of an odd batch
+    # the kernel's packing -- two 16-lane groups per warp, group masks, segmented shuffles, ballot halves.  (a) the second
+    # group shadows the first one's stream, which is what the kernel does with the last stream of an odd batch;
     e = sim.SimEncoder(rate=13600, emu="gw16", emu_nsq=True)
-    for p in range(32):
+    for p in range(16):
         b, nb, n = e.encode(clip[p * 640:(p + 1) * 640])
         assert nb == tuple(g["fix_nbytes"][p]) and b[:n] == bytes(g["fix_bits"][p, :n]), ("gw16", p)
     e.close()
+    # (b) two DIFFERENT streams in one warp: the groups go their own ways between the full-warp sample loops (rewhitening of
+    # voiced frames, decision-window flushes, rescaling), every collective names its lanes, and the emulation's barriers wait
+    # for exactly those
+    rng = np.random.Generator(np.random.PCG64(3))
+    t = np.arange(640 * 12)
+    others = {"noise3000": np.clip(rng.normal(0, 3000, 640 * 12), -32768, 32767).astype(np.int16),
+              "zeros": np.zeros(640 * 12, np.int16),
+              "sine200": (8000 * np.sin(2 * np.pi * 200 * t / 16000)).astype(np.int16),
+              "speech_later": clip[640 * 60:640 * 72]}
+    for name, xo in others.items():
+        ea, eb = sim.SimEncoder(emu="gw16"), sim.SimEncoder(emu="gw16")
+        ra, rb = sim.SimEncoder(emu=False), sim.SimEncoder(emu=False)
+        for p in range(8):
+            xa, xb = clip[(p + 14) * 640:(p + 15) * 640], xo[p * 640:(p + 1) * 640]
+            a, b = sim.encode_pair(ea, eb, xa, xb)
+            assert a == ra.encode(xa) and b == rb.encode(xb), (name, p)
+        for o in (ea, eb, ra, rb):
+            o.close()
 
 
 def test_fast_reciprocal_division_is_exact():
