@@ -416,21 +416,28 @@ SB_NSQ_KFN void nsq_del_dec_warp(NsqSmem& S, NsqState* ns3, EncCtrl* c, const i1
 #pragma unroll
                 for (int m = 1; m < 4; m++) { const bool t = j0[m] < RDmin; RDmin = t ? j0[m] : RDmin; W0 = t ? m : W0; }
                 const i32 wrs = shfl(fm, rs, qz * 4 + W0);
-                const unsigned bal = (__ballot_sync(fm, act && rs != wrs) >> gsh) & 0xffffu;
-                const unsigned mstate = (bal | (bal >> 4) | (bal >> 8)) & 0xF;
-                int RandSyncCtl = __popc(mstate);
-                const i32 PEN = SB_I32_MAX >> 4;
+                // De-synchronised random generators (a state whose delayed sample saw another dither sequence than the
+                // winner's) are rare -- under 2 % of the samples on speech: the penalties and the extra replacement trips sit
+                // behind a warp-uniform test of the ballot.
+                const unsigned bal_all = __ballot_sync(fm, act && rs != wrs);
+                int my_trips = 1, trips = 1;
+                if (bal_all != 0) {
+                    const unsigned bal = (bal_all >> gsh) & 0xffffu;
+                    const unsigned mstate = (bal | (bal >> 4) | (bal >> 8)) & 0xF;
+                    const int RandSyncCtl = __popc(mstate);
+                    const i32 PEN = SB_I32_MAX >> 4;
 #pragma unroll
-                for (int m = 0; m < 4; m++) {
-                    const i32 pen = ((mstate >> m) & 1) ? PEN : 0;
-                    j0[m] = addw(j0[m], pen); j1[m] = addw(j1[m], pen); ra[m] = addw(ra[m], pen); rb[m] = addw(rb[m], pen);
+                    for (int m = 0; m < 4; m++) {
+                        const i32 pen = ((mstate >> m) & 1) ? PEN : 0;
+                        j0[m] = addw(j0[m], pen); j1[m] = addw(j1[m], pen); ra[m] = addw(ra[m], pen); rb[m] = addw(rb[m], pen);
+                    }
+                    { const i32 pen = ((qz == 0) & ((mstate >> s) & 1)) ? PEN : 0; c0.RD = addw(c0.RD, pen); c1.RD = addw(c1.RD, pen); }
+                    // The reference repeats the replacement once per de-synchronised state (at least once).  Both streams of
+                    // the warp run the same number of trips (the larger of the two) so that the shuffles below stay
+                    // warp-uniform; a stream that is done (or finds nothing to replace) shuffles every lane onto itself.
+                    my_trips = RandSyncCtl > 1 ? RandSyncCtl : 1;
+                    trips = __reduce_max_sync(fm, my_trips);
                 }
-                { const i32 pen = ((qz == 0) & ((mstate >> s) & 1)) ? PEN : 0; c0.RD = addw(c0.RD, pen); c1.RD = addw(c1.RD, pen); }
-                // The reference repeats the replacement once per de-synchronised state (at least once).  Both streams of
-                // the warp run the same number of trips (the larger of the two) so that the shuffles below stay warp-uniform;
-                // a stream that is done (or finds nothing to replace) shuffles every lane onto itself.
-                const int my_trips = RandSyncCtl > 1 ? RandSyncCtl : 1;
-                const int trips = __reduce_max_sync(fm, my_trips);
                 for (int it = 0; it < trips; it++) {
                     i32 RDmax = ra[0], RDmin2 = rb[0], j1n = j1[0]; int imx = 0, imn = 0;
 #pragma unroll
